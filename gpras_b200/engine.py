@@ -1,0 +1,152 @@
+"""Thin object wrapper over the exact-GP handle of the C ABI (``include/gpras_b200.h``).
+
+``ExactGP`` owns one ``gpras_gp`` handle: one GPU, one stream, one (N, D, P) problem with a single
+hyperparameter set shared by all P target columns.  It replaces, for the exact (``Z == X``) model,
+what the reference obtains from ``gpflow.models.SGPR`` at ``gpras/gpr.py:293-308``:
+``training_loss`` + gradient (``lml_grad``) and ``predict_y`` (``condition`` + ``predict``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KERNEL_IDS, check, ptr
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class ExactGP:
+    def __init__(self, kernel: str, n: int, d: int, p: int, device: int = 0):
+        self.lib = _lib.load()
+        if self.lib.gpras_device_count() <= 0:
+            raise _lib.GprasError("no CUDA device visible: gpras_b200 has no CPU fallback")
+        self.kernel, self.n, self.d, self.p, self.device = kernel, int(n), int(d), int(p), int(device)
+        h = C.c_void_p()
+        check(self.lib.gpras_gp_create(C.byref(h), device, KERNEL_IDS[kernel], self.n, self.d, self.p))
+        self._h = h
+        self._keep = []
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.gpras_gp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data -----------------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int | None) -> None:
+        check(self.lib.gpras_gp_set_stream(self._h, cuda_stream or None))
+
+    def set_data(self, x, y) -> None:
+        """x (N, D), y (N, P): numpy (host) arrays or CUDA float64 torch tensors."""
+        on_device = not isinstance(x, np.ndarray) and hasattr(x, "data_ptr")
+        if not on_device:
+            x, y = _f64(x), _f64(y)
+        if tuple(x.shape) != (self.n, self.d) or tuple(y.shape) != (self.n, self.p):
+            raise ValueError(f"expected x {(self.n, self.d)} and y {(self.n, self.p)}, got {tuple(x.shape)}, {tuple(y.shape)}")
+        self._keep = [x, y]
+        check(self.lib.gpras_gp_set_data(self._h, ptr(x), ptr(y), int(on_device)))
+
+    def theta_vector(self, variance: float, noise: float, lengthscales) -> np.ndarray:
+        ls = np.asarray(lengthscales, np.float64).reshape(-1)
+        if ls.size == 1:
+            ls = np.full(self.d, ls[0])
+        if ls.size != self.d:
+            raise ValueError(f"{ls.size} lengthscales for {self.d} features")
+        return np.concatenate([[float(variance), float(noise)], ls])
+
+    # ---- objective --------------------------------------------------------------------------
+    def lml_grad(self, theta, want_grad: bool = True):
+        """(LML, d LML / d log theta [2 + D]) at theta = [variance, noise, l_0..l_{D-1}]."""
+        theta = _f64(theta)
+        lml = C.c_double()
+        grad = np.empty(2 + self.d) if want_grad else None
+        check(self.lib.gpras_gp_lml_grad(self._h, ptr(theta), C.byref(lml), ptr(grad) if want_grad else None))
+        return lml.value, grad
+
+    def lml_grad_host(self, x, y, theta):
+        """End-to-end call from host buffers (uploads x, y, theta; returns host scalars)."""
+        x, y, theta = _f64(x), _f64(y), _f64(theta)
+        lml = C.c_double()
+        grad = np.empty(2 + self.d)
+        check(self.lib.gpras_gp_lml_grad_host(self._h, ptr(x), ptr(y), ptr(theta), C.byref(lml), ptr(grad)))
+        return lml.value, grad
+
+    def enqueue(self, theta, want_grad: bool = True) -> None:
+        theta = _f64(theta)
+        check(self.lib.gpras_gp_lml_grad_enqueue(self._h, ptr(theta), int(want_grad)))
+
+    def fetch(self):
+        lml = C.c_double()
+        grad = np.empty(2 + self.d)
+        check(self.lib.gpras_gp_lml_grad_fetch(self._h, C.byref(lml), ptr(grad)))
+        return lml.value, grad
+
+    # ---- prediction -------------------------------------------------------------------------
+    def condition(self, theta) -> None:
+        theta = _f64(theta)
+        check(self.lib.gpras_gp_condition(self._h, ptr(theta)))
+
+    def predict(self, xs):
+        """(mean (T, P), var (T, P)) with likelihood noise included (``predict_y``)."""
+        xs = _f64(xs)
+        if xs.ndim != 2 or xs.shape[1] != self.d:
+            raise ValueError(f"expected (T, {self.d}) test inputs, got {xs.shape}")
+        t = xs.shape[0]
+        mean = np.empty((t, self.p))
+        var = np.empty((t, self.p))
+        check(self.lib.gpras_gp_predict(self._h, ptr(xs), t, ptr(mean), ptr(var), 0))
+        return mean, var
+
+    def set_cell_map(self, e_mean, bias) -> None:
+        e_mean, bias = _f64(e_mean), _f64(bias)
+        if e_mean.shape != (self.p, bias.shape[0]):
+            raise ValueError("e_mean must be (P, C) and bias (C,)")
+        check(self.lib.gpras_gp_set_cell_map(self._h, ptr(e_mean), ptr(bias), bias.shape[0]))
+
+    def cell_pitch(self) -> int:
+        return int(self.lib.gpras_gp_cell_pitch(self._h))
+
+    def predict_cells(self, xs, cell_mean=None, cell_var=None, want_modes: bool = True):
+        """Predict and expand to mesh cells on the device.  ``cell_mean`` / ``cell_var`` are CUDA float64
+        torch tensors of shape (T, cell_pitch()) or None (tiles go to an internal ring buffer)."""
+        on_device = not isinstance(xs, np.ndarray) and hasattr(xs, "data_ptr")
+        if not on_device:
+            xs = _f64(xs)
+        t = int(xs.shape[0])
+        mm = np.empty((t, self.p)) if want_modes else None
+        mv = np.empty((t, self.p)) if want_modes else None
+        ldc = int(cell_mean.shape[1]) if cell_mean is not None else (int(cell_var.shape[1]) if cell_var is not None else 0)
+        check(
+            self.lib.gpras_gp_predict_cells(
+                self._h, ptr(xs), t, int(on_device), ptr(mm) if want_modes else None, ptr(mv) if want_modes else None,
+                ptr(cell_mean) if cell_mean is not None else None, ptr(cell_var) if cell_var is not None else None, ldc,
+            )
+        )
+        return mm, mv
+
+    # ---- introspection ----------------------------------------------------------------------
+    def get_matrix(self, which: int) -> np.ndarray:
+        out = np.empty((self.n, self.p if which == 4 else self.n))
+        check(self.lib.gpras_gp_get_matrix(self._h, which, ptr(out)))
+        return out
+
+    def last_launches(self) -> int:
+        return int(self.lib.gpras_gp_last_launches(self._h))
+
+    def set_stage_timing(self, enabled: bool) -> None:
+        check(self.lib.gpras_gp_set_stage_timing(self._h, int(enabled)))
+
+    def last_stage_ms(self) -> dict:
+        ms = np.zeros(7)
+        check(self.lib.gpras_gp_last_stage_ms(self._h, ptr(ms)))
+        return dict(zip(["cov", "potrf", "trtri", "lauum", "alpha", "grad", "total"], ms.tolist()))

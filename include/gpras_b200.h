@@ -1,0 +1,107 @@
+/* gpras_b200 -- C ABI of the B200-native Gaussian-process-regression hot path.
+ *
+ * Drop-in boundary for the numerical work that fema-ffrd/gpras delegates to GPflow/TensorFlow from
+ * gpras/gpr.py (the reference has no FFI of its own; its boundary is the Python class
+ * gpras.gpr.GPRAS, gpr.py:217-384).  Each entry point below names the reference call it replaces.
+ * The Python mirror gpras_b200/gpr.py binds these with ctypes.
+ *
+ * Conventions
+ *   - FP64 everywhere (gpr.py:18 gpflow.config.set_default_float(tf.float64)); matrices row-major.
+ *   - theta = [variance, noise, l_0 .. l_{D-1}] constrained values (kernel variance, Gaussian
+ *     likelihood variance, ARD lengthscales; an isotropic model repeats one value D times).
+ *   - Gradients are d/d log(theta_j); the softplus / prior chain rule is host logic.
+ *   - Every function returns int: 0 ok; > 0 LAPACK-style info (index+1 of the first non-positive
+ *     pivot); < 0 a GPRAS_E_* code, message via gpras_last_error().  Nothing throws across the ABI.
+ *   - There is no CPU fallback: without a CUDA device every compute entry returns GPRAS_E_CUDA.
+ *   - A handle owns one device, one stream and its workspace; it is not thread-safe.
+ */
+#ifndef GPRAS_B200_H
+#define GPRAS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPRAS_B200_ABI_VERSION 1
+
+/* kernel ids == KERNEL_FACTORY keys that are constructible in the reference (gpr.py:21-29, 298) */
+#define GPRAS_KERNEL_RBF 0
+#define GPRAS_KERNEL_MATERN12 1
+#define GPRAS_KERNEL_MATERN32 2
+#define GPRAS_KERNEL_MATERN52 3
+#define GPRAS_KERNEL_EXPONENTIAL 4
+
+#define GPRAS_E_ARG (-1)
+#define GPRAS_E_CUDA (-2)
+#define GPRAS_E_STATE (-3)
+#define GPRAS_E_NOMEM (-4)
+
+typedef struct gpras_gp gpras_gp; /* exact-GP model state on one GPU */
+
+int gpras_abi_version(void);
+const char* gpras_last_error(void);
+/* number of CUDA devices visible (0 if none / no driver) */
+int gpras_device_count(void);
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+/* Replaces SGPR(data=(x, y), kernel=...) construction, gpr.py:293-308, for the shared-theta exact model. */
+int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int p);
+int gpras_gp_destroy(gpras_gp* h);
+/* Run on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream. */
+int gpras_gp_set_stream(gpras_gp* h, void* cuda_stream);
+/* Upload / bind training data (gpr.py:265-266).  on_device != 0: pointers are device pointers. */
+int gpras_gp_set_data(gpras_gp* h, const double* x, const double* y, int on_device);
+
+/* ---- objective: replaces model.training_loss() + GradientTape (gpr.py:153-155,199) ------- */
+/* Synchronous.  theta is a host array of 2 + d doubles.  grad (2 + d, d/dlog theta) may be NULL. */
+int gpras_gp_lml_grad(gpras_gp* h, const double* theta, double* lml, double* grad);
+/* Same, end to end from host buffers: uploads x (n*d) and y (n*p) first. */
+int gpras_gp_lml_grad_host(gpras_gp* h, const double* x, const double* y, const double* theta, double* lml,
+                           double* grad);
+/* Asynchronous pair for throughput runs: enqueue on the handle's stream, then fetch (synchronises). */
+int gpras_gp_lml_grad_enqueue(gpras_gp* h, const double* theta, int want_grad);
+int gpras_gp_lml_grad_fetch(gpras_gp* h, double* lml, double* grad);
+
+/* ---- prediction: replaces model.predict_y(x) (gpr.py:337) ------------------------------- */
+/* Factorise at theta and form alpha; must precede predict. */
+int gpras_gp_condition(gpras_gp* h, const double* theta);
+/* mean (t*p) and var (t*p), noise included; xs is (t, d).  Host or device buffers (on_device). */
+int gpras_gp_predict(gpras_gp* h, const double* xs, int t, double* mean, double* var, int on_device);
+/* Bind the modes->cells map (PreProcessor.reverse_transform, preprocess.py:1052-1094):
+ * e_mean[p][c] = x_std[p]*eofs[p][c]/weights[c] on wet cells (0 on dry), bias[c] = offset / dry fill.
+ * Host arrays; c = number of cells. */
+int gpras_gp_set_cell_map(gpras_gp* h, const double* e_mean, const double* bias, int c);
+/* Predict and expand to cells on the device: cell_mean, cell_var are DEVICE buffers (t x ldc doubles, ldc >=
+ * padded cells, see gpras_gp_cell_pitch) or NULL to run without keeping the cell-space output (the tiles are
+ * written to an internal ring buffer).  mode_mean / mode_var (t*p, host) may be NULL. */
+int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_device, double* mode_mean,
+                           double* mode_var, double* cell_mean, double* cell_var, long ldc);
+long gpras_gp_cell_pitch(gpras_gp* h);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+/* Copy internal matrices to host (n x n, row-major, lower triangle meaningful): which = 0 K~ as built,
+ * 1 L, 2 W = L^-1, 3 K~^-1;  4 alpha (n x p). For tests. */
+int gpras_gp_get_matrix(gpras_gp* h, int which, double* out);
+/* Count of kernel launches issued by the last lml_grad / condition / predict call. */
+int gpras_gp_last_launches(gpras_gp* h);
+/* CUDA-event milliseconds of the stages of the last lml_grad call: [cov, potrf, trtri, lauum, alpha, grad, total]. */
+int gpras_gp_last_stage_ms(gpras_gp* h, double* ms7);
+int gpras_gp_set_stage_timing(gpras_gp* h, int enabled);
+
+/* ---- stand-alone building blocks on device pointers (tests, composition) ------------------ */
+/* C (op)= alpha * A(.)B(.)  with all extents multiples of 128 (k: 16): layout flags select row/k-major. */
+int gpras_dgemm_tiles(void* cuda_stream, int a_kmajor, int b_kmajor, const double* A, long lda, const double* B, long ldb,
+                      double* C, long ldc, int m, int n, int k, double alpha, double beta);
+/* In-place lower Cholesky of the n x n (n % 128 == 0) device matrix A, W = L^-1 diagonal blocks as by-product;
+ * info_dev: device int, logdet_parts_dev: n/128 device doubles. */
+int gpras_dpotrf(void* cuda_stream, double* A, long lda, double* W, long ldw, int n, double* logdet_parts_dev,
+                 int* info_dev);
+/* Complete W = L^-1 (lower) given L and W's diagonal blocks; scratch: n x n device doubles. */
+int gpras_dtrtri(void* cuda_stream, const double* L, long ldl, double* W, long ldw, double* scratch, long lds, int n);
+/* Kinv = W^T W (lower tiles). */
+int gpras_dlauum(void* cuda_stream, const double* W, long ldw, double* Kinv, long ldk, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPRAS_B200_H */
