@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the GPR hot path: LML+grad evaluations/s at N=8192 (BASELINE.json metric, config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" is one exact-GP log-marginal-likelihood + analytic-gradient evaluation at a fresh hyperparameter
+vector (covariance build, Cholesky, triangular inverse, K^-1, alpha, fused trace pass) on synthetic storm-event
+data of BASELINE config 3: N=8192 training rows x 32 features, 32 target columns sharing theta, Matern-5/2 ARD.
+With N GPUs (torchrun, one rank per GPU) every rank evaluates its own shard of optimiser restarts -- K steps per
+rank, no data-path collective, one tiny all-gather of the [LML, grad] rows at the end ("weak" scaling).
+
+Printed JSON line (rank 0): `value` = evaluations/s with inputs resident in HBM, timed with CUDA events on the
+launching stream; `e2e` = the same through the host-buffer C-ABI call (X, Y, theta uploaded from pinned host memory
+and LML+grad read back every step); `roofline` = the DMMA tile-GEMM engine's algorithmic FP64 FLOP/s against the
+measured cuBLAS DGEMM rate; `cpu_baseline` = the oracle port timed on this box's host cores.
+`--impl reference` times that CPU port (the reference's GPflow/TensorFlow stack cannot be installed offline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = dict(n=8192, d=32, p=32, kernel="Matern52", ard=True)
+METRIC = "LML+grad evals/s at N=8192"
+UNIT = "evals/s"
+# measured on this pool's B200 (profiles/r01/lib_bars_cublas_cusolver.json): cuBLAS DGEMM 8192^3, sustained
+FP64_DGEMM_TFLOPS = 35.4
+FP64_PEAK_SOURCE = "measured cuBLAS Dgemm 8192^3 on this pool (profiles/r01/lib_bars_cublas_cusolver.json); MEASURED_PEAKS.json has no FP64 entry"
+
+
+def f_eval(n: int, p: int) -> float:
+    """Algorithmic FP64 FLOPs of one evaluation's dense stages: N^3 + 3 N^2 P."""
+    return float(n) ** 3 + 3.0 * float(n) ** 2 * p
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def cpu_port_eval_seconds(data, thetas, n_evals: int, warm: int):
+    """Time the oracle's CPU restatement (LAPACK potrf/potri + GEMM traces) on all host cores."""
+    from threadpoolctl import threadpool_limits
+
+    from oracle.exact_gp import Theta, lml_and_grad_fast
+
+    cores = os.cpu_count() or 1
+    with threadpool_limits(limits=cores):
+        for i in range(warm):
+            lml_and_grad_fast(WORKLOAD["kernel"], data.x, data.y, Theta(thetas[i, 0], thetas[i, 1], thetas[i, 2:]))
+        t0 = time.perf_counter()
+        for i in range(n_evals):
+            th = thetas[(warm + i) % len(thetas)]
+            lml_and_grad_fast(WORKLOAD["kernel"], data.x, data.y, Theta(th[0], th[1], th[2:]))
+        dt = time.perf_counter() - t0
+    return dt, cores
+
+
+def make_thetas(count: int, d: int, seed: int = 2) -> np.ndarray:
+    """Well-conditioned hyperparameter candidates around the fixed parity point."""
+    from gpras_b200.synth import fixed_theta
+
+    rng = np.random.default_rng(seed)
+    v, s, ls = fixed_theta(d, True)
+    out = np.empty((count, 2 + d))
+    out[:, 0] = v * np.exp(rng.uniform(-0.3, 0.3, count))
+    out[:, 1] = s * np.exp(rng.uniform(-0.3, 0.3, count))
+    out[:, 2:] = ls[None, :] * np.exp(rng.uniform(-0.2, 0.2, (count, d)))
+    return out
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gpras_b200.synth import make_gp_data
+
+    w = WORKLOAD
+    data = make_gp_data(w["n"], w["d"], w["p"], 0, seed=0)
+    thetas = make_thetas(8, w["d"])
+    n_evals = max(1, min(args.steps, 2))
+    warm = 1 if args.warmup > 0 else 0
+    dt, cores = cpu_port_eval_seconds(data, thetas, n_evals, warm)
+    value = n_evals / dt
+    sample = f"{n_evals} full LML+grad evals at N={w['n']} (of {args.steps} requested) after {warm} warm-up, NumPy/SciPy-OpenBLAS oracle port"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / n_evals, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cfg3: exact GP LML+grad, N={w['n']}, D={w['d']}, P={w['p']}, {w['kernel']} ARD + noise, shared theta"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from gpras_b200.engine import ExactGP
+    from gpras_b200.synth import make_cell_map, make_gp_data
+    from gpras_b200.cells import fold_cell_map
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOAD
+    n, d, p = w["n"], w["d"], w["p"]
+    K, W = args.steps, max(args.warmup, 3)
+    data = make_gp_data(n, d, p, 4096, seed=0)
+    thetas = make_thetas(W + K, d, seed=2 + rank)  # every rank = its own shard of restarts / candidates
+    stream = torch.cuda.current_stream()
+    gp = ExactGP(w["kernel"], n, d, p, device=local)
+    gp.set_stream(stream.cuda_stream)
+    gp.set_data(data.x, data.y)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    results = np.zeros((K, 3 + d))
+    # ---- resident-input throughput -------------------------------------------------------------
+    for i in range(W):
+        gp.lml_grad(thetas[i])
+    launches_per_eval = gp.last_launches()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        lml, g = gp.lml_grad(thetas[W + i])
+        results[i, 0], results[i, 1:] = lml, g
+    if world > 1:  # the path's only exchange: all-gather of per-restart [LML, grad] rows
+        loc = torch.from_numpy(results).cuda()
+        allr = torch.empty((world * K, 3 + d), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, loc)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * K / (ms_total * 1e-3)
+
+    # ---- stage timing for the roofline (separate pass; event records perturb nothing measurable) --
+    gp.set_stage_timing(True)
+    stage = []
+    for i in range(min(K, 5)):
+        gp.lml_grad(thetas[W + i])
+        stage.append(gp.last_stage_ms())
+    gp.set_stage_timing(False)
+    dense_ms = float(np.mean([s["potrf"] + s["trtri"] + s["lauum"] + s["alpha"] for s in stage]))
+    stage_mean = {k: float(np.mean([s[k] for s in stage])) for k in stage[0]}
+    achieved = f_eval(n, p) / (dense_ms * 1e-3) * 1e-12
+
+    # ---- end to end through the host-buffer C-ABI entry point ------------------------------------
+    xp = torch.from_numpy(data.x).pin_memory().numpy()
+    yp = torch.from_numpy(data.y).pin_memory().numpy()
+    for i in range(2):
+        gp.lml_grad_host(xp, yp, thetas[i])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        gp.lml_grad_host(xp, yp, thetas[W + i])
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / float(dt.item())
+    h2d = 8 * (n * d + n * p + 2 + d)
+    d2h = 8 * (3 + d) + 4
+
+    # ---- second headline: predicted cell-depths/s (predict + modes->cells on device, ring buffer) --
+    predict = None
+    if rank == 0 or world > 1:
+        c = 200_000
+        cm = make_cell_map(p, c, seed=0)
+        e_mean, bias = fold_cell_map(cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices, cm.elevations)
+        gp.condition(thetas[0])
+        gp.set_cell_map(e_mean, bias)
+        xt = torch.from_numpy(data.x_test).cuda()
+        gp.predict_cells(xt, want_modes=False)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        p0.record(stream)
+        for _ in range(reps):
+            gp.predict_cells(xt, want_modes=False)
+        p1.record(stream)
+        barrier()
+        pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+        t_events = world * reps * xt.shape[0]
+        predict = {
+            "metric": "predicted cell-depths/s", "value": t_events * c / (float(pms.item()) * 1e-3), "unit": "cell-depths/s",
+            "events_per_s": t_events / (float(pms.item()) * 1e-3), "cells": c, "events_per_rank": int(xt.shape[0]),
+            "output": "mean+variance per cell written to a device ring buffer (T*C*16 B cannot be kept)",
+        }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dtc, cores = cpu_port_eval_seconds(data, thetas, 1, 0)
+        cpu = {"value": 1.0 / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 full LML+grad eval at N={n} (NumPy/SciPy-OpenBLAS oracle port, all host threads), {dtc:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"cfg3: exact GP LML+grad, N={n}, D={d}, P={p}, {w['kernel']} ARD + noise, shared theta; "
+                                   f"{K} restarts' evaluations per GPU", "l2": "working set 1.5 GiB per eval >> 126 MB L2 (no flush needed)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_eval * K,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / FP64_DGEMM_TFLOPS, "traffic": None, "kernel": "gemm_tile_kernel (DMMA engine) + leaf, dense stages of one eval",
+                         "flops_per_eval": f_eval(n, p), "dense_ms_per_eval": dense_ms, "peak_source": FP64_PEAK_SOURCE},
+            "stage_ms": stage_mean,
+            "cpu_baseline": cpu,
+            "predict": predict,
+        }
+        print(json.dumps(line), flush=True)
+    gp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -430,9 +430,11 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
   CU(cudaMallocHost((void**)&h->h_theta, sizeof(double) * (2 + d)));
   CU(cudaMallocHost((void**)&h->h_result, sizeof(double) * (3 + d)));
   CU(cudaMallocHost((void**)&h->h_info, sizeof(int)));
-  CU(cudaMemset(h->X, 0, sizeof(double) * h->n_pad * d));
-  CU(cudaMemset(h->Y, 0, sizeof(double) * np));
-  CU(cudaMemset(h->gsum, 0, sizeof(double) * (2 + d)));
+  // stream-ordered: the handle's stream is non-blocking, so legacy-stream memsets would race with set_data
+  CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->n_pad * d, h->stream));
+  CU(cudaMemsetAsync(h->Y, 0, sizeof(double) * np, h->stream));
+  CU(cudaMemsetAsync(h->gsum, 0, sizeof(double) * (2 + d), h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
   *out = h;
   return 0;
@@ -630,10 +632,11 @@ int gpras_gp_set_cell_map(gpras_gp* h, const double* e_mean, const double* bias,
       e2[(size_t)pp * h->c_pad + cc] = v * v;
     }
   memcpy(b.data(), bias, sizeof(double) * c);
-  CU(cudaMemcpy(h->E1, e1.data(), sizeof(double) * ne, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->E2, e2.data(), sizeof(double) * ne, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->bias, b.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice));
-  CU(cudaMemset(h->zbias, 0, sizeof(double) * h->c_pad));
+  CU(cudaMemcpyAsync(h->E1, e1.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->E2, e2.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->bias, b.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->zbias, 0, sizeof(double) * h->c_pad, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -1,0 +1,586 @@
+"""B200-native drop-in for ``gpras.gpr`` -- the GPR surrogate of fema-ffrd/gpras.
+
+Mirrors the reference module's public surface (``gpras/gpr.py:21-41,206-384``): ``KERNEL_FACTORY``,
+``KernelType``, ``OptimizerType``, ``InductionInitializerType``, ``OPTIMIZERS`` and the ``GPRAS`` class with
+``fit / predict / to_file / from_file / models``.  The numerics that the reference delegates to
+GPflow/TensorFlow run in hand-written sm_100a kernels behind ``libgpras_b200.so``; the host side stays
+Python (SciPy L-BFGS-B / differential evolution drive the GPU objective exactly as
+``gpflow.optimizers.Scipy`` does at ``gpr.py:197-203``).  There is no CPU fallback.
+
+Two model families sit behind the same API:
+
+* ``n_inducing=None`` (or ``exact=True``): the exact GP named by BASELINE.json's north_star, i.e. the
+  ``Z == X`` limit of the reference's SGPR.  ``shared_kernel=True`` shares one hyperparameter set across all
+  target columns (one factorisation, multi-RHS solves); the default keeps the reference's one model per
+  column (``gpr.py:293-308``).
+* ``n_inducing=M``: the reference's sparse model (see ``sparse.py``).
+
+Parameterisation, initial values and priors follow the reference: variance 1, scalar lengthscale
+``mean(|x|)`` (``gpr.py:289,298``; ``ard=True`` is an extension), likelihood variance 1 (GPflow default),
+softplus transforms with a 1e-6 floor on the likelihood variance, LogNormal(0, 1) priors on the three
+constrained hyperparameters (``gpr.py:303-305``) counted only while the parameter is trainable.
+"""
+
+from __future__ import annotations
+
+import pickle
+from pathlib import Path
+from typing import Any, Literal
+
+import numpy as np
+from numpy.typing import NDArray
+
+from .engine import ExactGP
+
+LOG_2PI = float(np.log(2.0 * np.pi))
+NOISE_FLOOR = 1e-6  # GPflow Gaussian likelihood DEFAULT_VARIANCE_LOWER_BOUND
+
+
+class KernelSpec:
+    """Stand-in for the GPflow kernel classes held by the reference's ``KERNEL_FACTORY``."""
+
+    def __init__(self, name: str, supported: bool = True):
+        self.name, self.supported = name, supported
+
+    def __repr__(self) -> str:
+        return f"KernelSpec({self.name!r})"
+
+
+KERNEL_FACTORY = {
+    "Matern12": KernelSpec("Matern12"),
+    "Matern32": KernelSpec("Matern32"),
+    "Matern52": KernelSpec("Matern52"),
+    "RBF": KernelSpec("RBF"),
+    # listed by the reference but not constructible there either (``lengthscales=`` is rejected, gpr.py:26-28,298)
+    "Linear": KernelSpec("Linear", supported=False),
+    "Polynomial": KernelSpec("Polynomial", supported=False),
+    "Periodic": KernelSpec("Periodic", supported=False),
+    "Exponential": KernelSpec("Exponential"),
+}
+
+KernelType = Literal["Matern12", "Matern32", "Matern52", "RBF", "Linear", "Polynomial", "Periodic", "Exponential"]
+OptimizerType = Literal["two-stage", "adam", "L-BFGS-B", "stochastic", "diffential_evolution"]
+InductionInitializerType = Literal["kmeans", "grid"]
+
+
+# ------------------------------------------------------------------------------------------------
+# parameters (GPflow ``Parameter`` look-alikes: ``.numpy()``, ``.assign()``, ``.prior``, trainable flag)
+# ------------------------------------------------------------------------------------------------
+def _softplus(u):
+    return np.logaddexp(0.0, u)
+
+
+def _softplus_inv(v):
+    return v + np.log(-np.expm1(-v))
+
+
+def _sigmoid(u):
+    return 0.5 * (1.0 + np.tanh(0.5 * u))
+
+
+class Parameter:
+    """Positive parameter stored unconstrained: value = softplus(u) + lower."""
+
+    def __init__(self, value, lower: float = 0.0, prior: str | None = None, trainable: bool = True):
+        self.lower = float(lower)
+        self.prior = prior  # "LogNormal(0,1)" or None
+        self.trainable = trainable
+        self.unconstrained = np.atleast_1d(_softplus_inv(np.asarray(value, np.float64) - self.lower)).astype(np.float64)
+        self._scalar = np.ndim(value) == 0
+
+    def numpy(self):
+        v = _softplus(self.unconstrained) + self.lower
+        return float(v[0]) if self._scalar else v
+
+    def assign(self, value) -> None:
+        value = np.asarray(value, np.float64)
+        self._scalar = value.ndim == 0
+        self.unconstrained = np.atleast_1d(_softplus_inv(value - self.lower)).astype(np.float64)
+
+    @property
+    def size(self) -> int:
+        return self.unconstrained.size
+
+    def dvalue_du(self):
+        return _sigmoid(self.unconstrained)
+
+    def log_prior(self) -> float:
+        if self.prior is None:
+            return 0.0
+        lv = np.log(_softplus(self.unconstrained) + self.lower)
+        return float(np.sum(-lv - 0.5 * LOG_2PI - 0.5 * lv * lv))
+
+    def dlog_prior_dvalue(self):
+        if self.prior is None:
+            return np.zeros_like(self.unconstrained)
+        v = _softplus(self.unconstrained) + self.lower
+        return -(1.0 + np.log(v)) / v
+
+    def __repr__(self) -> str:
+        return f"Parameter({self.numpy()!r}, trainable={self.trainable})"
+
+
+class _Kernel:
+    def __init__(self, name: str, variance, lengthscales):
+        self.name = name
+        self.variance = Parameter(variance, prior="LogNormal(0,1)")
+        self.lengthscales = Parameter(lengthscales, prior="LogNormal(0,1)")
+
+
+class _Likelihood:
+    def __init__(self, variance=1.0):
+        self.variance = Parameter(variance, lower=NOISE_FLOOR, prior="LogNormal(0,1)")
+
+
+class _Inducing:
+    """``model.inducing_variable.Z`` as read by ``production/analysis/pipeline.py:115``."""
+
+    def __init__(self, z: NDArray[Any], trainable: bool = True):
+        self.Z = np.asarray(z, np.float64)
+        self.trainable = trainable
+
+
+class _DeviceSlot:
+    """One shared device handle per (kernel, N, D, P): per-column models take turns on it."""
+
+    def __init__(self):
+        self.gp: ExactGP | None = None
+        self.key = None
+        self.owner = None
+
+    def acquire(self, model: "ExactModel") -> ExactGP:
+        key = (model.kernel.name, model.x.shape[0], model.x.shape[1], model.y.shape[1], model.device)
+        if self.gp is None or self.key != key:
+            if self.gp is not None:
+                self.gp.close()
+            self.gp = ExactGP(model.kernel.name, key[1], key[2], key[3], device=model.device)
+            self.key, self.owner = key, None
+        if self.owner is not model:
+            self.gp.set_data(model.x, model.y)
+            self.owner = model
+        return self.gp
+
+
+class ExactModel:
+    """Exact GP with one hyperparameter set for all columns of ``y`` (the ``Z == X`` limit of the
+    reference's per-column ``SGPR``).  Exposes the attribute names the reference's recipes touch:
+    ``kernel.variance / kernel.lengthscales / likelihood.variance / inducing_variable.Z / data /
+    trainable_variables / training_loss()`` (``gpr.py:57-62,80-81,88-91,155``)."""
+
+    def __init__(self, kernel_name, x, y, lengthscales, slot: _DeviceSlot, device: int = 0, priors: bool = True):
+        self.x, self.y = x, y
+        self.data = (x, y)
+        self.device = device
+        self.kernel = _Kernel(kernel_name, 1.0, lengthscales)
+        self.likelihood = _Likelihood(1.0)
+        self.inducing_variable = _Inducing(x, trainable=False)
+        if not priors:
+            self.kernel.variance.prior = self.kernel.lengthscales.prior = self.likelihood.variance.prior = None
+        self._slot = slot
+        self.n_evals = 0
+
+    # -- parameter plumbing --
+    @property
+    def parameters(self):
+        return [self.kernel.variance, self.likelihood.variance, self.kernel.lengthscales]
+
+    @property
+    def trainable_variables(self):
+        return [p.unconstrained for p in self.parameters if p.trainable]
+
+    def set_trainable(self, flag: bool, hypers: bool = True) -> None:
+        if hypers:
+            for p in self.parameters:
+                p.trainable = flag
+
+    def get_u(self) -> NDArray[Any]:
+        ps = [p for p in self.parameters if p.trainable]
+        return np.concatenate([p.unconstrained for p in ps]) if ps else np.zeros(0)
+
+    def set_u(self, u) -> None:
+        u = np.asarray(u, np.float64)
+        o = 0
+        for p in self.parameters:
+            if p.trainable:
+                p.unconstrained = u[o : o + p.size].copy()
+                o += p.size
+
+    def theta(self) -> NDArray[Any]:
+        d = self.x.shape[1]
+        ls = np.atleast_1d(self.kernel.lengthscales.numpy())
+        if ls.size == 1:
+            ls = np.full(d, ls[0])
+        return np.concatenate([[self.kernel.variance.numpy(), self.likelihood.variance.numpy()], ls])
+
+    # -- objective --
+    def _log_prior(self) -> float:
+        return sum(p.log_prior() for p in self.parameters if p.trainable)
+
+    def training_loss(self) -> float:
+        """-(LML + log prior over trainable hyperparameters), loss only."""
+        gp = self._slot.acquire(self)
+        lml, _ = gp.lml_grad(self.theta(), want_grad=False)
+        self.n_evals += 1
+        return -(lml + self._log_prior())
+
+    def loss_and_grad(self, u=None):
+        """Loss and its gradient w.r.t. the trainable unconstrained variables (what ``GradientTape`` returns)."""
+        if u is not None:
+            self.set_u(u)
+        gp = self._slot.acquire(self)
+        lml, glog = gp.lml_grad(self.theta(), want_grad=True)
+        self.n_evals += 1
+        g_var, g_noise, g_ls = glog[0], glog[1], glog[2:]
+        if self.kernel.lengthscales.size == 1:
+            g_ls = np.array([g_ls.sum()])
+        parts = []
+        for p, gl in ((self.kernel.variance, np.array([g_var])), (self.likelihood.variance, np.array([g_noise])),
+                      (self.kernel.lengthscales, g_ls)):
+            if p.trainable:
+                v = _softplus(p.unconstrained) + p.lower
+                dv = gl / v + p.dlog_prior_dvalue()
+                parts.append(-(dv * p.dvalue_du()))
+        grad = np.concatenate(parts) if parts else np.zeros(0)
+        return -(lml + self._log_prior()), grad
+
+    # -- prediction --
+    def predict_y(self, xs):
+        gp = self._slot.acquire(self)
+        gp.condition(self.theta())
+        return gp.predict(np.asarray(xs, np.float64))
+
+    def parameter_dict(self) -> dict:
+        """Plain-ndarray version of ``gpflow.utilities.parameter_dict`` (same keys)."""
+        return {
+            ".kernel.variance": np.asarray(self.kernel.variance.numpy()),
+            ".kernel.lengthscales": np.asarray(self.kernel.lengthscales.numpy()),
+            ".likelihood.variance": np.asarray(self.likelihood.variance.numpy()),
+            ".inducing_variable.Z": np.asarray(self.inducing_variable.Z),
+        }
+
+    def assign_parameters(self, d: dict) -> None:
+        self.kernel.variance.assign(d[".kernel.variance"])
+        self.kernel.lengthscales.assign(d[".kernel.lengthscales"])
+        self.likelihood.variance.assign(d[".likelihood.variance"])
+
+
+# ------------------------------------------------------------------------------------------------
+# optimiser recipes (gpras/gpr.py:44-214) acting on any model exposing get_u / set_u / loss_and_grad
+# ------------------------------------------------------------------------------------------------
+def _has_z(model) -> bool:
+    return getattr(model, "supports_z_training", False)
+
+
+def _set_stage(model, hypers: bool, z: bool) -> None:
+    """``gpflow.set_trainable`` choreography of the recipes."""
+    model.set_trainable(hypers, hypers=True)
+    if _has_z(model):
+        model.inducing_variable.trainable = z
+
+
+def _optimize_adam(model, max_iter: int, learning_rate: float = 0.001) -> None:
+    """Keras Adam (lr 1e-3, beta 0.9 / 0.999, eps 1e-7) with the reference's early-stopping rule
+    (relative improvement <= 10e-6 for more than 50 steps, ``gpr.py:159-173``)."""
+    u = model.get_u()
+    if u.size == 0:
+        return
+    m = np.zeros_like(u)
+    v = np.zeros_like(u)
+    b1, b2, eps = 0.9, 0.999, 1e-7
+    best, count, tol, patience = np.inf, 0, 10e-6, 50
+    for t in range(1, int(max_iter) + 1):
+        loss, g = model.loss_and_grad(u)
+        m = b1 * m + (1.0 - b1) * g
+        v = b2 * v + (1.0 - b2) * g * g
+        alpha = learning_rate * np.sqrt(1.0 - b2**t) / (1.0 - b1**t)
+        u = u - alpha * m / (np.sqrt(v) + eps)
+        model.set_u(u)
+        if ((best - loss) / abs(loss)) > tol:
+            best, count = loss, 0
+        else:
+            count += 1
+            if count > patience:
+                break
+
+
+def _optimize_adadelta(model, max_iter: int, learning_rate: float = 0.001) -> float:
+    """Keras Adadelta (lr 1e-3, rho 0.95, eps 1e-7), fixed ``max_iter`` steps (``gpr.py:176-192``)."""
+    u = model.get_u()
+    acc_g = np.zeros_like(u)
+    acc_d = np.zeros_like(u)
+    rho, eps = 0.95, 1e-7
+    loss = float("nan")
+    for _ in range(int(max_iter)):
+        loss, g = model.loss_and_grad(u)
+        acc_g = rho * acc_g + (1.0 - rho) * g * g
+        upd = g * np.sqrt(acc_d + eps) / np.sqrt(acc_g + eps)
+        acc_d = rho * acc_d + (1.0 - rho) * upd * upd
+        u = u - learning_rate * upd
+        model.set_u(u)
+    return loss
+
+
+def _optimize_bfgs(model, max_iter: int) -> Any:
+    """SciPy L-BFGS-B over the trainable unconstrained variables, as ``gpflow.optimizers.Scipy`` (``gpr.py:195-203``)."""
+    from scipy.optimize import minimize
+
+    u0 = model.get_u()
+    if u0.size == 0:
+        return None
+    res = minimize(model.loss_and_grad, u0, jac=True, method="L-BFGS-B", options={"maxiter": int(max_iter)})
+    model.set_u(res.x)
+    return res
+
+
+def _optimize_two_stage(model, max_iter: int = 100) -> float:
+    """Adam on the inducing inputs, then Adam on the hyperparameters (``gpr.py:112-127``)."""
+    _set_stage(model, hypers=False, z=True)
+    _optimize_adam(model, max_iter)
+    _set_stage(model, hypers=True, z=False)
+    _optimize_adam(model, max_iter)
+    _set_stage(model, hypers=True, z=True)
+    return model.training_loss()
+
+
+def _optimize_three_stage(model, max_iter: int = 100) -> None:
+    """Adam on Z, L-BFGS on hyperparameters, L-BFGS on everything (``gpr.py:130-144``)."""
+    _set_stage(model, hypers=False, z=True)
+    _optimize_adam(model, max_iter)
+    _set_stage(model, hypers=True, z=False)
+    _optimize_bfgs(model, max_iter)
+    _set_stage(model, hypers=True, z=True)
+    _optimize_bfgs(model, max_iter)
+
+
+def _optimize_multi_start(model, n_starts: int = 40, iter_initial: int = 20, iter_final: int = 1000, seed=None,
+                          starts=None, pick_best: bool = False) -> None:
+    """Random restarts with a short Adam run each, then L-BFGS from the selected start (``gpr.py:73-109``).
+
+    Faithful to the reference by default: its ``best_loss`` is never assigned (``gpr.py:86,96``), so the LAST
+    start is the one that gets polished; ``pick_best=True`` selects the lowest coarse loss instead.  The
+    reference's generator is unseeded (``gpr.py:76-77``); ``seed`` / ``starts`` ((R, 3) constrained
+    [variance, lengthscale, noise]) make runs reproducible.
+    """
+    rng = np.random.default_rng(seed)
+    x = model.data[0]
+    mins, maxs = x.min(axis=0), x.max(axis=0)
+    best_loss, best = None, None
+    for r in range(int(n_starts)):
+        if starts is not None:
+            var0, ls0, noise0 = starts[r]
+        else:
+            var0, ls0, noise0 = 10 ** rng.uniform(-1, 1), 10 ** rng.uniform(-1, 1), 10 ** rng.uniform(-3, 0)
+        model.kernel.variance.assign(var0)
+        model.kernel.lengthscales.assign(np.full(model.kernel.lengthscales.size, ls0) if model.kernel.lengthscales.size > 1 else ls0)
+        model.likelihood.variance.assign(noise0)
+        if _has_z(model):
+            model.inducing_variable.Z = rng.uniform(mins, maxs, size=model.inducing_variable.Z.shape)
+        _optimize_adam(model, iter_initial)
+        loss = model.training_loss()
+        if not pick_best or best_loss is None or loss < best_loss:
+            best = (model.kernel.variance.numpy(), model.kernel.lengthscales.numpy(), model.likelihood.variance.numpy(),
+                    np.array(model.inducing_variable.Z))
+            best_loss = loss
+    model.kernel.variance.assign(best[0])
+    model.kernel.lengthscales.assign(best[1])
+    model.likelihood.variance.assign(best[2])
+    if _has_z(model):
+        model.inducing_variable.Z = best[3]
+    _optimize_bfgs(model, iter_final)
+
+
+def _optimize_differential_evolutions(model, popsize: int = 15, max_iter: int = 500, seed=None, verbose: bool = False) -> None:
+    """Adam on Z (3000 its), then SciPy differential evolution over (log10 variance, log10 lengthscale,
+    log10 noise) in [-1, 1]^2 x [-3, 0] with the loss as objective (``gpr.py:44-70``).  The reference prints
+    every evaluation (``gpr.py:61``); pass ``verbose=True`` for that."""
+    from scipy.optimize import differential_evolution
+
+    _set_stage(model, hypers=False, z=True)
+    _optimize_adam(model, max_iter=3000)
+    bounds = [(-1, 1), (-1, 1), (-3, 0)]
+    nls = model.kernel.lengthscales.size
+
+    def assign(p):
+        model.kernel.variance.assign(10 ** p[0])
+        model.kernel.lengthscales.assign(np.full(nls, 10 ** p[1]) if nls > 1 else 10 ** p[1])
+        model.likelihood.variance.assign(10 ** p[2])
+
+    def objective(p):
+        assign(p)
+        loss = model.training_loss()
+        if verbose:
+            print(loss)
+        return loss
+
+    res = differential_evolution(objective, bounds, popsize=popsize, maxiter=max_iter, seed=seed)
+    assign(res.x)
+
+
+OPTIMIZERS: dict[str, Any] = {
+    "two-stage": _optimize_two_stage,
+    "three-stage": _optimize_three_stage,
+    "adam": _optimize_adam,
+    "adadelta": _optimize_adadelta,
+    "L-BFGS-B": _optimize_bfgs,
+    "stochastic": _optimize_multi_start,
+    "diffential_evolution": _optimize_differential_evolutions,
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPRAS
+# ------------------------------------------------------------------------------------------------
+class GPRAS:
+    """Gaussian Process Regression for HEC-RAS model upskilling and emulation (``gpras/gpr.py:217``)."""
+
+    def __init__(self, kernel: KernelType) -> None:
+        self.kernel_str = kernel
+        self.kernel = KERNEL_FACTORY[kernel]  # KeyError on an unknown name, as the reference (gpr.py:230)
+        self.models: list[Any] = []
+        self.x: NDArray[Any] | None = None
+        self.y: NDArray[Any] | None = None
+        self._slot = _DeviceSlot()
+        self._opts: dict[str, Any] = {}
+
+    # -- fit ------------------------------------------------------------------------------------
+    def fit(
+        self,
+        x: NDArray[Any],
+        y: NDArray[Any],
+        n_inducing: int | None,
+        inducing_initializer: InductionInitializerType = "kmeans",
+        optimization_method: OptimizerType = "two-stage",
+        *,
+        exact: bool | None = None,
+        ard: bool = False,
+        shared_kernel: bool = False,
+        priors: bool = True,
+        device: int = 0,
+        initial_theta: NDArray[Any] | None = None,
+        restarts: NDArray[Any] | None = None,
+        **opt_kwargs: Any,
+    ) -> None:
+        """Fit the surrogate (``gpr.py:237-275``).  Positional arguments and ``**opt_kwargs`` are the reference's.
+
+        Keyword-only extensions (defaults reproduce the reference): ``exact`` / ``n_inducing=None`` selects the
+        exact GP; ``ard`` one lengthscale per feature; ``shared_kernel`` one hyperparameter set for all columns;
+        ``priors=False`` drops the LogNormal priors (scikit-learn's objective); ``initial_theta``
+        ([variance, noise, lengthscale(s)]) overrides the initial values; ``restarts`` ((R, 2 + n_ls) constrained
+        start points, column order [variance, noise, lengthscale(s)]) runs the recipe from every start and keeps
+        the lowest final loss (sharded across ranks when ``torch.distributed`` is initialised).
+        """
+        self.x = np.asarray(x).astype(np.float64)
+        self.y = np.asarray(y).astype(np.float64)
+        if exact is None:
+            exact = n_inducing is None
+        self._opts = dict(exact=exact, ard=ard, shared_kernel=shared_kernel, priors=priors, device=device)
+        self._init_models(self.x, self.y, n_inducing, inducing_initializer)
+        opt = OPTIMIZERS[optimization_method]  # KeyError on an unknown method, as the reference (gpr.py:272)
+        unique = self.models[:1] if (shared_kernel and exact) else self.models
+        for model in unique:
+            if initial_theta is not None:
+                _assign_theta(model, initial_theta)
+            if restarts is None:
+                opt(model, **opt_kwargs)
+            else:
+                from .parallel import run_restarts
+
+                run_restarts(model, opt, np.asarray(restarts, np.float64), opt_kwargs)
+
+    def _init_models(self, x, y, n_inducing, inducing_initializer: InductionInitializerType = "kmeans") -> None:
+        """One model per spatial mode with the reference's initial values (``gpr.py:277-308``)."""
+        o = self._opts or dict(exact=n_inducing is None, ard=False, shared_kernel=False, priors=True, device=0)
+        if not self.kernel.supported:
+            raise NotImplementedError(
+                f"kernel {self.kernel_str!r} cannot be constructed with lengthscales= in the reference either (gpr.py:26-28,298)"
+            )
+        ini_length = float(np.mean(np.abs(x)))
+        ls0 = np.full(x.shape[1], ini_length) if o["ard"] else ini_length
+        self.models = []
+        if o["exact"]:
+            if o["shared_kernel"]:
+                m = ExactModel(self.kernel_str, x, y, ls0, self._slot, o["device"], o["priors"])
+                self.models = [m] * y.shape[1]
+            else:
+                for i in range(y.shape[1]):
+                    self.models.append(ExactModel(self.kernel_str, x, np.ascontiguousarray(y[:, i : i + 1]), ls0, self._slot,
+                                                  o["device"], o["priors"]))
+            return
+        from .sparse import SparseModel
+
+        inducing = self._create_inducing(x, int(n_inducing), inducing_initializer)
+        for i in range(y.shape[1]):
+            self.models.append(SparseModel(self.kernel_str, x, np.ascontiguousarray(y[:, i : i + 1]), inducing.copy(), ls0,
+                                           o["device"], o["priors"]))
+
+    def _create_inducing(self, x, n_inducing: int, method: InductionInitializerType) -> NDArray[Any]:
+        """Inducing-input initialisation (``gpr.py:310-320``): KMeans centres or a per-feature linspace diagonal."""
+        if method == "kmeans":
+            from sklearn.cluster import KMeans
+
+            km = KMeans(n_clusters=n_inducing, random_state=0, n_init="auto")
+            km.fit(x)
+            return km.cluster_centers_.astype(np.float64)
+        elif method == "grid":
+            cols = [np.linspace(x[:, j].min(), x[:, j].max(), n_inducing) for j in range(x.shape[1])]
+            return np.stack(cols, axis=1).astype(np.float64)
+        return None  # the reference falls through the same way for an unknown initializer
+
+    # -- predict --------------------------------------------------------------------------------
+    def predict(self, x: NDArray[Any]) -> tuple[NDArray[Any], NDArray[Any]]:
+        """Predicted means and VARIANCES, both (n_samples, n_outputs), likelihood noise included (``gpr.py:322-342``)."""
+        x = np.asarray(x).astype(np.float64)
+        if self._opts.get("shared_kernel") and self._opts.get("exact") and self.models:
+            return self.models[0].predict_y(x)
+        means, variances = [], []
+        for m in self.models:
+            mu, var = m.predict_y(x)
+            means.append(mu)
+            variances.append(var)
+        return np.concatenate(means, axis=1), np.concatenate(variances, axis=1)
+
+    def predict_std(self, x: NDArray[Any]) -> tuple[NDArray[Any], NDArray[Any]]:
+        """Explicit extra: (mean, std); callers of the reference take ``np.sqrt`` themselves (pipeline.py:262-263)."""
+        mean, var = self.predict(x)
+        return mean, np.sqrt(var)
+
+    # -- persistence ----------------------------------------------------------------------------
+    def to_file(self, json_path: str | Path, model_dir: str | Path | None = None) -> None:
+        """Pickle with the reference's keys (``gpr.py:344-366``); values are plain ndarrays (GPflow ``Parameter``
+        objects cannot be unpickled without GPflow)."""
+        d = {
+            "kernel": self.kernel_str,
+            "data": {"x": self.x, "y": self.y},
+            "n_inducing": self.models[0].inducing_variable.Z.shape[0],
+            "models": [m.parameter_dict() for m in self.models],
+            "gpras_b200": dict(self._opts),
+        }
+        with open(json_path, mode="wb") as f:
+            pickle.dump(d, f)
+
+    @classmethod
+    def from_file(cls, json_path: str | Path):
+        """Rebuild from :meth:`to_file` output (``gpr.py:368-384``): re-initialise with the "grid" initializer,
+        then assign the saved parameters."""
+        with open(json_path, mode="rb") as f:
+            d = pickle.load(f)
+        inst = cls(d["kernel"])
+        inst.x, inst.y = d["data"]["x"], d["data"]["y"]
+        inst._opts = d.get("gpras_b200", dict(exact=False, ard=False, shared_kernel=False, priors=True, device=0))
+        inst._init_models(inst.x, inst.y, d["n_inducing"], "grid")
+        seen = set()
+        for ind, params in enumerate(d["models"]):
+            m = inst.models[ind]
+            if id(m) in seen:
+                continue
+            seen.add(id(m))
+            m.assign_parameters(params)
+        return inst
+
+
+def _assign_theta(model, theta) -> None:
+    theta = np.asarray(theta, np.float64)
+    model.kernel.variance.assign(theta[0])
+    model.likelihood.variance.assign(theta[1])
+    nls = model.kernel.lengthscales.size
+    model.kernel.lengthscales.assign(theta[2 : 2 + nls] if nls > 1 else theta[2])

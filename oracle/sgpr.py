@@ -95,7 +95,7 @@ def training_loss_and_grads(name, x, y, z, u_var, u_ls, u_noise, train_hypers=Tr
     loss = -obj
     wrt = [v for v in (uv, ul, un, zt) if v.requires_grad]
     grads = torch.autograd.grad(loss, wrt) if wrt else ()
-    out = {"loss": float(loss)}
+    out = {"loss": float(loss.detach())}
     it = iter(grads)
     if train_hypers:
         out["u_var"], out["u_ls"], out["u_noise"] = (next(it).numpy() for _ in range(3))

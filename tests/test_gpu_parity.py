@@ -1,0 +1,312 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle / golden vectors.
+
+Tolerances are the north_star's: relative 1e-8 on LML and predictive mean, 1e-6 on predictive std (FP64
+throughout); gradients 1e-7; building blocks near machine precision.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, golden_case
+
+pytestmark = pytest.mark.gpu
+
+LML_RTOL, MEAN_RTOL, STD_RTOL, GRAD_RTOL = 1e-8, 1e-8, 1e-6, 1e-7
+
+
+@pytest.fixture(scope="module")
+def cuda(lib):
+    import torch
+
+    assert torch.cuda.is_available() and lib.gpras_device_count() > 0, "GPU tests need a CUDA device"
+    return torch
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(np.asarray(b))), 1e-300))
+
+
+# ---- building blocks ---------------------------------------------------------------------------
+@pytest.mark.parametrize("akm", [0, 1])
+@pytest.mark.parametrize("bkm", [0, 1])
+def test_tile_gemm_all_layouts(cuda, lib, akm, bkm):
+    torch = cuda
+    from gpras_b200 import _lib
+
+    m, n, k = 384, 256, 272
+    g = torch.Generator(device="cuda").manual_seed(akm * 2 + bkm)
+    A = torch.randn((k, m) if akm else (m, k), dtype=torch.float64, device="cuda", generator=g)
+    B = torch.randn((k, n) if bkm else (n, k), dtype=torch.float64, device="cuda", generator=g)
+    Cc = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    ref = 0.7 * ((A.T if akm else A) @ (B if bkm else B.T)) - 0.3 * Cc
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.gpras_dgemm_tiles(st, akm, bkm, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cc.data_ptr(),
+                                     Cc.stride(0), m, n, k, 0.7, -0.3))
+    torch.cuda.synchronize()
+    assert _rel(Cc.cpu().numpy(), ref.cpu().numpy()) < 1e-13
+
+
+@pytest.mark.parametrize("n", [128, 384, 640, 2048])
+def test_potrf_trtri_lauum_against_lapack(cuda, lib, n):
+    torch = cuda
+    from gpras_b200 import _lib
+
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n))
+    spd = a @ a.T / n + np.eye(n)
+    A = torch.from_numpy(spd).cuda()
+    W = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    T = torch.zeros_like(W)
+    Kinv = torch.zeros_like(W)
+    ld = torch.zeros(n // 128, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.gpras_dpotrf(st, A.data_ptr(), n, W.data_ptr(), n, n, ld.data_ptr(), info.data_ptr()))
+    _lib.check(lib.gpras_dtrtri(st, A.data_ptr(), n, W.data_ptr(), n, T.data_ptr(), n, n))
+    _lib.check(lib.gpras_dlauum(st, W.data_ptr(), n, Kinv.data_ptr(), n, n))
+    torch.cuda.synchronize()
+    assert int(info) == 0
+    L = np.linalg.cholesky(spd)
+    assert _rel(np.tril(A.cpu().numpy()), L) < 1e-13
+    assert _rel(np.tril(W.cpu().numpy()), np.linalg.inv(L)) < 1e-12
+    assert _rel(np.tril(Kinv.cpu().numpy()), np.tril(np.linalg.inv(spd))) < 1e-11
+    assert abs(float(ld.sum()) - np.log(np.diag(L)).sum()) < 1e-10 * n
+
+
+def test_potrf_reports_first_bad_pivot(cuda, lib):
+    torch = cuda
+    from gpras_b200 import _lib
+
+    n = 256
+    spd = np.eye(n)
+    spd[130, 130] = -1.0
+    A = torch.from_numpy(spd).cuda()
+    W = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    ld = torch.zeros(2, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(lib.gpras_dpotrf(torch.cuda.current_stream().cuda_stream, A.data_ptr(), n, W.data_ptr(), n, n, ld.data_ptr(), info.data_ptr()))
+    torch.cuda.synchronize()
+    assert int(info) == 131  # LAPACK info: 1-based index of the failing pivot
+
+
+# ---- LML / gradient / prediction against golden vectors and the oracle ------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_exact_gp_matches_sklearn_golden(cuda, golden, name):
+    from gpras_b200.engine import ExactGP
+
+    c = golden_case(golden, name)
+    n, d = c["x"].shape
+    p = c["y"].shape[1]
+    gp = ExactGP(c["kernel"], n, d, p)
+    gp.set_data(c["x"], c["y"])
+    th = gp.theta_vector(c["variance"], c["noise"], c["ls"])
+    lml, g = gp.lml_grad(th)
+    gl = g[2:] if c["ls"].size > 1 else np.array([g[2:].sum()])
+    assert abs(lml - c["lml"]) <= LML_RTOL * abs(c["lml"])
+    np.testing.assert_allclose(np.concatenate([g[:2], gl]), c["grad_log"], rtol=GRAD_RTOL, atol=1e-8)
+    lml_only, _ = gp.lml_grad(th, want_grad=False)
+    assert lml_only == lml
+    gp.condition(th)
+    mean, var = gp.predict(c["xs"])
+    np.testing.assert_allclose(mean, c["mean"], rtol=MEAN_RTOL, atol=MEAN_RTOL * np.abs(c["mean"]).max())
+    np.testing.assert_allclose(np.sqrt(var), c["std"].reshape(var.shape), rtol=STD_RTOL)
+    gp.close()
+
+
+@pytest.mark.parametrize(
+    "kernel,ard,n,d,p,t",
+    [("RBF", False, 256, 8, 8, 1000),        # BASELINE config 1 (reference-runnable size)
+     ("Matern52", True, 300, 5, 3, 77),      # ragged: n, t not multiples of the tile
+     ("Matern32", True, 129, 16, 16, 1),
+     ("Matern12", False, 127, 4, 2, 130),
+     ("Exponential", False, 513, 3, 1, 2500),
+     ("Matern52", True, 1000, 64, 40, 300)],  # widest supported feature count, p > 32
+)
+def test_exact_gp_matches_oracle(cuda, kernel, ard, n, d, p, t):
+    from gpras_b200.engine import ExactGP
+    from gpras_b200.synth import fixed_theta, make_gp_data
+    from oracle.exact_gp import Theta, lml_and_grad, predict
+
+    data = make_gp_data(n, d, p, t, seed=n + d)
+    v, s, ls = fixed_theta(d, ard)
+    gp = ExactGP(kernel, n, d, p)
+    gp.set_data(data.x, data.y)
+    th = gp.theta_vector(v, s, ls)
+    lml, g = gp.lml_grad(th)
+    o = lml_and_grad(kernel, data.x, data.y, Theta(v, s, ls))
+    assert abs(lml - o[0]) <= LML_RTOL * abs(o[0])
+    np.testing.assert_allclose(g, np.concatenate([[o[1], o[2]], o[3]]), rtol=GRAD_RTOL, atol=1e-8)
+    gp.condition(th)
+    mean, var = gp.predict(data.x_test)
+    om, ov = predict(kernel, data.x, data.y, Theta(v, s, ls), data.x_test)
+    np.testing.assert_allclose(mean, om, rtol=MEAN_RTOL, atol=MEAN_RTOL * np.abs(om).max())
+    np.testing.assert_allclose(np.sqrt(var), np.sqrt(ov), rtol=STD_RTOL)
+    # internal matrices
+    L = np.tril(gp.get_matrix(1))
+    kt = L @ L.T
+    from oracle.kernels import cov
+
+    assert _rel(kt, cov(kernel, data.x, data.x, v, ls) + s * np.eye(n)) < 1e-12
+    gp.close()
+
+
+def test_not_positive_definite_raises(cuda):
+    from gpras_b200 import _lib
+    from gpras_b200.engine import ExactGP
+
+    x = np.zeros((40, 2))  # all rows identical and (almost) no noise -> singular
+    y = np.ones((40, 1))
+    gp = ExactGP("RBF", 40, 2, 1)
+    gp.set_data(x, y)
+    with pytest.raises(_lib.NotPositiveDefiniteError):
+        gp.lml_grad(gp.theta_vector(1.0, 0.0, 1.0))
+    gp.close()
+
+
+def test_host_buffer_entry_point_equals_resident_path(cuda):
+    from gpras_b200.engine import ExactGP
+    from gpras_b200.synth import fixed_theta, make_gp_data
+
+    data = make_gp_data(200, 6, 4, seed=1)
+    v, s, ls = fixed_theta(6, True)
+    gp = ExactGP("Matern52", 200, 6, 4)
+    th = gp.theta_vector(v, s, ls)
+    a = gp.lml_grad_host(data.x, data.y, th)
+    gp.set_data(data.x, data.y)
+    b = gp.lml_grad(th)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])  # deterministic reductions: bitwise repeatable
+    gp.enqueue(th)
+    c = gp.fetch()
+    assert c[0] == b[0] and np.array_equal(c[1], b[1])
+    assert gp.last_launches() > 0
+    gp.close()
+
+
+# ---- modes -> cells -----------------------------------------------------------------------------
+def test_predict_cells_matches_reverse_transform_oracle(cuda):
+    torch = cuda
+    from gpras_b200.cells import fold_cell_map
+    from gpras_b200.engine import ExactGP
+    from gpras_b200.synth import fixed_theta, make_cell_map, make_gp_data
+    from oracle.cells import reverse_transform
+    from oracle.exact_gp import Theta, predict
+
+    n, d, p, t, c = 200, 5, 5, 300, 1111
+    data = make_gp_data(n, d, p, t, seed=3)
+    cm = make_cell_map(p, c, seed=3)
+    v, s, ls = fixed_theta(d, True)
+    gp = ExactGP("Matern52", n, d, p)
+    gp.set_data(data.x, data.y)
+    th = gp.theta_vector(v, s, ls)
+    gp.condition(th)
+    e_mean, bias = fold_cell_map(cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices, cm.elevations)
+    gp.set_cell_map(e_mean, bias)
+    pitch = gp.cell_pitch()
+    cmean = torch.empty((384, pitch), dtype=torch.float64, device="cuda")
+    cvar = torch.empty((384, pitch), dtype=torch.float64, device="cuda")
+    mm, mv = gp.predict_cells(data.x_test, cmean, cvar)
+    torch.cuda.synchronize()
+    om, ov = predict("Matern52", data.x, data.y, Theta(v, s, ls), data.x_test)
+    rm, rv = reverse_transform(om, ov, cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices, cm.elevations)
+    np.testing.assert_allclose(mm, om, rtol=MEAN_RTOL, atol=MEAN_RTOL * np.abs(om).max())
+    np.testing.assert_allclose(cmean[:t, :c].cpu().numpy(), rm, rtol=MEAN_RTOL, atol=MEAN_RTOL * np.abs(rm).max())
+    np.testing.assert_allclose(np.sqrt(cvar[:t, :c].cpu().numpy()), np.sqrt(rv), rtol=STD_RTOL, atol=1e-12)
+    # ring-buffer mode (no cell-space output kept) gives the same mode-space result
+    mm2, mv2 = gp.predict_cells(data.x_test)
+    assert np.array_equal(mm, mm2) and np.array_equal(mv, mv2)
+    gp.close()
+
+
+# ---- the GPRAS drop-in ------------------------------------------------------------------------
+def test_gpras_fit_lbfgs_lands_on_oracle_optimum(cuda, tmp_path):
+    from gpras_b200 import GPRAS
+    from gpras_b200.synth import make_gp_data
+    from oracle.exact_gp import Objective, fit_lbfgs
+
+    data = make_gp_data(256, 8, 3, 50, seed=0)
+    for ard in (False, True):
+        g = GPRAS("Matern52")
+        g.fit(data.x, data.y, None, "kmeans", "L-BFGS-B", ard=ard, shared_kernel=True, max_iter=1000)
+        m = g.models[0]
+        obj = Objective("Matern52", data.x, data.y, ard=ard, space="softplus", priors=True)
+        ls0 = np.full(8 if ard else 1, np.mean(np.abs(data.x)))
+        r = fit_lbfgs(obj, obj.unconstrain(np.concatenate([[1.0, 1.0], ls0])), max_iter=1000)
+        want = obj.constrain(r.x)
+        got = np.concatenate([[m.kernel.variance.numpy(), m.likelihood.variance.numpy()], np.atleast_1d(m.kernel.lengthscales.numpy())])
+        np.testing.assert_allclose(got, want, rtol=1e-4)  # north_star: optimum within 1e-4 relative from the same start
+        mean, var = g.predict(data.x_test)
+        assert mean.shape == (50, 3) and var.shape == (50, 3) and np.all(var > 0)
+        # persistence round trip (pipeline.py:254-255)
+        path = tmp_path / f"gpr_{ard}.pkl"
+        g.to_file(path)
+        g2 = GPRAS.from_file(path)
+        m2, v2 = g2.predict(data.x_test)
+        np.testing.assert_allclose(m2, mean, rtol=1e-12)
+        np.testing.assert_allclose(v2, var, rtol=1e-12)
+        import pickle
+
+        d = pickle.load(open(path, "rb"))
+        assert {"kernel", "data", "n_inducing", "models"} <= set(d) and set(d["data"]) == {"x", "y"}
+
+
+def test_gpras_per_column_models_like_the_reference(cuda):
+    from gpras_b200 import GPRAS
+    from gpras_b200.synth import make_gp_data
+    from oracle.exact_gp import Theta, predict
+
+    data = make_gp_data(150, 4, 3, 20, seed=5)
+    g = GPRAS("RBF")
+    g.fit(data.x, data.y, None, "kmeans", "adam", max_iter=5)
+    assert len(g.models) == 3 and g.models[0] is not g.models[1]
+    assert g.models[0].inducing_variable.Z.shape == (150, 4)  # pipeline.py:115 reads this
+    mean, var = g.predict(data.x_test)
+    assert mean.shape == (20, 3)
+    for i, m in enumerate(g.models):
+        om, ov = predict("RBF", data.x, data.y[:, i : i + 1],
+                         Theta(m.kernel.variance.numpy(), m.likelihood.variance.numpy(), m.kernel.lengthscales.numpy()), data.x_test)
+        np.testing.assert_allclose(mean[:, i : i + 1], om, rtol=MEAN_RTOL, atol=1e-9)
+        np.testing.assert_allclose(np.sqrt(var[:, i : i + 1]), np.sqrt(ov), rtol=STD_RTOL)
+
+
+# ---- full-size, size-independent properties (BASELINE config 2 / 3 sizes) ----------------------------
+@pytest.mark.parametrize("n,d,p", [(2048, 16, 16), (8192, 32, 32)])
+def test_full_size_properties(cuda, n, d, p):
+    from gpras_b200.engine import ExactGP
+    from gpras_b200.synth import fixed_theta, make_gp_data
+
+    data = make_gp_data(n, d, p, 256, seed=0)
+    v, s, ls = fixed_theta(d, True)
+    gp = ExactGP("Matern52", n, d, p)
+    gp.set_data(data.x, data.y)
+    th = gp.theta_vector(v, s, ls)
+    lml, g = gp.lml_grad(th)
+    assert np.isfinite(lml) and np.all(np.isfinite(g))
+    # (1) repeatability: deterministic reductions give bit-identical results
+    lml2, g2 = gp.lml_grad(th)
+    assert lml2 == lml and np.array_equal(g, g2)
+    # (2) directional derivative of the GPU LML agrees with the GPU gradient
+    rng = np.random.default_rng(0)
+    dirn = rng.standard_normal(2 + d)
+    dirn /= np.linalg.norm(dirn)
+    eps = 1e-5
+    up, _ = gp.lml_grad(th * np.exp(eps * dirn), want_grad=False)
+    dn, _ = gp.lml_grad(th * np.exp(-eps * dirn), want_grad=False)
+    fd = (up - dn) / (2 * eps)
+    assert abs(fd - g @ dirn) <= 1e-5 * max(1.0, abs(fd))
+    # (3) factor identities on sampled rows:  (L L^T)[rows] == K[rows],  W L == I,  Kinv K == I
+    lml, g = gp.lml_grad(th)  # leaves L, W; Kinv was overwritten by alpha alpha^T - P Kinv, so use W^T W
+    L = np.tril(gp.get_matrix(1))
+    W = np.tril(gp.get_matrix(2))
+    rows = rng.choice(n, 16, replace=False)
+    from oracle.kernels import cov
+
+    krows = cov("Matern52", data.x[rows], data.x, v, ls)
+    krows[np.arange(16), rows] += s
+    assert _rel(L[rows] @ L.T, krows) < 1e-11
+    assert _rel(W[rows] @ L, np.eye(n)[rows]) < 1e-9
+    # (4) posterior at the training inputs: mean = y - noise * alpha, variance below the prior, above the noise floor
+    gp.condition(th)
+    mean, var = gp.predict(data.x[:256])
+    alpha = gp.get_matrix(4)
+    np.testing.assert_allclose(mean, data.y[:256] - s * alpha[:256], rtol=1e-8, atol=1e-8)
+    assert np.all(var > s * (1 - 1e-9)) and np.all(var < v + s)
+    gp.close()

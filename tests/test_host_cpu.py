@@ -1,0 +1,178 @@
+"""CPU: host logic of the drop-in (parameters, recipes, persistence keys) and the C-ABI surface.
+No compute call reaches the library here: without a GPU the ABI must refuse loudly, never fall back."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from gpras_b200 import _lib, gpr
+from gpras_b200.synth import make_gp_data
+from oracle.exact_gp import Objective, Theta, lml_and_grad
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+class OracleBackedModel(gpr.ExactModel):
+    """ExactModel whose device evaluation is replaced by the CPU oracle -- lets the recipes, chain rule and
+    restart sharding be tested on a box without a GPU.  Test infrastructure only."""
+
+    class _Slot:
+        def __init__(self, outer):
+            self.outer = outer
+
+        def acquire(self, model):
+            return self
+
+        def lml_grad(self, theta, want_grad=True):
+            m = self.outer
+            lml, gv, gn, gl = lml_and_grad(m.kernel.name, m.x, m.y, Theta(theta[0], theta[1], theta[2:]), want_grad=want_grad)
+            return lml, (np.concatenate([[gv, gn], gl]) if want_grad else None)
+
+    def __init__(self, kernel_name, x, y, lengthscales, priors=True):
+        super().__init__(kernel_name, x, y, lengthscales, slot=None, priors=priors)
+        self._slot = OracleBackedModel._Slot(self)
+
+
+def test_module_surface_matches_reference():
+    # gpras/gpr.py:21-41,206-214
+    assert set(gpr.KERNEL_FACTORY) == {"Matern12", "Matern32", "Matern52", "RBF", "Linear", "Polynomial", "Periodic", "Exponential"}
+    assert set(gpr.OPTIMIZERS) == {"two-stage", "three-stage", "adam", "adadelta", "L-BFGS-B", "stochastic", "diffential_evolution"}
+    for name in ("GPRAS", "KernelType", "OptimizerType", "InductionInitializerType"):
+        assert hasattr(gpr, name)
+    with pytest.raises(KeyError):
+        gpr.GPRAS("NoSuchKernel")
+    g = gpr.GPRAS("RBF")
+    assert g.kernel_str == "RBF" and g.models == [] and g.x is None and g.y is None
+
+
+def test_parameter_transform_roundtrip_and_floor():
+    p = gpr.Parameter(0.37)
+    assert abs(p.numpy() - 0.37) < 1e-15
+    q = gpr.Parameter(1.0, lower=gpr.NOISE_FLOOR)
+    assert abs(q.numpy() - 1.0) < 1e-15
+    q.unconstrained[:] = -50.0
+    assert q.numpy() >= gpr.NOISE_FLOOR
+    r = gpr.Parameter(np.array([0.5, 2.0, 7.0]))
+    np.testing.assert_allclose(r.numpy(), [0.5, 2.0, 7.0], rtol=1e-15)
+    r.assign(np.array([1.0, 1.0, 1.0]))
+    np.testing.assert_allclose(r.numpy(), 1.0)
+
+
+def test_loss_and_grad_matches_oracle_objective():
+    d = make_gp_data(50, 3, 1, seed=1)
+    for ard in (False, True):
+        ls0 = np.full(3, 1.4) if ard else 1.4
+        m = OracleBackedModel("Matern52", d.x, d.y, ls0)
+        m.kernel.variance.assign(1.3)
+        m.likelihood.variance.assign(0.07)
+        loss, g = m.loss_and_grad()
+        obj = Objective("Matern52", d.x, d.y, ard=ard, space="softplus", priors=True)
+        u = obj.unconstrain(np.concatenate([[1.3, 0.07], np.atleast_1d(ls0)]))
+        f, go = obj(u)
+        assert abs(loss - f) <= 1e-12 * abs(f)
+        np.testing.assert_allclose(g, go, rtol=1e-10, atol=1e-12)
+        assert abs(m.training_loss() - f) <= 1e-12 * abs(f)
+
+
+def test_recipes_decrease_the_loss_and_respect_trainable_sets():
+    d = make_gp_data(60, 2, 1, seed=2)
+    for method, kw in [("adam", dict(max_iter=30)), ("adadelta", dict(max_iter=5)), ("L-BFGS-B", dict(max_iter=50)),
+                       ("two-stage", dict(max_iter=20)), ("three-stage", dict(max_iter=30)),
+                       ("stochastic", dict(n_starts=2, iter_initial=3, iter_final=20, seed=0)),
+                       ("diffential_evolution", dict(popsize=3, max_iter=2, seed=0))]:
+        m = OracleBackedModel("RBF", d.x, d.y, float(np.mean(np.abs(d.x))))
+        before = m.training_loss()
+        gpr.OPTIMIZERS[method](m, **kw)
+        after = m.training_loss()
+        assert np.isfinite(after)
+        if method not in ("adadelta",):
+            assert after < before, method
+        if method != "diffential_evolution":  # the reference leaves the hyperparameters non-trainable after DE (gpr.py:48-49)
+            assert all(p.trainable for p in m.parameters), method
+
+
+def test_adam_early_stopping_rule():
+    # a flat objective stops after patience + 1 = 52 evaluations (gpr.py:159-173)
+    class Flat:
+        n = 0
+
+        def get_u(self):
+            return np.zeros(2)
+
+        def set_u(self, u):
+            pass
+
+        def loss_and_grad(self, u=None):
+            Flat.n += 1
+            return 1.0, np.zeros(2)
+
+    gpr._optimize_adam(Flat(), 1000)
+    assert Flat.n == 52
+
+
+def test_multi_start_last_start_wins_like_the_reference(monkeypatch):
+    monkeypatch.setattr(gpr, "_optimize_bfgs", lambda model, max_iter: None)  # isolate the start selection
+    d = make_gp_data(40, 2, 1, seed=3)
+    starts = np.array([[1.0, 1.0, 0.1], [0.2, 3.0, 0.5]])
+    m = OracleBackedModel("RBF", d.x, d.y, 1.0)
+    gpr._optimize_multi_start(m, n_starts=2, iter_initial=0, iter_final=0, starts=starts)
+    assert abs(m.kernel.variance.numpy() - 0.2) < 1e-12  # last start (reference quirk, gpr.py:86,96)
+    m2 = OracleBackedModel("RBF", d.x, d.y, 1.0)
+    gpr._optimize_multi_start(m2, n_starts=2, iter_initial=0, iter_final=0, starts=starts, pick_best=True)
+    l0 = lml_and_grad("RBF", d.x, d.y, Theta(1.0, 0.1, 1.0), want_grad=False)[0]
+    l1 = lml_and_grad("RBF", d.x, d.y, Theta(0.2, 0.5, 3.0), want_grad=False)[0]
+    assert abs(m2.kernel.variance.numpy() - (1.0 if l0 > l1 else 0.2)) < 1e-12
+
+
+def test_create_inducing_grid_and_kmeans():
+    g = gpr.GPRAS("RBF")
+    x = np.random.default_rng(0).standard_normal((100, 3))
+    z = g._create_inducing(x, 7, "grid")
+    assert z.shape == (7, 3)
+    np.testing.assert_allclose(z[0], x.min(axis=0))
+    np.testing.assert_allclose(z[-1], x.max(axis=0))
+    zk = g._create_inducing(x, 5, "kmeans")
+    assert zk.shape == (5, 3) and zk.dtype == np.float64
+
+
+def test_unsupported_kernels_fail_like_the_reference():
+    g = gpr.GPRAS("Linear")
+    with pytest.raises(NotImplementedError):
+        g._init_models(np.zeros((4, 2)), np.zeros((4, 1)), None)
+
+
+# ---- C ABI surface ---------------------------------------------------------------------------
+def test_header_symbols_are_exported_and_bound(lib):
+    header = (ROOT / "include" / "gpras_b200.h").read_text()
+    declared = set(re.findall(r"\b(gpras_[a-z0-9_]+)\s*\(", header))
+    declared.discard("gpras_gp")
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert declared <= exported, declared - exported
+    assert lib.gpras_abi_version() == 1
+
+
+def test_library_contains_dmma_and_no_cpu_fallback(lib):
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "DMMA.8x8x4" in sass and "sm_100a" in sass
+    if lib.gpras_device_count() == 0:
+        h = C.c_void_p()
+        assert lib.gpras_gp_create(C.byref(h), 0, 0, 8, 2, 1) == -2  # GPRAS_E_CUDA, loudly
+        assert b"no CPU fallback" in lib.gpras_last_error()
+        from gpras_b200.engine import ExactGP
+
+        with pytest.raises(_lib.GprasError):
+            ExactGP("RBF", 8, 2, 1)
+
+
+def test_abi_argument_validation(lib):
+    h = C.c_void_p()
+    assert lib.gpras_gp_create(C.byref(h), 0, 9, 8, 2, 1) == -1
+    assert lib.gpras_gp_create(C.byref(h), 0, 0, 0, 2, 1) == -1
+    assert lib.gpras_gp_create(C.byref(h), 0, 0, 8, 65, 1) == -1
+    assert lib.gpras_dgemm_tiles(None, 0, 0, None, 0, None, 0, None, 0, 100, 128, 16, 1.0, 0.0) == -1
+    assert lib.gpras_dpotrf(None, None, 0, None, 0, 100, None, None) == -1
