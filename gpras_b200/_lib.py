@@ -42,7 +42,7 @@ SYMBOLS = {
     "gpras_gp_set_stage_timing": (C.c_int, [vp, C.c_int]),
     "gpras_dgemm_tiles": (
         C.c_int,
-        [vp, C.c_int, C.c_int, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double],
+        [vp, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double],
     ),
     "gpras_dpotrf": (C.c_int, [vp, vp, C.c_long, vp, C.c_long, C.c_int, vp, vp]),
     "gpras_dtrtri": (C.c_int, [vp, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]),

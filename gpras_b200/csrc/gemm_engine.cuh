@@ -6,25 +6,47 @@
 //
 //   C[i, j] (op)= alpha * sum_{k in [k_begin, k_end)} A(i, k) * B(k, j)
 //
-// * CTA tile 128 x 128, 8 warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA.8x8x4 accumulators.
-// * Operand tiles stream global -> shared with 16-byte cp.async in a 4-stage ring, BK = 16.
+// * 256 threads = 8 warps arranged WARPS_M x WARPS_N over a BM x BN CTA tile; every warp owns
+//   MF x NF DMMA.8x8x4 accumulators.  Three tile shapes are instantiated:
+//       CfgL 128x128, warp 64x32, 4 stages, 1 CTA/SM  -- long-k products (LAUUM, TRTRI, predictor)
+//       CfgS 128x64,  warp 32x32, 3 stages, 2 CTA/SM  -- short-k rank-128 updates of the Cholesky, where a
+//                                                        second resident CTA hides prologue / epilogue
+//       CfgN 128x32,  warp 16x32, 4 stages, 2 CTA/SM  -- skinny right-hand sides (P <= 32 columns), split-k
+//       CfgP 64x128,  warp 32x32, 3 stages, 2 CTA/SM  -- the in-place Cholesky panel L21 = A21 W_jj^T
+// * Operand tiles stream global -> shared with 16-byte cp.async in a multi-stage ring, BK = 16.
 // * A is either row-major A[i][k] or k-major A[k][i]; B either n-major B[j][k] or k-major B[k][j];
 //   shared tiles are padded (+4 doubles) so every fragment LDS.64 is bank-conflict free.
 // * Triangular structure is exploited at tile granularity by clipping the k range per tile
 //   (k_begin / k_end modes) and by launching only the lower-triangular tiles of C (tri mode).
 //   Operand tiles that straddle the diagonal must hold explicit zeros in their dead half.
+// * beta != 0 initialises the accumulators from C before the k loop, so the read of C overlaps the
+//   pipeline prologue instead of sitting in the epilogue.
+// * k_split > 0 cuts the k range into chunks handled by blockIdx.z, each writing its own partial C
+//   (stride splitC); a fixed-order reduction kernel adds them, keeping results bitwise repeatable.
 // * All extents are multiples of the tile sizes: the host pads (identity on the diagonal).
 #pragma once
 #include "common.cuh"
 
 namespace gpras {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
-constexpr int LD_RM = BK + 4;             // [128][20] row / n-major tile (k contiguous)
-constexpr int LD_KM = BM + 4;             // [16][132] k-major tile (m or n contiguous)
-constexpr int TILE_DOUBLES = 128 * LD_RM;  // 2560 >= 16 * 132
-constexpr int STAGE_DOUBLES = 2 * TILE_DOUBLES;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);  // 160 KiB
+constexpr int BK = 16, GEMM_THREADS = 256;
+constexpr int LD_RM = BK + 4;  // row / n-major tile [rows][20] (k contiguous)
+
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int MF = WM / 8, NF = WN / 8;
+  static constexpr int A_DOUBLES = BM * LD_RM;  // >= 16 * (BM + 4)
+  static constexpr int B_DOUBLES = BN * LD_RM;  // >= 16 * (BN + 4)
+  static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
+  static_assert(WARPS_M * WARPS_N == 8, "8 warps per CTA");
+};
+using CfgL = TileCfg<128, 128, 64, 32, 4, 1>;
+using CfgS = TileCfg<128, 64, 32, 32, 3, 2>;
+using CfgN = TileCfg<128, 32, 16, 32, 4, 2>;
+using CfgP = TileCfg<64, 128, 32, 32, 3, 2>;   // in-place Cholesky panel: full 128-column width per CTA (no tri mode)
 
 enum KBegin { KB_ZERO = 0, KB_TI = 1, KB_TJ = 2 };   // k_begin = 0 | ti*BM | tj*BN
 enum KEnd { KE_FULL = 0, KE_TI = 1, KE_TJ = 2 };     // k_end   = K | (ti+1)*BM | (tj+1)*BN
@@ -37,51 +59,57 @@ struct GemmDesc {
   const double* bias;   // EPI_BIAS: per-column bias (length n_tiles*BN)
   long lda, ldb, ldc;
   long batchA, batchB, batchC;  // element strides between batch entries (grid.y)
+  long splitC;          // element stride between k-split partial outputs (grid.z)
   int m_tiles, n_tiles;
   int K;                // multiple of BK
+  int k_split;          // 0, or chunk length (multiple of BK) per blockIdx.z
   int kb_mode, ke_mode;
-  int tri;              // 1: only tiles with tj <= ti (m_tiles == n_tiles)
-  int reverse;          // 1: heaviest-last orders are reversed (LPT scheduling)
+  int tri;              // 1: only tiles whose columns start at or below the row tile's last row
+  int reverse;          // 1: launch order reversed (heaviest tiles first for LPT scheduling)
   int epilogue;
   double alpha, beta;
 };
 
-template <bool KMAJOR>
+// rows x 16 tile, global -> shared.  Row-major: rows of 128 B; k-major: 16 rows of ROWS doubles.
+template <bool KMAJOR, int ROWS>
 __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ g, long ld, int tid) {
-  // g points at the tile origin: row-major -> (row0, k0); k-major -> (k0, col0).
-  if (!KMAJOR) {
+  constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks in the tile
+  constexpr int PER_THREAD = (CHUNKS + GEMM_THREADS - 1) / GEMM_THREADS;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      int c = tid + GEMM_THREADS * q;
-      int row = c >> 3, kc = c & 7;
-      cp_async16(s + row * LD_RM + 2 * kc, g + (long)row * ld + 2 * kc);
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      int c = tid + GEMM_THREADS * q;
-      int kr = c >> 6, mc = c & 63;
-      cp_async16(s + kr * LD_KM + 2 * mc, g + (long)kr * ld + 2 * mc);
+  for (int q = 0; q < PER_THREAD; q++) {
+    const int c = tid + GEMM_THREADS * q;
+    if (CHUNKS % GEMM_THREADS == 0 || c < CHUNKS) {
+      if (!KMAJOR) {
+        const int row = c >> 3, kc = c & 7;
+        cp_async16(s + row * LD_RM + 2 * kc, g + (long)row * ld + 2 * kc);
+      } else {
+        constexpr int CPR = ROWS / 2;  // chunks per k row
+        const int kr = c / CPR, mc = c - kr * CPR;
+        cp_async16(s + kr * (ROWS + 4) + 2 * mc, g + (long)kr * ld + 2 * mc);
+      }
     }
   }
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmDesc d) {
+template <typename Cfg, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(const GemmDesc d) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, MF = Cfg::MF, NF = Cfg::NF, STAGES = Cfg::STAGES;
+  constexpr int LDA_KM = BM + 4, LDB_KM = BN + 4, RATIO = BM >= BN ? BM / BN : 1;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int wm = (warp / Cfg::WARPS_N) * Cfg::WM, wn = (warp % Cfg::WARPS_N) * Cfg::WN;
 
   // ---- tile coordinates ----
   int t = blockIdx.x;
   if (d.reverse) t = gridDim.x - 1 - t;
   int ti, tj;
   if (d.tri) {
-    ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((long)(ti + 1) * (ti + 2) / 2 <= t) ti++;
-    while ((long)ti * (ti + 1) / 2 > t) ti--;
-    tj = t - (int)((long)ti * (ti + 1) / 2);
+    // row ti holds RATIO*(ti+1) column tiles; prefix = RATIO*ti*(ti+1)/2
+    ti = (int)((sqrt(8.0 * (double)t / RATIO + 1.0) - 1.0) * 0.5);
+    while ((long)RATIO * (ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while ((long)RATIO * ti * (ti + 1) / 2 > t) ti--;
+    tj = t - (int)((long)RATIO * ti * (ti + 1) / 2);
   } else {
     ti = t / d.n_tiles;
     tj = t - ti * d.n_tiles;
@@ -89,76 +117,97 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmDe
   const long by = blockIdx.y;
   const double* __restrict__ A = d.A + by * d.batchA;
   const double* __restrict__ B = d.B + by * d.batchB;
-  double* __restrict__ C = d.C + by * d.batchC;
+  double* __restrict__ C = d.C + by * d.batchC + (long)blockIdx.z * d.splitC;
 
   int k_begin = d.kb_mode == KB_TI ? ti * BM : (d.kb_mode == KB_TJ ? tj * BN : 0);
   int k_end = d.ke_mode == KE_TI ? (ti + 1) * BM : (d.ke_mode == KE_TJ ? (tj + 1) * BN : d.K);
   if (k_end > d.K) k_end = d.K;
-  const int nk = k_end > k_begin ? (k_end - k_begin) / BK : 0;
+  k_begin = k_begin / BK * BK;
+  if (d.k_split > 0) {
+    const int lo = (int)blockIdx.z * d.k_split, hi = lo + d.k_split;
+    if (k_begin < lo) k_begin = lo;
+    if (k_end > hi) k_end = hi;
+  }
+  const int nk = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
 
   const double* gA = A_KMAJOR ? A + (long)k_begin * d.lda + (long)ti * BM : A + (long)ti * BM * d.lda + k_begin;
   const double* gB = B_KMAJOR ? B + (long)k_begin * d.ldb + (long)tj * BN : B + (long)tj * BN * d.ldb + k_begin;
   const long stepA = A_KMAJOR ? (long)BK * d.lda : BK;
   const long stepB = B_KMAJOR ? (long)BK * d.ldb : BK;
 
-  double acc[8][4][2];
-#pragma unroll
-  for (int f = 0; f < 8; f++)
-#pragma unroll
-    for (int h = 0; h < 4; h++) acc[f][h][0] = acc[f][h][1] = 0.0;
-
   // ---- prologue: fill STAGES-1 slots ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
     if (s < nk) {
-      double* sA = smem + s * STAGE_DOUBLES;
-      load_tile<A_KMAJOR>(sA, gA + s * stepA, d.lda, tid);
-      load_tile<B_KMAJOR>(sA + TILE_DOUBLES, gB + s * stepB, d.ldb, tid);
+      double* sA = smem + s * Cfg::STAGE_DOUBLES;
+      load_tile<A_KMAJOR, BM>(sA, gA + s * stepA, d.lda, tid);
+      load_tile<B_KMAJOR, BN>(sA + Cfg::A_DOUBLES, gB + s * stepB, d.ldb, tid);
     }
     cp_async_commit();
+  }
+
+  // ---- accumulators; beta != 0 folds C in up front (overlaps the prologue loads) ----
+  double acc[MF][NF][2];
+  double* Ct = C + (long)(ti * BM + wm) * d.ldc + (long)tj * BN + wn;
+  const double alpha = d.alpha;
+  if (d.epilogue == EPI_STORE && d.beta != 0.0) {
+    const double scale = d.beta / alpha;
+#pragma unroll
+    for (int f = 0; f < MF; f++)
+#pragma unroll
+      for (int h = 0; h < NF; h++) {
+        const double2 o = *reinterpret_cast<const double2*>(Ct + (long)(8 * f + g) * d.ldc + 8 * h + 2 * q);
+        acc[f][h][0] = scale * o.x;
+        acc[f][h][1] = scale * o.y;
+      }
+  } else {
+#pragma unroll
+    for (int f = 0; f < MF; f++)
+#pragma unroll
+      for (int h = 0; h < NF; h++) acc[f][h][0] = acc[f][h][1] = 0.0;
   }
 
   for (int kt = 0; kt < nk; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     {
-      int nx = kt + STAGES - 1;
+      const int nx = kt + STAGES - 1;
       if (nx < nk) {
-        double* sA = smem + (nx % STAGES) * STAGE_DOUBLES;
-        load_tile<A_KMAJOR>(sA, gA + nx * stepA, d.lda, tid);
-        load_tile<B_KMAJOR>(sA + TILE_DOUBLES, gB + nx * stepB, d.ldb, tid);
+        double* sA = smem + (nx % STAGES) * Cfg::STAGE_DOUBLES;
+        load_tile<A_KMAJOR, BM>(sA, gA + nx * stepA, d.lda, tid);
+        load_tile<B_KMAJOR, BN>(sA + Cfg::A_DOUBLES, gB + nx * stepB, d.ldb, tid);
       }
       cp_async_commit();
     }
-    const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
-    const double* sB = sA + TILE_DOUBLES;
+    const double* sA = smem + (kt % STAGES) * Cfg::STAGE_DOUBLES;
+    const double* sB = sA + Cfg::A_DOUBLES;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ks++) {
-      double a[8], b[4];
+      double a[MF], b[NF];
 #pragma unroll
-      for (int f = 0; f < 8; f++)
-        a[f] = A_KMAJOR ? sA[(4 * ks + q) * LD_KM + wm + 8 * f + g] : sA[(wm + 8 * f + g) * LD_RM + 4 * ks + q];
+      for (int f = 0; f < MF; f++)
+        a[f] = A_KMAJOR ? sA[(4 * ks + q) * LDA_KM + wm + 8 * f + g] : sA[(wm + 8 * f + g) * LD_RM + 4 * ks + q];
 #pragma unroll
-      for (int h = 0; h < 4; h++)
-        b[h] = B_KMAJOR ? sB[(4 * ks + q) * LD_KM + wn + 8 * h + g] : sB[(wn + 8 * h + g) * LD_RM + 4 * ks + q];
+      for (int h = 0; h < NF; h++)
+        b[h] = B_KMAJOR ? sB[(4 * ks + q) * LDB_KM + wn + 8 * h + g] : sB[(wn + 8 * h + g) * LD_RM + 4 * ks + q];
 #pragma unroll
-      for (int f = 0; f < 8; f++)
+      for (int f = 0; f < MF; f++)
 #pragma unroll
-        for (int h = 0; h < 4; h++) dmma(acc[f][h][0], acc[f][h][1], a[f], b[h]);
+        for (int h = 0; h < NF; h++) dmma(acc[f][h][0], acc[f][h][1], a[f], b[h]);
     }
   }
   cp_async_wait<0>();
 
   // ---- epilogue ----
   if (d.epilogue == EPI_COLSUMSQ) {
-    // column sums of squares of this 128 x 128 tile -> C[ti * ldc + tj*BN + col]
+    // column sums of squares of this BM x BN tile -> C[ti * ldc + tj*BN + col]
     __syncthreads();
-    double* red = smem;  // [2][128]
+    double* red = smem;  // [WARPS_M][BN]
 #pragma unroll
-    for (int h = 0; h < 4; h++) {
+    for (int h = 0; h < NF; h++) {
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int f = 0; f < 8; f++) {
+      for (int f = 0; f < MF; f++) {
         s0 += acc[f][h][0] * acc[f][h][0];
         s1 += acc[f][h][1] * acc[f][h][1];
       }
@@ -168,20 +217,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmDe
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       }
       if (g == 0) {
-        red[(warp >> 2) * 128 + wn + 8 * h + 2 * q] = s0;
-        red[(warp >> 2) * 128 + wn + 8 * h + 2 * q + 1] = s1;
+        red[(warp / Cfg::WARPS_N) * BN + wn + 8 * h + 2 * q] = s0;
+        red[(warp / Cfg::WARPS_N) * BN + wn + 8 * h + 2 * q + 1] = s1;
       }
     }
     __syncthreads();
-    if (tid < 128) C[(long)ti * d.ldc + (long)tj * BN + tid] = d.alpha * d.alpha * (red[tid] + red[128 + tid]);
+    if (tid < BN) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < Cfg::WARPS_M; r++) s += red[r * BN + tid];
+      C[(long)ti * d.ldc + (long)tj * BN + tid] = alpha * alpha * s;
+    }
     return;
   }
-  double* Ct = C + (long)(ti * BM + wm) * d.ldc + (long)tj * BN + wn;
-  const double alpha = d.alpha, beta = d.beta;
 #pragma unroll
-  for (int f = 0; f < 8; f++) {
+  for (int f = 0; f < MF; f++) {
 #pragma unroll
-    for (int h = 0; h < 4; h++) {
+    for (int h = 0; h < NF; h++) {
       double2* p = reinterpret_cast<double2*>(Ct + (long)(8 * f + g) * d.ldc + 8 * h + 2 * q);
       double2 v;
       v.x = alpha * acc[f][h][0];
@@ -190,14 +242,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmDe
         const double2 bb = *reinterpret_cast<const double2*>(d.bias + (long)tj * BN + wn + 8 * h + 2 * q);
         v.x += bb.x;
         v.y += bb.y;
-      } else if (beta != 0.0) {
-        const double2 o = *p;
-        v.x += beta * o.x;
-        v.y += beta * o.y;
       }
       *p = v;
     }
   }
+}
+
+// out[e] = sum_z part[z * stride + e]  (fixed order -> deterministic), e < count
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, long stride, int nz, long count,
+                                     double* __restrict__ out) {
+  long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  double s = 0.0;
+  for (int z = 0; z < nz; z++) s += part[(long)z * stride + e];
+  out[e] = s;
 }
 
 }  // namespace gpras

@@ -220,13 +220,21 @@ __global__ void __launch_bounds__(PT_THREADS) grad_kernel(const double* __restri
   }
 }
 
-// out[c] = sum_r part[r][c] in fixed row order (deterministic); one thread per column.
+// out[c] = sum_r part[r][c]: one 256-thread CTA per column; strided partial sums then a fixed-shape tree, so the
+// result is bitwise repeatable.
 __global__ void colsum_kernel(const double* __restrict__ part, int rows, int cols, long ld, double* __restrict__ out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double red[256];
+  const int c = blockIdx.x;
   if (c >= cols) return;
   double s = 0.0;
-  for (int r = 0; r < rows; r++) s += part[(long)r * ld + c];
-  out[c] = s;
+  for (int r = threadIdx.x; r < rows; r += 256) s += part[(long)r * ld + c];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = red[0];
 }
 
 // Per-CTA sum of squares of a (rows x cols) block with pitch ld -> part[blockIdx.x].

@@ -60,10 +60,14 @@ int prepare_device() {
   CU(cudaGetDevice(&dev));
   if (dev < 64 && g_prepared[dev]) return 0;
   int r;
-  if ((r = opt_in_smem(gemm_tile_kernel<false, false>, GEMM_SMEM_BYTES))) return r;
-  if ((r = opt_in_smem(gemm_tile_kernel<false, true>, GEMM_SMEM_BYTES))) return r;
-  if ((r = opt_in_smem(gemm_tile_kernel<true, false>, GEMM_SMEM_BYTES))) return r;
-  if ((r = opt_in_smem(gemm_tile_kernel<true, true>, GEMM_SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgL, false, false>, CfgL::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgL, false, true>, CfgL::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgL, true, false>, CfgL::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgL, true, true>, CfgL::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgS, false, false>, CfgS::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgP, false, false>, CfgP::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgN, false, true>, CfgN::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgN, true, true>, CfgN::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(leaf_potrf_inv_kernel, LEAF_SMEM_BYTES))) return r;
   if ((r = prepare_kid<K_RBF>())) return r;
   if ((r = prepare_kid<K_MATERN12>())) return r;
@@ -84,45 +88,150 @@ GemmDesc make_desc(const double* A, long lda, const double* B, long ldb, double*
   return d;
 }
 
-int launch_gemm(cudaStream_t s, bool akm, bool bkm, const GemmDesc& d, int batch, int* launches) {
-  if (d.m_tiles <= 0 || d.n_tiles <= 0 || batch <= 0) return 0;
-  long tiles = d.tri ? (long)d.m_tiles * (d.m_tiles + 1) / 2 : (long)d.m_tiles * d.n_tiles;
-  dim3 grid((unsigned)tiles, (unsigned)batch);
-  if (!akm && !bkm)
-    gemm_tile_kernel<false, false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(d);
-  else if (!akm && bkm)
-    gemm_tile_kernel<false, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(d);
-  else if (akm && !bkm)
-    gemm_tile_kernel<true, false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(d);
-  else
-    gemm_tile_kernel<true, true><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(d);
-  if (launches) ++*launches;
+enum TileShape { SHAPE_L = 0, SHAPE_S = 1, SHAPE_N = 2, SHAPE_P = 3 };
+
+template <typename Cfg, bool AKM, bool BKM>
+int launch_cfg(cudaStream_t s, const GemmDesc& d, int batch, int nz) {
+  constexpr int ratio = Cfg::BM / Cfg::BN;
+  long tiles = d.tri ? (long)ratio * d.m_tiles * (d.m_tiles + 1) / 2 : (long)d.m_tiles * d.n_tiles;
+  dim3 grid((unsigned)tiles, (unsigned)batch, (unsigned)nz);
+  gemm_tile_kernel<Cfg, AKM, BKM><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(d);
   CU(cudaGetLastError());
   return 0;
 }
 
+// m_tiles counts BM-row tiles (128; 64 for SHAPE_P); n_tiles counts BN-column tiles of the chosen shape.
+int launch_gemm(cudaStream_t s, bool akm, bool bkm, const GemmDesc& d, int batch, int* launches, int shape = SHAPE_L,
+                int nz = 1) {
+  if (d.m_tiles <= 0 || d.n_tiles <= 0 || batch <= 0) return 0;
+  if (launches) ++*launches;
+  if (shape == SHAPE_L) {
+    if (!akm && !bkm) return launch_cfg<CfgL, false, false>(s, d, batch, nz);
+    if (!akm && bkm) return launch_cfg<CfgL, false, true>(s, d, batch, nz);
+    if (akm && !bkm) return launch_cfg<CfgL, true, false>(s, d, batch, nz);
+    return launch_cfg<CfgL, true, true>(s, d, batch, nz);
+  }
+  if (shape == SHAPE_S) {
+    if (!akm && !bkm) return launch_cfg<CfgS, false, false>(s, d, batch, nz);
+    return fail(GPRAS_E_ARG, "CfgS is instantiated for the NT layout only");
+  }
+  if (shape == SHAPE_P) {
+    if (!akm && !bkm && !d.tri) return launch_cfg<CfgP, false, false>(s, d, batch, nz);
+    return fail(GPRAS_E_ARG, "CfgP is instantiated for the NT layout, non-triangular, only");
+  }
+  if (!akm && bkm) return launch_cfg<CfgN, false, true>(s, d, batch, nz);
+  if (akm && bkm) return launch_cfg<CfgN, true, true>(s, d, batch, nz);
+  return fail(GPRAS_E_ARG, "CfgN is instantiated for k-major B only");
+}
+
+// Skinny product with split-k: partial results in `part` (nz slabs of rows x ldc), reduced in fixed order into C.
+int launch_skinny(cudaStream_t s, bool akm, GemmDesc d, double* part, int rows, int* launches) {
+  int ks = d.K / 16;
+  ks = (ks + 127) / 128 * 128;
+  if (ks < 512) ks = 512;
+  const int nz = (d.K + ks - 1) / ks;
+  double* out = d.C;
+  const long slab = (long)rows * d.ldc;
+  d.k_split = ks;
+  d.splitC = slab;
+  d.C = part;
+  int r = launch_gemm(s, akm, true, d, 1, launches, SHAPE_N, nz);
+  if (r) return r;
+  splitk_reduce_kernel<<<(unsigned)((slab + 255) / 256), 256, 0, s>>>(part, slab, nz, slab, out);
+  if (launches) ++*launches;
+  CU(cudaGetLastError());
+  return 0;
+}
+constexpr int SKINNY_MAX_SLABS = 16;
+
 // ---- dense building blocks -------------------------------------------------------------------
-// Right-looking blocked Cholesky, panel width 128: leaf (potrf + inverse of the diagonal block),
-// panel L21 = A21 W_jj^T on the DMMA engine, trailing SYRK on the DMMA engine.
-int potrf_impl(cudaStream_t s, double* A, long lda, double* W, long ldw, int n, double* logdet_parts, int* info,
-               int* launches) {
+// Side stream + events for the one-panel look-ahead of the Cholesky.
+struct LookAhead {
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev;
+  int ensure(size_t n) {
+    if (!side) {
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));  // `hi` is the greatest priority
+    }
+    while (ev.size() < n) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev.push_back(e);
+    }
+    return 0;
+  }
+  void destroy() {
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+    if (side) cudaStreamDestroy(side);
+    side = nullptr;
+  }
+};
+
+// Right-looking blocked Cholesky, panel width 128, with one panel of look-ahead on a high-priority side stream:
+//   leaf   (1 CTA)   potrf + inverse of the diagonal block  -> L_jj, W_jj
+//   panel  (CfgP)    L21 = A21 W_jj^T, in place
+//   col    (CfgS)    block column j+1 of the trailing matrix -= panel_j panel_j^T        [side stream]
+//   rest   (CfgS)    the trailing triangle right of block column j+1 -= panel_j panel_j^T  [main stream]
+// so leaf(j+1) and panel(j+1) run while rest(j) occupies the machine.
+int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, long ldw, int n, double* logdet_parts,
+               int* info, int* launches) {
   const int nt = n / 128;
-  for (int jb = 0; jb < nt; jb++) {
-    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, s>>>(A, lda, W, ldw, logdet_parts, info, jb);
+  int r;
+  if ((r = la.ensure(2 * (size_t)nt + 2))) return r;
+  cudaStream_t s2 = la.side;
+  cudaEvent_t* evPanel = la.ev.data();        // [nt]
+  cudaEvent_t* evRest = la.ev.data() + nt;    // [nt]
+  cudaEvent_t evFork = la.ev[2 * nt], evJoin = la.ev[2 * nt + 1];
+  auto leaf = [&](cudaStream_t st, int jb) -> int {
+    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(A, lda, W, ldw, logdet_parts, info, jb);
     if (launches) ++*launches;
     CU(cudaGetLastError());
+    return 0;
+  };
+  auto panel = [&](cudaStream_t st, int jb) -> int {  // rows of tiles jb+1.. , columns of block jb
     const int rem = nt - jb - 1;
-    if (rem == 0) break;
-    double* panel = A + (long)(jb + 1) * 128 * lda + (long)jb * 128;
+    double* pn = A + (long)(jb + 1) * 128 * lda + (long)jb * 128;
     const double* wjj = W + (long)jb * 128 * ldw + (long)jb * 128;
-    GemmDesc p = make_desc(panel, lda, wjj, ldw, panel, lda, rem, 1, 128);
-    int r = launch_gemm(s, false, false, p, 1, launches);
-    if (r) return r;
-    double* trail = A + (long)(jb + 1) * 128 * (lda + 1);
-    GemmDesc u = make_desc(panel, lda, panel, lda, trail, lda, rem, rem, 128);
-    u.tri = 1, u.alpha = -1.0, u.beta = 1.0;
-    if ((r = launch_gemm(s, false, false, u, 1, launches))) return r;
+    GemmDesc p = make_desc(pn, lda, wjj, ldw, pn, lda, 2 * rem, 1, 128);
+    return launch_gemm(st, false, false, p, 1, launches, SHAPE_P);
+  };
+  CU(cudaEventRecord(evFork, s));
+  CU(cudaStreamWaitEvent(s2, evFork, 0));
+  if ((r = leaf(s, 0))) return r;
+  if (nt == 1) return 0;
+  if ((r = panel(s, 0))) return r;
+  CU(cudaEventRecord(evPanel[0], s));
+  for (int j = 0; j + 1 < nt; j++) {
+    const int rem = nt - j - 1;  // tiles below / right of block j
+    double* pn = A + (long)(j + 1) * 128 * lda + (long)j * 128;  // panel j, rows from tile j+1
+    // ---- side stream: block column j+1, then the next diagonal block and panel ----
+    CU(cudaStreamWaitEvent(s2, evPanel[j], 0));
+    if (j > 0) CU(cudaStreamWaitEvent(s2, evRest[j - 1], 0));
+    {
+      double* col = A + (long)(j + 1) * 128 * (lda + 1);
+      GemmDesc c = make_desc(pn, lda, pn, lda, col, lda, rem, 2, 128);
+      c.alpha = -1.0, c.beta = 1.0;
+      if ((r = launch_gemm(s2, false, false, c, 1, launches, SHAPE_S))) return r;
+    }
+    if ((r = leaf(s2, j + 1))) return r;
+    if (rem > 1) {
+      if ((r = panel(s2, j + 1))) return r;
+      CU(cudaEventRecord(evPanel[j + 1], s2));
+      // ---- main stream: the rest of the trailing triangle ----
+      if (j > 0) CU(cudaStreamWaitEvent(s, evPanel[j], 0));
+      double* pn2 = pn + (long)128 * lda;  // panel j, rows from tile j+2
+      double* trail = A + (long)(j + 2) * 128 * (lda + 1);
+      GemmDesc u = make_desc(pn2, lda, pn2, lda, trail, lda, rem - 1, 2 * (rem - 1), 128);
+      u.tri = 1, u.alpha = -1.0, u.beta = 1.0;
+      if ((r = launch_gemm(s, false, false, u, 1, launches, SHAPE_S))) return r;
+      CU(cudaEventRecord(evRest[j], s));
+    }
   }
+  CU(cudaEventRecord(evJoin, s2));
+  CU(cudaStreamWaitEvent(s, evJoin, 0));
   return 0;
 }
 
@@ -242,7 +351,7 @@ struct gpras_gp {
   // training state
   double *X = nullptr, *Xs = nullptr, *Y = nullptr, *K = nullptr, *W = nullptr, *Kinv = nullptr, *U = nullptr,
          *alpha = nullptr, *theta = nullptr, *logdet = nullptr, *gpart = nullptr, *gsum = nullptr, *usq = nullptr,
-         *result = nullptr;
+         *result = nullptr, *skinny = nullptr;
   int* info = nullptr;
   double *h_theta = nullptr, *h_result = nullptr;
   int* h_info = nullptr;
@@ -254,6 +363,7 @@ struct gpras_gp {
   double *E1 = nullptr, *E2 = nullptr, *bias = nullptr, *zbias = nullptr, *ring_m = nullptr, *ring_v = nullptr;
   cudaEvent_t ev[8] = {};
   double stage_ms[7] = {};
+  LookAhead la;
 };
 
 namespace {
@@ -305,7 +415,7 @@ int factorise(gpras_gp* h, bool need_alpha, bool need_kinv) {
   if ((r = dispatch_cov(h->kid, s, h->Xs, n, n_pad, h->Xs, n, n_pad, D, h->theta, h->K, ld, 1))) return r;
   h->launches++;
   mark(h, 1);
-  if ((r = potrf_impl(s, h->K, ld, h->W, ld, n_pad, h->logdet, h->info, &h->launches))) return r;
+  if ((r = potrf_impl(s, h->la, h->K, ld, h->W, ld, n_pad, h->logdet, h->info, &h->launches))) return r;
   mark(h, 2);
   if ((r = trtri_impl(s, h->K, ld, h->W, ld, h->Kinv, ld, n_pad, &h->launches))) return r;
   mark(h, 3);
@@ -315,15 +425,14 @@ int factorise(gpras_gp* h, bool need_alpha, bool need_kinv) {
   mark(h, 4);
   // U = W Y
   {
-    GemmDesc g = make_desc(h->W, ld, h->Y, h->p_pad, h->U, h->p_pad, nt, h->p_pad / 128, n_pad);
+    GemmDesc g = make_desc(h->W, ld, h->Y, h->p_pad, h->U, h->p_pad, nt, h->p_pad / 32, n_pad);
     g.ke_mode = KE_TI;
-    g.reverse = 1;
-    if ((r = launch_gemm(s, false, true, g, 1, &h->launches))) return r;
+    if ((r = launch_skinny(s, false, g, h->skinny, n_pad, &h->launches))) return r;
   }
   if (need_alpha) {
-    GemmDesc g = make_desc(h->W, ld, h->U, h->p_pad, h->alpha, h->p_pad, nt, h->p_pad / 128, n_pad);
+    GemmDesc g = make_desc(h->W, ld, h->U, h->p_pad, h->alpha, h->p_pad, nt, h->p_pad / 32, n_pad);
     g.kb_mode = KB_TI;
-    if ((r = launch_gemm(s, true, true, g, 1, &h->launches))) return r;
+    if ((r = launch_skinny(s, true, g, h->skinny, n_pad, &h->launches))) return r;
   }
   mark(h, 5);
   return 0;
@@ -345,11 +454,11 @@ int enqueue_eval(gpras_gp* h, const double* theta, int want_grad) {
   if (want_grad) {
     const int ntile = h->nt * (h->nt + 1) / 2;
     // Wt = alpha alpha^T - P Kinv, in place over Kinv (lower tiles) on the DMMA engine
-    GemmDesc gw = make_desc(h->alpha, h->p_pad, h->alpha, h->p_pad, h->Kinv, n_pad, h->nt, h->nt, round_up(P, 16));
+    GemmDesc gw = make_desc(h->alpha, h->p_pad, h->alpha, h->p_pad, h->Kinv, n_pad, h->nt, 2 * h->nt, round_up(P, 16));
     gw.tri = 1, gw.alpha = 1.0, gw.beta = -(double)P;
-    if ((r = launch_gemm(s, false, false, gw, 1, &h->launches))) return r;
+    if ((r = launch_gemm(s, false, false, gw, 1, &h->launches, SHAPE_S))) return r;
     if ((r = dispatch_grad(h->kid, s, h->Xs, n, n_pad, D, h->Kinv, n_pad, h->gpart, 2 + D))) return r;
-    colsum_kernel<<<(2 + D + 63) / 64, 64, 0, s>>>(h->gpart, ntile, 2 + D, 2 + D, h->gsum);
+    colsum_kernel<<<2 + D, 256, 0, s>>>(h->gpart, ntile, 2 + D, 2 + D, h->gsum);
     h->launches += 2;
     CU(cudaGetLastError());
   }
@@ -413,7 +522,7 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
   if ((r = prepare_device())) return r;
   gpras_gp* h = new gpras_gp();
   h->device = device, h->kid = kernel_id, h->n = n, h->d = d, h->p = p;
-  h->n_pad = round_up(n, 128), h->p_pad = round_up(p, 128), h->nt = h->n_pad / 128;
+  h->n_pad = round_up(n, 128), h->p_pad = round_up(p, 32), h->nt = h->n_pad / 128;
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   const size_t nn = (size_t)h->n_pad * h->n_pad, np = (size_t)h->n_pad * h->p_pad;
@@ -422,7 +531,8 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
       (r = dalloc(&h->K, nn)) || (r = dalloc(&h->W, nn)) || (r = dalloc(&h->Kinv, nn)) || (r = dalloc(&h->U, np)) ||
       (r = dalloc(&h->alpha, np)) || (r = dalloc(&h->theta, 2 + d)) || (r = dalloc(&h->logdet, h->nt)) ||
       (r = dalloc(&h->gpart, (size_t)ntile * (2 + d))) || (r = dalloc(&h->gsum, 2 + d)) ||
-      (r = dalloc(&h->usq, USQ_PARTS)) || (r = dalloc(&h->result, 3 + d))) {
+      (r = dalloc(&h->usq, USQ_PARTS)) || (r = dalloc(&h->result, 3 + d)) ||
+      (r = dalloc(&h->skinny, (size_t)SKINNY_MAX_SLABS * (h->n_pad > PRED_TB ? h->n_pad : PRED_TB) * h->p_pad))) {
     gpras_gp_destroy(h);
     return r;
   }
@@ -445,7 +555,7 @@ int gpras_gp_destroy(gpras_gp* h) {
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   double* bufs[] = {h->X,    h->Xs,  h->Y,   h->K,  h->W,     h->Kinv, h->U,    h->alpha, h->theta, h->logdet, h->gpart,
-                    h->gsum, h->usq, h->result, h->Xt, h->Xts, h->Ks,   h->mean, h->vpart, h->var,   h->varm,   h->E1,
+                    h->gsum, h->usq, h->result, h->skinny, h->Xt, h->Xts, h->Ks,   h->mean, h->vpart, h->var,   h->varm,   h->E1,
                     h->E2,   h->bias, h->zbias, h->ring_m, h->ring_v};
   for (double* b : bufs)
     if (b) cudaFree(b);
@@ -455,6 +565,7 @@ int gpras_gp_destroy(gpras_gp* h) {
   if (h->h_info) cudaFreeHost(h->h_info);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  h->la.destroy();
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -558,8 +669,8 @@ static int predict_batch(gpras_gp* h, int tb, int tb_pad) {
   if ((r = dispatch_cov(h->kid, s, h->Xts, tb, tb_pad, h->Xs, h->n, n_pad, D, h->theta, h->Ks, n_pad, 0))) return r;
   h->launches += 2;
   // mean = Ks alpha
-  GemmDesc gm = make_desc(h->Ks, n_pad, h->alpha, h->p_pad, h->mean, h->p_pad, tb_pad / 128, h->p_pad / 128, n_pad);
-  if ((r = launch_gemm(s, false, true, gm, 1, &h->launches))) return r;
+  GemmDesc gm = make_desc(h->Ks, n_pad, h->alpha, h->p_pad, h->mean, h->p_pad, tb_pad / 128, h->p_pad / 32, n_pad);
+  if ((r = launch_skinny(s, false, gm, h->skinny, tb_pad, &h->launches))) return r;
   // |W ks|^2 : tiles of V = W Ks^T reduced on the fly to column sums of squares
   GemmDesc gv = make_desc(h->W, n_pad, h->Ks, n_pad, h->vpart, PRED_TB, h->nt, tb_pad / 128, n_pad);
   gv.ke_mode = KE_TI;
@@ -729,15 +840,17 @@ int gpras_gp_last_stage_ms(gpras_gp* h, double* ms7) {
 }
 
 // ---- stand-alone building blocks --------------------------------------------------------------
-int gpras_dgemm_tiles(void* cuda_stream, int a_kmajor, int b_kmajor, const double* A, long lda, const double* B, long ldb,
-                      double* C, long ldc, int m, int n, int k, double alpha, double beta) {
-  if (m % 128 || n % 128 || k % 16 || m <= 0 || n <= 0 || k <= 0) return fail(GPRAS_E_ARG, "extents must be tile multiples");
+int gpras_dgemm_tiles(void* cuda_stream, int shape, int a_kmajor, int b_kmajor, const double* A, long lda, const double* B,
+                      long ldb, double* C, long ldc, int m, int n, int k, double alpha, double beta) {
+  const int bn = shape == SHAPE_L ? 128 : (shape == SHAPE_S ? 64 : 32);
+  if (shape < 0 || shape > 2) return fail(GPRAS_E_ARG, "shape must be 0 (128x128), 1 (128x64) or 2 (128x32)");
+  if (m % 128 || n % bn || k % 16 || m <= 0 || n <= 0 || k <= 0) return fail(GPRAS_E_ARG, "extents must be tile multiples");
   if (gpras_device_count() <= 0) return fail(GPRAS_E_CUDA, "no CUDA device (no CPU fallback)");
   int r;
   if ((r = prepare_device())) return r;
-  GemmDesc d = make_desc(A, lda, B, ldb, C, ldc, m / 128, n / 128, k);
+  GemmDesc d = make_desc(A, lda, B, ldb, C, ldc, m / 128, n / bn, k);
   d.alpha = alpha, d.beta = beta;
-  return launch_gemm((cudaStream_t)cuda_stream, a_kmajor != 0, b_kmajor != 0, d, 1, nullptr);
+  return launch_gemm((cudaStream_t)cuda_stream, a_kmajor != 0, b_kmajor != 0, d, 1, nullptr, shape);
 }
 
 int gpras_dpotrf(void* cuda_stream, double* A, long lda, double* W, long ldw, int n, double* logdet_parts_dev,
@@ -746,7 +859,8 @@ int gpras_dpotrf(void* cuda_stream, double* A, long lda, double* W, long ldw, in
   if (gpras_device_count() <= 0) return fail(GPRAS_E_CUDA, "no CUDA device (no CPU fallback)");
   int r;
   if ((r = prepare_device())) return r;
-  return potrf_impl((cudaStream_t)cuda_stream, A, lda, W, ldw, n, logdet_parts_dev, info_dev, nullptr);
+  static thread_local LookAhead la;  // stand-alone entry: one side stream per calling thread
+  return potrf_impl((cudaStream_t)cuda_stream, la, A, lda, W, ldw, n, logdet_parts_dev, info_dev, nullptr);
 }
 
 int gpras_dtrtri(void* cuda_stream, const double* L, long ldl, double* W, long ldw, double* scratch, long lds, int n) {

@@ -89,9 +89,11 @@ int gpras_gp_last_stage_ms(gpras_gp* h, double* ms7);
 int gpras_gp_set_stage_timing(gpras_gp* h, int enabled);
 
 /* ---- stand-alone building blocks on device pointers (tests, composition) ------------------ */
-/* C (op)= alpha * A(.)B(.)  with all extents multiples of 128 (k: 16): layout flags select row/k-major. */
-int gpras_dgemm_tiles(void* cuda_stream, int a_kmajor, int b_kmajor, const double* A, long lda, const double* B, long ldb,
-                      double* C, long ldc, int m, int n, int k, double alpha, double beta);
+/* C = alpha * A(.)B(.) + beta * C on the DMMA tile engine.  shape: 0 = 128x128 CTA tile (all four layouts),
+ * 1 = 128x64 (row-major A, n-major B only), 2 = 128x32 (k-major B only).  m % 128 == 0, n % tile == 0, k % 16 == 0;
+ * layout flags select row-major A[i][k] / k-major A[k][i] and n-major B[j][k] / k-major B[k][j]. */
+int gpras_dgemm_tiles(void* cuda_stream, int shape, int a_kmajor, int b_kmajor, const double* A, long lda, const double* B,
+                      long ldb, double* C, long ldc, int m, int n, int k, double alpha, double beta);
 /* In-place lower Cholesky of the n x n (n % 128 == 0) device matrix A, W = L^-1 diagonal blocks as by-product;
  * info_dev: device int, logdet_parts_dev: n/128 device doubles. */
 int gpras_dpotrf(void* cuda_stream, double* A, long lda, double* W, long ldw, int n, double* logdet_parts_dev,

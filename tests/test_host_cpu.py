@@ -174,5 +174,5 @@ def test_abi_argument_validation(lib):
     assert lib.gpras_gp_create(C.byref(h), 0, 9, 8, 2, 1) == -1
     assert lib.gpras_gp_create(C.byref(h), 0, 0, 0, 2, 1) == -1
     assert lib.gpras_gp_create(C.byref(h), 0, 0, 8, 65, 1) == -1
-    assert lib.gpras_dgemm_tiles(None, 0, 0, None, 0, None, 0, None, 0, 100, 128, 16, 1.0, 0.0) == -1
+    assert lib.gpras_dgemm_tiles(None, 0, 0, 0, None, 0, None, 0, None, 0, 100, 128, 16, 1.0, 0.0) == -1
     assert lib.gpras_dpotrf(None, None, 0, None, 0, 100, None, None) == -1

@@ -27,7 +27,7 @@ for akm in (0, 1):
         B = torch.randn(k, n, dtype=torch.float64, device=dev) if bkm else torch.randn(n, k, dtype=torch.float64, device=dev)
         Cc = torch.randn(m, n, dtype=torch.float64, device=dev)
         ref = 0.7 * ((A.T if akm else A) @ (B if bkm else B.T)) - 0.3 * Cc
-        _lib.check(lib.gpras_dgemm_tiles(st, akm, bkm, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cc.data_ptr(), Cc.stride(0), m, n, k, 0.7, -0.3))
+        _lib.check(lib.gpras_dgemm_tiles(st, 0, akm, bkm, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cc.data_ptr(), Cc.stride(0), m, n, k, 0.7, -0.3))
         torch.cuda.synchronize()
         print("gemm", akm, bkm, rel(Cc, ref))
 
