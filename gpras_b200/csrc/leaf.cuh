@@ -5,10 +5,11 @@
 // transposed in the strictly-upper triangle (W[i][k] at S[k][i], i > k) with its diagonal 1/L_ii in
 // dvec[], so L, W and the temporaries of the inverse all fit in one 135 KB tile.
 //
-//   1. potrf, right-looking over 16 panels of 8 columns with one panel of look-ahead: warp 0 factors panel
-//      J+1 in registers with shuffles (one rsqrt per column on the critical path) WHILE warps 1..7 apply
+//   1. potrf, right-looking over 16 panels of 8 columns with one panel of look-ahead: warps 0..3 factor panel
+//      J+1 (one row per lane; the 8x8 diagonal tile is factored redundantly in every lane's registers, so only
+//      one rsqrt per column sits on the critical path and no shuffle or barrier) WHILE warps 4..7 apply
 //      panel J's rank-8 update to the rest of the trailing triangle with DMMA.8x8x4 on 8 x 8 tiles; only
-//      the update of block column J+1 itself sits between two panel factorisations.
+//      the update of block column J+1 itself (all warps) sits between two panel factorisations.
 //   2. inverse by recursive doubling: 8 x 8 diagonal blocks by forward substitution (one thread per
 //      column), then for b = 8, 16, 32, 64 every pair of adjacent blocks fills its off-diagonal block
 //      W21 = -W22 (L21 W11) with two DMMA products (T = L21 W11 is parked in the pair's mirrored
@@ -46,124 +47,163 @@ __host__ __device__ constexpr LeafTileTable make_leaf_table() {
 }
 __constant__ LeafTileTable c_leaf_tiles = make_leaf_table();
 
+#ifdef LEAF_TIMING
+__device__ long long* g_leaf_timing;
+#define LT_DECL long long lt_acc[16] = {0}; const unsigned lt_sa = (unsigned)__cvta_generic_to_shared(smem); long long lt_prev = clock64(), lt_start = lt_prev
+// the shared load + dependent predicate makes the clock read wait for a preceding barrier's RELEASE
+#define LT_MARK(i) do { unsigned lt_d; long long lt_now; \
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(lt_d) : "r"(lt_sa)); \
+    asm volatile("{ .reg .pred p; setp.eq.u32 p, %1, 0x7fc12345; @p trap; mov.u64 %0, %%clock64; }" : "=l"(lt_now) : "r"(lt_d)); \
+    lt_acc[i] += lt_now - lt_prev; lt_prev = lt_now; } while (0)
+#else
+#define LT_DECL
+#define LT_MARK(i)
+#endif
+
 __device__ __forceinline__ double leaf_getW(const double* S, const double* dvec, int i, int k) {
   const double s = S[k * LEAF_LD + i];
   const double dg = dvec[i];
   return i == k ? dg : (i > k ? s : 0.0);
 }
 
-// rank-8 update of one 8x8 tile (I, Cc) with panel columns [j0, j0+8)
-__device__ __forceinline__ void leaf_update_tile(double* S, int I, int Cc, int j0, int g, int q) {
-  double* cp = S + (8 * I + g) * LEAF_LD + 8 * Cc + 2 * q;
-  double2 cv = *reinterpret_cast<double2*>(cp);
-  double c0 = -cv.x, c1 = -cv.y;
-  const double a0 = S[(8 * I + g) * LEAF_LD + j0 + q], a1 = S[(8 * I + g) * LEAF_LD + j0 + 4 + q];
-  const double b0 = S[(8 * Cc + g) * LEAF_LD + j0 + q], b1 = S[(8 * Cc + g) * LEAF_LD + j0 + 4 + q];
-  dmma(c0, c1, a0, b0);
-  dmma(c0, c1, a1, b1);
-  cv.x = -c0;
-  cv.y = -c1;
-  *reinterpret_cast<double2*>(cp) = cv;
+// rank-8 update, with panel columns [j0, j0+8), of up to NT 8x8 tiles listed in c_leaf_tiles[t0 + n*stride]
+// (n < NT, t < t_end); the NT dependent LDS -> DMMA -> DMMA -> STS chains are interleaved.
+template <int NT>
+__device__ __forceinline__ void leaf_update_tiles(double* S, int t0, int stride, int t_end, int j0, int g, int q) {
+  double2 cv[NT];
+  double a0[NT], a1[NT], b0[NT], b1[NT];
+  double* cp[NT];
+#pragma unroll
+  for (int n = 0; n < NT; n++) {
+    const int t = t0 + n * stride;
+    const bool on = t < t_end;  // warp-uniform
+    const int I = on ? c_leaf_tiles.I[t] : 15, Cc = on ? c_leaf_tiles.C[t] : 15;
+    cp[n] = S + (8 * I + g) * LEAF_LD + 8 * Cc + 2 * q;
+    cv[n] = *reinterpret_cast<double2*>(cp[n]);
+    a0[n] = S[(8 * I + g) * LEAF_LD + j0 + q], a1[n] = S[(8 * I + g) * LEAF_LD + j0 + 4 + q];
+    b0[n] = S[(8 * Cc + g) * LEAF_LD + j0 + q], b1[n] = S[(8 * Cc + g) * LEAF_LD + j0 + 4 + q];
+  }
+#pragma unroll
+  for (int n = 0; n < NT; n++) {
+    cv[n].x = -cv[n].x, cv[n].y = -cv[n].y;
+    dmma(cv[n].x, cv[n].y, a0[n], b0[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < NT; n++) dmma(cv[n].x, cv[n].y, a1[n], b1[n]);
+#pragma unroll
+  for (int n = 0; n < NT; n++) {
+    if (t0 + n * stride < t_end) *reinterpret_cast<double2*>(cp[n]) = make_double2(-cv[n].x, -cv[n].y);
+  }
 }
 
-// warp 0: factor the 8-column panel starting at column j0 (rows j0..127), in registers.
-__device__ __forceinline__ void leaf_factor_panel(double* S, double* dvec, int j0, int lane, double& logsum, int* info,
-                                                  int col_base) {
-  const int nm = (LEAF_N - j0 + 31) >> 5;  // row groups of 32 that hold real rows (warp-uniform)
-  double v[4][8];
+__device__ __forceinline__ double leaf_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // Newton from the ~2^-22 seed, three dependent operations per step: y += y * (1/2 - (x/2) y^2).
+  // Two steps reach 2^-43 and then the rounding floor of the arithmetic itself.
+  const double hx = 0.5 * x;
 #pragma unroll
-  for (int m = 0; m < 4; m++) {
-    const int r = j0 + lane + 32 * m;
-#pragma unroll
-    for (int c = 0; c < 8; c++) v[m][c] = (m < nm && r < LEAF_N) ? S[r * LEAF_LD + j0 + c] : 0.0;
+  for (int it = 0; it < 2; it++) {
+    const double t = hx * y;
+    const double u = fma(-t, y, 0.5);
+    y = fma(y, u, y);
   }
+  return y;
+}
+
+// warps 0..3: factor the 8-column panel starting at column j0 (rows j0..127).  Every lane holds the 8x8 diagonal
+// tile and factors it redundantly in registers (no shuffles, no barrier on the critical path) while carrying its
+// own row j0 + 32*warp + lane of the panel along.
+__device__ __forceinline__ void leaf_factor_panel(double* S, double* dvec, int j0, int warp, int lane, int* info,
+                                                  int col_base) {
+  if (j0 + 32 * warp >= LEAF_N) return;  // warp-uniform: no rows left for this warp
+  const int r = j0 + 32 * warp + lane;
+  const bool live = r < LEAF_N;
+  double D[8][8], v[8];
+#pragma unroll
+  for (int rr = 0; rr < 8; rr++)
+#pragma unroll
+    for (int c = 0; c <= rr; c++) D[rr][c] = S[(j0 + rr) * LEAF_LD + j0 + c];
+#pragma unroll
+  for (int c = 0; c < 8; c++) v[c] = live ? S[r * LEAF_LD + j0 + c] : 0.0;
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    double dpiv = __shfl_sync(0xffffffffu, v[0][c], c);
-    if (!(dpiv > 0.0)) {
-      if (lane == 0) atomicCAS(info, 0, col_base + j0 + c + 1);
+    double dpiv = D[c][c];
+    if (!(dpiv > 0.0)) {  // identical on every lane
+      if (warp == 0 && lane == 0) atomicCAS(info, 0, col_base + j0 + c + 1);
       dpiv = 1.0;
     }
-    double rs = rsqrt(dpiv);
-    rs = rs * (1.5 - 0.5 * dpiv * rs * rs);  // one Newton step: full double accuracy
-    const double sq = dpiv * rs;
-    if (lane == c) {
-      logsum += log(sq);
-      dvec[j0 + c] = rs;
-    }
+    const double rs = leaf_rsqrt(dpiv);
+    if (warp == 0 && lane == 0) dvec[j0 + c] = rs;
 #pragma unroll
-    for (int m = 0; m < 4; m++) v[m][c] = (m == 0 && lane == c) ? sq : v[m][c] * rs;
+    for (int rr = c + 1; rr < 8; rr++) D[rr][c] *= rs;
 #pragma unroll
-    for (int c2 = c + 1; c2 < 8; c2++) {
-      const double l = __shfl_sync(0xffffffffu, v[0][c], c2);
+    for (int c2 = c + 1; c2 < 8; c2++)
 #pragma unroll
-      for (int m = 0; m < 4; m++) v[m][c2] -= v[m][c] * l;
-    }
+      for (int rr = c2; rr < 8; rr++) D[rr][c2] -= D[rr][c] * D[c2][c];
+    v[c] *= rs;
+#pragma unroll
+    for (int c2 = c + 1; c2 < 8; c2++) v[c2] -= v[c] * D[c2][c];
   }
+  if (live) {
 #pragma unroll
-  for (int m = 0; m < 4; m++) {
-    const int r = j0 + lane + 32 * m;
-    if (m < nm && r < LEAF_N) {
-#pragma unroll
-      for (int c = 0; c < 8; c++) S[r * LEAF_LD + j0 + c] = (r >= j0 + c) ? v[m][c] : 0.0;
-    }
+    for (int c = 0; c < 8; c++) S[r * LEAF_LD + j0 + c] = (r >= j0 + c) ? v[c] : 0.0;
   }
 }
 
-// One recursive-doubling level of the inverse at block size B (8x8-tile units TB = B/8): every warp owns
-// TPW = B/8 output tiles and advances them together.
+// One recursive-doubling level of the inverse at block size B.  A pair of adjacent B-blocks has TB x TB output
+// tiles (TB = B/8) and is served by TB warps; warp u of the pair takes tiles (n, (u + n) mod TB), n < TB, so every
+// warp sees each row index and each column index once and the triangular k ranges balance.
 template <int B>
 __device__ __forceinline__ void leaf_inverse_level(double* S, const double* dvec, int warp, int g, int q) {
-  constexpr int TB = B / 8, TPP = TB * TB, TPW = B / 8;
-  int i0[TPW], jj0[TPW], r0[TPW];
+  constexpr int TB = B / 8;
+  const int p = warp / TB, u = warp % TB, r0 = 2 * B * p;
+  int i0[TB], jj0[TB];
 #pragma unroll
-  for (int n = 0; n < TPW; n++) {
-    const int t = warp + 8 * n;
-    const int p = t / TPP, rem = t - p * TPP;
-    i0[n] = 8 * (rem / TB);
-    jj0[n] = 8 * (rem % TB);
-    r0[n] = 2 * B * p;
+  for (int n = 0; n < TB; n++) {
+    i0[n] = 8 * n;
+    jj0[n] = 8 * ((u + n) % TB);
   }
-  double c0[TPW], c1[TPW];
+  double c0[TB], c1[TB];
   // GEMM1: T[i][j] = sum_{k >= j} L21[i][k] W11[k][j]; stored transposed in the pair's mirrored upper block
 #pragma unroll
-  for (int n = 0; n < TPW; n++) c0[n] = c1[n] = 0.0;
+  for (int n = 0; n < TB; n++) c0[n] = c1[n] = 0.0;
 #pragma unroll
   for (int k0 = 0; k0 < B; k0 += 4) {
 #pragma unroll
-    for (int n = 0; n < TPW; n++) {
+    for (int n = 0; n < TB; n++) {
       if (k0 >= jj0[n]) {
-        const double a = S[(r0[n] + B + i0[n] + g) * LEAF_LD + r0[n] + k0 + q];
-        const double bb = leaf_getW(S, dvec, r0[n] + k0 + q, r0[n] + jj0[n] + g);
+        const double a = S[(r0 + B + i0[n] + g) * LEAF_LD + r0 + k0 + q];
+        const double bb = leaf_getW(S, dvec, r0 + k0 + q, r0 + jj0[n] + g);
         dmma(c0[n], c1[n], a, bb);
       }
     }
   }
 #pragma unroll
-  for (int n = 0; n < TPW; n++) {
-    S[(r0[n] + jj0[n] + 2 * q) * LEAF_LD + r0[n] + B + i0[n] + g] = c0[n];
-    S[(r0[n] + jj0[n] + 2 * q + 1) * LEAF_LD + r0[n] + B + i0[n] + g] = c1[n];
+  for (int n = 0; n < TB; n++) {
+    S[(r0 + jj0[n] + 2 * q) * LEAF_LD + r0 + B + i0[n] + g] = c0[n];
+    S[(r0 + jj0[n] + 2 * q + 1) * LEAF_LD + r0 + B + i0[n] + g] = c1[n];
   }
   __syncthreads();
   // GEMM2: W21[i][j] = -sum_{k <= i} W22[i][k] T[k][j]; overwrites T in place after a barrier
 #pragma unroll
-  for (int n = 0; n < TPW; n++) c0[n] = c1[n] = 0.0;
+  for (int n = 0; n < TB; n++) c0[n] = c1[n] = 0.0;
 #pragma unroll
   for (int k0 = 0; k0 < B; k0 += 4) {
 #pragma unroll
-    for (int n = 0; n < TPW; n++) {
+    for (int n = 0; n < TB; n++) {
       if (k0 < i0[n] + 8) {
-        const double a = leaf_getW(S, dvec, r0[n] + B + i0[n] + g, r0[n] + B + k0 + q);
-        const double bb = S[(r0[n] + jj0[n] + g) * LEAF_LD + r0[n] + B + k0 + q];
+        const double a = leaf_getW(S, dvec, r0 + B + i0[n] + g, r0 + B + k0 + q);
+        const double bb = S[(r0 + jj0[n] + g) * LEAF_LD + r0 + B + k0 + q];
         dmma(c0[n], c1[n], a, bb);
       }
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int n = 0; n < TPW; n++) {
-    S[(r0[n] + jj0[n] + 2 * q) * LEAF_LD + r0[n] + B + i0[n] + g] = -c0[n];
-    S[(r0[n] + jj0[n] + 2 * q + 1) * LEAF_LD + r0[n] + B + i0[n] + g] = -c1[n];
+  for (int n = 0; n < TB; n++) {
+    S[(r0 + jj0[n] + 2 * q) * LEAF_LD + r0 + B + i0[n] + g] = -c0[n];
+    S[(r0 + jj0[n] + 2 * q + 1) * LEAF_LD + r0 + B + i0[n] + g] = -c1[n];
   }
   __syncthreads();
 }
@@ -172,6 +212,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_inv_kernel(double* __restrict__ A, long lda, double* __restrict__ W, long ldw,
                       double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
   extern __shared__ __align__(16) double smem[];
+  __shared__ double logred[4];
   double* S = smem;
   double* dvec = smem + LEAF_N * LEAF_LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -179,40 +220,59 @@ leaf_potrf_inv_kernel(double* __restrict__ A, long lda, double* __restrict__ W, 
   A += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
   W += (long)jb * LEAF_N * ldw + (long)jb * LEAF_N;
 
-  // ---- load (lower triangle; upper zeroed) ----
-  for (int e = tid; e < LEAF_N * (LEAF_N / 2); e += LEAF_THREADS) {
-    const int r = e >> 6, c2 = (e & 63) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (c2 <= r) v = *reinterpret_cast<const double2*>(A + (long)r * lda + c2);
-    S[r * LEAF_LD + c2] = v.x;
-    S[r * LEAF_LD + c2 + 1] = c2 + 1 <= r ? v.y : 0.0;
+  LT_DECL;
+  // ---- load (lower triangle; upper zeroed), eight independent 16-byte loads in flight per thread ----
+#pragma unroll 1
+  for (int e0 = tid; e0 < LEAF_N * (LEAF_N / 2); e0 += 8 * LEAF_THREADS) {
+    double2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = e0 + u * LEAF_THREADS, r = e >> 6, c2 = (e & 63) * 2;
+      v[u] = make_double2(0.0, 0.0);
+      if (c2 <= r) v[u] = *reinterpret_cast<const double2*>(A + (long)r * lda + c2);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = e0 + u * LEAF_THREADS, r = e >> 6, c2 = (e & 63) * 2;
+      if (c2 + 1 > r) v[u].y = 0.0;
+      *reinterpret_cast<double2*>(S + r * LEAF_LD + c2) = v[u];
+    }
   }
   __syncthreads();
+  LT_MARK(0);
 
-  // ---- 1. blocked Cholesky with one panel of look-ahead ----
-  double logsum = 0.0;  // warp 0, lanes 0..7: partial sums of log L_ii
-  if (warp == 0) leaf_factor_panel(S, dvec, 0, lane, logsum, info, jb * LEAF_N);
+  // ---- 1. blocked Cholesky, right-looking over 16 panels of 8 columns with one panel of look-ahead ----
+  if (warp < 4) leaf_factor_panel(S, dvec, 0, warp, lane, info, jb * LEAF_N);
   __syncthreads();
+  LT_MARK(1);
   for (int J = 0; J < 15; J++) {
     const int j0 = 8 * J;
-    // phase A: block column J+1 (tiles (I, J+1), I = J+1..15) gets panel J's update
-    for (int I = J + 1 + warp; I < 16; I += 8) leaf_update_tile(S, I, J + 1, j0, g, q);
+    // phase A: block column J+1 (<= 15 tiles, <= 2 per warp) gets panel J's update
+    leaf_update_tiles<2>(S, c_leaf_tiles.off[J + 1] + warp, 8, c_leaf_tiles.off[J + 2], j0, g, q);
     __syncthreads();
-    // phase B: warp 0 factors panel J+1; warps 1..7 update the rest of the trailing triangle with panel J
-    if (warp == 0) {
-      leaf_factor_panel(S, dvec, j0 + 8, lane, logsum, info, jb * LEAF_N);
+    LT_MARK(2);
+    if (warp < 4) {
+      // phase B, warps 0..3: factor panel J+1
+      leaf_factor_panel(S, dvec, j0 + 8, warp, lane, info, jb * LEAF_N);
+      LT_MARK(3);
     } else {
-      const int t_end = c_leaf_tiles.off[16];
-#pragma unroll 2
-      for (int t = c_leaf_tiles.off[J + 2 > 16 ? 16 : J + 2] + (warp - 1); t < t_end; t += 7)
-        leaf_update_tile(S, c_leaf_tiles.I[t], c_leaf_tiles.C[t], j0, g, q);
+      // phase B, warps 4..7: the rest of the trailing triangle (block columns >= J+2) gets panel J's update
+      const int te = c_leaf_tiles.off[16];
+      for (int t = c_leaf_tiles.off[J + 2] + (warp - 4); t < te; t += 16) leaf_update_tiles<4>(S, t, 4, te, j0, g, q);
+      LT_MARK(4);
     }
     __syncthreads();
+    LT_MARK(5);
   }
-  if (warp == 0) {
-    const double tot = warp_sum(logsum);
-    if (lane == 0) logdet_part[jb] = tot;
+  // sum(log L_ii) = -sum(log dvec): 128 logs in parallel, fixed-shape reduction
+  if (tid < 128) {
+    double lg = -log(dvec[tid]);
+    lg = warp_sum(lg);
+    if (lane == 0) logred[warp] = lg;
   }
+  __syncthreads();
+  if (tid == 0) logdet_part[jb] = (logred[0] + logred[1]) + (logred[2] + logred[3]);
+  LT_MARK(6);
 
   // ---- 2. inverse: 8x8 diagonal blocks (thread = one column of one block) ----
   if (tid < 128) {
@@ -231,23 +291,41 @@ leaf_potrf_inv_kernel(double* __restrict__ A, long lda, double* __restrict__ W, 
       if (i > c) S[(o + c) * LEAF_LD + o + i] = w[i];  // W[o+i][o+c] stored transposed
   }
   __syncthreads();
+  LT_MARK(7);
   leaf_inverse_level<8>(S, dvec, warp, g, q);
+  LT_MARK(8);
   leaf_inverse_level<16>(S, dvec, warp, g, q);
+  LT_MARK(9);
   leaf_inverse_level<32>(S, dvec, warp, g, q);
+  LT_MARK(10);
   leaf_inverse_level<64>(S, dvec, warp, g, q);
+  LT_MARK(11);
 
-  // ---- 3. write back ----
+  // ---- 3. write back: L by rows (16-byte stores); W in 8 x 4 element blocks (32-byte sectors, transposed
+  //         conflict-free reads of the upper triangle) ----
+#pragma unroll 8
   for (int e = tid; e < LEAF_N * (LEAF_N / 2); e += LEAF_THREADS) {
     const int r = e >> 6, c2 = (e & 63) * 2;
-    double2 v;
-    v.x = c2 <= r ? S[r * LEAF_LD + c2] : 0.0;
-    v.y = c2 + 1 <= r ? S[r * LEAF_LD + c2 + 1] : 0.0;
+    double2 v = *reinterpret_cast<const double2*>(S + r * LEAF_LD + c2);
+    if (c2 > r) v.x = 0.0;
+    if (c2 + 1 > r) v.y = 0.0;
     *reinterpret_cast<double2*>(A + (long)r * lda + c2) = v;
-    double2 w;
-    w.x = leaf_getW(S, dvec, r, c2);
-    w.y = leaf_getW(S, dvec, r, c2 + 1);
-    *reinterpret_cast<double2*>(W + (long)r * ldw + c2) = w;
   }
+#pragma unroll 8
+  for (int blk = warp; blk < 16 * 32; blk += 8) {  // 16 row groups of 8 x 32 column groups of 4
+    const int rb = 8 * (blk >> 5), cb = 4 * (blk & 31);
+    const int r = rb + g, c = cb + q;
+    W[(long)r * ldw + c] = leaf_getW(S, dvec, r, c);
+  }
+#ifdef LEAF_TIMING
+  __syncthreads();
+  LT_MARK(12);
+  if (tid == 0 || tid == 128) {
+    for (int i = 0; i < 13; i++)
+      if ((tid == 0) != (i == 4 || i == 5)) g_leaf_timing[i] = lt_acc[i];
+    if (tid == 0) g_leaf_timing[13] = clock64() - lt_start;
+  }
+#endif
 }
 
 }  // namespace gpras
