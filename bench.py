@@ -173,28 +173,57 @@ def run_ours(args) -> None:
     data = make_gp_data(n, d, p, 4096, seed=0)
     thetas = make_thetas(W + K, d, seed=2 + rank)  # every rank = its own shard of restarts / candidates
     stream = torch.cuda.current_stream()
-    gp = ExactGP(w["kernel"], n, d, p, device=local)
-    gp.set_stream(stream.cuda_stream)
-    gp.set_data(data.x, data.y)
+    # C independent evaluations in flight per GPU (independent restarts / candidates): each handle owns its workspace
+    # and stream, so one evaluation's latency-bound Cholesky tail overlaps another's dense products.
+    C = max(1, args.concurrent)
+    streams = [torch.cuda.Stream() for _ in range(C)]
+    gps = []
+    for c in range(C):
+        g_ = ExactGP(w["kernel"], n, d, p, device=local)
+        g_.set_stream(streams[c].cuda_stream)
+        g_.set_data(data.x, data.y)
+        gps.append(g_)
+    gp = gps[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_evals(idx0, count, out=None, host_xy=None):
+        """Round-robin `count` evaluations over the C handles; returns when all results are on the host.
+        host_xy = (x, y) pinned host arrays: upload them before every evaluation (the end-to-end path)."""
+        pending = [None] * C
+        for i in range(count):
+            c = i % C
+            if pending[c] is not None:
+                lml, g = gps[c].fetch()
+                if out is not None:
+                    out[pending[c], 0], out[pending[c], 1:] = lml, g
+            if host_xy is not None:
+                gps[c].set_data(*host_xy)
+            gps[c].enqueue(thetas[idx0 + i])
+            pending[c] = i
+        for c in range(C):
+            if pending[c] is not None:
+                lml, g = gps[c].fetch()
+                if out is not None:
+                    out[pending[c], 0], out[pending[c], 1:] = lml, g
+
     results = np.zeros((K, 3 + d))
     # ---- resident-input throughput -------------------------------------------------------------
-    for i in range(W):
-        gp.lml_grad(thetas[i])
+    run_evals(0, W)
     launches_per_eval = gp.last_launches()
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(K):
-        lml, g = gp.lml_grad(thetas[W + i])
-        results[i, 0], results[i, 1:] = lml, g
+    for st in streams:
+        st.wait_stream(stream)
+    run_evals(W, K, results)
+    for st in streams:
+        stream.wait_stream(st)
     if world > 1:  # the path's only exchange: all-gather of per-restart [LML, grad] rows
         loc = torch.from_numpy(results).cuda()
         allr = torch.empty((world * K, 3 + d), dtype=torch.float64, device="cuda")
@@ -222,12 +251,10 @@ def run_ours(args) -> None:
     # ---- end to end through the host-buffer C-ABI entry point ------------------------------------
     xp = torch.from_numpy(data.x).pin_memory().numpy()
     yp = torch.from_numpy(data.y).pin_memory().numpy()
-    for i in range(2):
-        gp.lml_grad_host(xp, yp, thetas[i])
+    run_evals(0, 2, host_xy=(xp, yp))
     barrier()
     t0 = time.perf_counter()
-    for i in range(K):
-        gp.lml_grad_host(xp, yp, thetas[W + i])
+    run_evals(W, K, host_xy=(xp, yp))
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -276,7 +303,7 @@ def run_ours(args) -> None:
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"cfg3: exact GP LML+grad, N={n}, D={d}, P={p}, {w['kernel']} ARD + noise, shared theta; "
-                                   f"{K} restarts' evaluations per GPU", "l2": "working set 1.5 GiB per eval >> 126 MB L2 (no flush needed)"},
+                                   f"{K} restarts' evaluations per GPU, {C} in flight", "l2": "working set 1.5 GiB per eval >> 126 MB L2 (no flush needed)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_eval * K,
@@ -288,7 +315,8 @@ def run_ours(args) -> None:
             "predict": predict,
         }
         print(json.dumps(line), flush=True)
-    gp.close()
+    for g_ in gps:
+        g_.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -300,6 +328,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--concurrent", type=int, default=2, help="independent evaluations in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -8,12 +8,12 @@
 //
 // * 256 threads = 8 warps arranged WARPS_M x WARPS_N over a BM x BN CTA tile; every warp owns
 //   MF x NF DMMA.8x8x4 accumulators.  Three tile shapes are instantiated:
-//       CfgL 128x128, warp 64x32, 4 stages, 1 CTA/SM  -- long-k products (LAUUM, TRTRI, predictor)
+//       CfgL 128x128, warp 64x32, BK 32, 3 stages, 1 CTA/SM  -- long-k products (LAUUM, TRTRI, predictor)
 //       CfgS 128x64,  warp 32x32, 3 stages, 2 CTA/SM  -- short-k rank-128 updates of the Cholesky, where a
 //                                                        second resident CTA hides prologue / epilogue
 //       CfgN 128x32,  warp 16x32, 4 stages, 2 CTA/SM  -- skinny right-hand sides (P <= 32 columns), split-k
 //       CfgP 64x128,  warp 32x32, 3 stages, 2 CTA/SM  -- the in-place Cholesky panel L21 = A21 W_jj^T
-// * Operand tiles stream global -> shared with 16-byte cp.async in a multi-stage ring, BK = 16.
+// * Operand tiles stream global -> shared with 16-byte cp.async in a multi-stage ring (BK = 16, or 32 for CfgL).
 // * A is either row-major A[i][k] or k-major A[k][i]; B either n-major B[j][k] or k-major B[k][j];
 //   shared tiles are padded (+4 doubles) so every fragment LDS.64 is bank-conflict free.
 // * Triangular structure is exploited at tile granularity by clipping the k range per tile
@@ -29,24 +29,26 @@
 
 namespace gpras {
 
-constexpr int BK = 16, GEMM_THREADS = 256;
-constexpr int LD_RM = BK + 4;  // row / n-major tile [rows][20] (k contiguous)
+constexpr int GEMM_THREADS = 256;
+constexpr int K_ALIGN = 32;  // every k extent / clip point handed to the engine is a multiple of this (>= any BK)
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_>
+template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_, int MINB_>
 struct TileCfg {
-  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_, MINB = MINB_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int MF = WM / 8, NF = WN / 8;
-  static constexpr int A_DOUBLES = BM * LD_RM;  // >= 16 * (BM + 4)
-  static constexpr int B_DOUBLES = BN * LD_RM;  // >= 16 * (BN + 4)
+  static constexpr int LD_RM = BK + 4;  // row / n-major tile [rows][BK + 4] (k contiguous); == 4 mod 16
+  static constexpr int A_DOUBLES = BM * LD_RM > BK * (BM + 4) ? BM * LD_RM : BK * (BM + 4);
+  static constexpr int B_DOUBLES = BN * LD_RM > BK * (BN + 4) ? BN * LD_RM : BK * (BN + 4);
   static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
   static_assert(WARPS_M * WARPS_N == 8, "8 warps per CTA");
+  static_assert(BK % 16 == 0 && BK <= K_ALIGN, "BK");
 };
-using CfgL = TileCfg<128, 128, 64, 32, 4, 1>;
-using CfgS = TileCfg<128, 64, 32, 32, 3, 2>;
-using CfgN = TileCfg<128, 32, 16, 32, 4, 2>;
-using CfgP = TileCfg<64, 128, 32, 32, 3, 2>;   // in-place Cholesky panel: full 128-column width per CTA (no tri mode)
+using CfgL = TileCfg<128, 128, 64, 32, 32, 3, 1>;  // 216 KiB: three 72 KiB stages, one barrier per 256 DMMAs / warp
+using CfgS = TileCfg<128, 64, 32, 32, 16, 3, 2>;
+using CfgN = TileCfg<128, 32, 16, 32, 16, 4, 2>;
+using CfgP = TileCfg<64, 128, 32, 32, 16, 3, 2>;   // in-place Cholesky panel: full 128-column width per CTA (no tri mode)
 
 enum KBegin { KB_ZERO = 0, KB_TI = 1, KB_TJ = 2 };   // k_begin = 0 | ti*BM | tj*BN
 enum KEnd { KE_FULL = 0, KE_TI = 1, KE_TJ = 2 };     // k_end   = K | (ti+1)*BM | (tj+1)*BN
@@ -61,8 +63,8 @@ struct GemmDesc {
   long batchA, batchB, batchC;  // element strides between batch entries (grid.y)
   long splitC;          // element stride between k-split partial outputs (grid.z)
   int m_tiles, n_tiles;
-  int K;                // multiple of BK
-  int k_split;          // 0, or chunk length (multiple of BK) per blockIdx.z
+  int K;                // multiple of K_ALIGN
+  int k_split;          // 0, or chunk length (multiple of K_ALIGN) per blockIdx.z
   int kb_mode, ke_mode;
   int tri;              // 1: only tiles whose columns start at or below the row tile's last row
   int reverse;          // 1: launch order reversed (heaviest tiles first for LPT scheduling)
@@ -70,17 +72,19 @@ struct GemmDesc {
   double alpha, beta;
 };
 
-// rows x 16 tile, global -> shared.  Row-major: rows of 128 B; k-major: 16 rows of ROWS doubles.
-template <bool KMAJOR, int ROWS>
+// ROWS x BK tile, global -> shared.  Row-major: ROWS rows of BK doubles; k-major: BK rows of ROWS doubles.
+template <bool KMAJOR, int ROWS, int BK>
 __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ g, long ld, int tid) {
-  constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks in the tile
+  constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks in the tile
+  constexpr int LD_RM = BK + 4;
   constexpr int PER_THREAD = (CHUNKS + GEMM_THREADS - 1) / GEMM_THREADS;
 #pragma unroll
   for (int q = 0; q < PER_THREAD; q++) {
     const int c = tid + GEMM_THREADS * q;
     if (CHUNKS % GEMM_THREADS == 0 || c < CHUNKS) {
       if (!KMAJOR) {
-        const int row = c >> 3, kc = c & 7;
+        constexpr int CPK = BK / 2;  // chunks per row
+        const int row = c / CPK, kc = c - row * CPK;
         cp_async16(s + row * LD_RM + 2 * kc, g + (long)row * ld + 2 * kc);
       } else {
         constexpr int CPR = ROWS / 2;  // chunks per k row
@@ -93,7 +97,8 @@ __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* 
 
 template <typename Cfg, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(const GemmDesc d) {
-  constexpr int BM = Cfg::BM, BN = Cfg::BN, MF = Cfg::MF, NF = Cfg::NF, STAGES = Cfg::STAGES;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, MF = Cfg::MF, NF = Cfg::NF, STAGES = Cfg::STAGES, BK = Cfg::BK;
+  constexpr int LD_RM = Cfg::LD_RM;
   constexpr int LDA_KM = BM + 4, LDB_KM = BN + 4, RATIO = BM >= BN ? BM / BN : 1;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,8 +145,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(cons
   for (int s = 0; s < STAGES - 1; s++) {
     if (s < nk) {
       double* sA = smem + s * Cfg::STAGE_DOUBLES;
-      load_tile<A_KMAJOR, BM>(sA, gA + s * stepA, d.lda, tid);
-      load_tile<B_KMAJOR, BN>(sA + Cfg::A_DOUBLES, gB + s * stepB, d.ldb, tid);
+      load_tile<A_KMAJOR, BM, BK>(sA, gA + s * stepA, d.lda, tid);
+      load_tile<B_KMAJOR, BN, BK>(sA + Cfg::A_DOUBLES, gB + s * stepB, d.ldb, tid);
     }
     cp_async_commit();
   }
@@ -174,8 +179,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(cons
       const int nx = kt + STAGES - 1;
       if (nx < nk) {
         double* sA = smem + (nx % STAGES) * Cfg::STAGE_DOUBLES;
-        load_tile<A_KMAJOR, BM>(sA, gA + nx * stepA, d.lda, tid);
-        load_tile<B_KMAJOR, BN>(sA + Cfg::A_DOUBLES, gB + nx * stepB, d.ldb, tid);
+        load_tile<A_KMAJOR, BM, BK>(sA, gA + nx * stepA, d.lda, tid);
+        load_tile<B_KMAJOR, BN, BK>(sA + Cfg::A_DOUBLES, gB + nx * stepB, d.ldb, tid);
       }
       cp_async_commit();
     }

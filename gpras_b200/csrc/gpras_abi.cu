@@ -454,7 +454,7 @@ int enqueue_eval(gpras_gp* h, const double* theta, int want_grad) {
   if (want_grad) {
     const int ntile = h->nt * (h->nt + 1) / 2;
     // Wt = alpha alpha^T - P Kinv, in place over Kinv (lower tiles) on the DMMA engine
-    GemmDesc gw = make_desc(h->alpha, h->p_pad, h->alpha, h->p_pad, h->Kinv, n_pad, h->nt, 2 * h->nt, round_up(P, 16));
+    GemmDesc gw = make_desc(h->alpha, h->p_pad, h->alpha, h->p_pad, h->Kinv, n_pad, h->nt, 2 * h->nt, round_up(P, 32));
     gw.tri = 1, gw.alpha = 1.0, gw.beta = -(double)P;
     if ((r = launch_gemm(s, false, false, gw, 1, &h->launches, SHAPE_S))) return r;
     if ((r = dispatch_grad(h->kid, s, h->Xs, n, n_pad, D, h->Kinv, n_pad, h->gpart, 2 + D))) return r;
@@ -729,7 +729,7 @@ int gpras_gp_set_cell_map(gpras_gp* h, const double* e_mean, const double* bias,
   for (double* b : olds)
     if (b) cudaFree(b);
   h->E1 = h->E2 = h->bias = h->zbias = h->ring_m = h->ring_v = nullptr;
-  h->c = c, h->c_pad = round_up(c, 128), h->p16 = round_up(h->p, 16);
+  h->c = c, h->c_pad = round_up(c, 128), h->p16 = round_up(h->p, 32);
   const size_t ne = (size_t)h->p16 * h->c_pad;
   int r;
   if ((r = dalloc(&h->E1, ne)) || (r = dalloc(&h->E2, ne)) || (r = dalloc(&h->bias, h->c_pad)) ||
@@ -844,7 +844,7 @@ int gpras_dgemm_tiles(void* cuda_stream, int shape, int a_kmajor, int b_kmajor, 
                       long ldb, double* C, long ldc, int m, int n, int k, double alpha, double beta) {
   const int bn = shape == SHAPE_L ? 128 : (shape == SHAPE_S ? 64 : 32);
   if (shape < 0 || shape > 2) return fail(GPRAS_E_ARG, "shape must be 0 (128x128), 1 (128x64) or 2 (128x32)");
-  if (m % 128 || n % bn || k % 16 || m <= 0 || n <= 0 || k <= 0) return fail(GPRAS_E_ARG, "extents must be tile multiples");
+  if (m % 128 || n % bn || k % 32 || m <= 0 || n <= 0 || k <= 0) return fail(GPRAS_E_ARG, "extents must be tile multiples");
   if (gpras_device_count() <= 0) return fail(GPRAS_E_CUDA, "no CUDA device (no CPU fallback)");
   int r;
   if ((r = prepare_device())) return r;

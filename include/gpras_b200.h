@@ -90,7 +90,7 @@ int gpras_gp_set_stage_timing(gpras_gp* h, int enabled);
 
 /* ---- stand-alone building blocks on device pointers (tests, composition) ------------------ */
 /* C = alpha * A(.)B(.) + beta * C on the DMMA tile engine.  shape: 0 = 128x128 CTA tile (all four layouts),
- * 1 = 128x64 (row-major A, n-major B only), 2 = 128x32 (k-major B only).  m % 128 == 0, n % tile == 0, k % 16 == 0;
+ * 1 = 128x64 (row-major A, n-major B only), 2 = 128x32 (k-major B only).  m % 128 == 0, n % tile == 0, k % 32 == 0;
  * layout flags select row-major A[i][k] / k-major A[k][i] and n-major B[j][k] / k-major B[k][j]. */
 int gpras_dgemm_tiles(void* cuda_stream, int shape, int a_kmajor, int b_kmajor, const double* A, long lda, const double* B,
                       long ldb, double* C, long ldc, int m, int n, int k, double alpha, double beta);

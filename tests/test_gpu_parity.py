@@ -31,7 +31,7 @@ def test_tile_gemm_all_layouts(cuda, lib, shape, akm, bkm):
     torch = cuda
     from gpras_b200 import _lib
 
-    m, n, k = 384, 256, 272
+    m, n, k = 384, 256, 288
     g = torch.Generator(device="cuda").manual_seed(shape * 4 + akm * 2 + bkm)
     A = torch.randn((k, m) if akm else (m, k), dtype=torch.float64, device="cuda", generator=g)
     B = torch.randn((k, n) if bkm else (n, k), dtype=torch.float64, device="cuda", generator=g)
