@@ -40,6 +40,13 @@ SYMBOLS = {
     "gpras_gp_last_launches": (C.c_int, [vp]),
     "gpras_gp_last_stage_ms": (C.c_int, [vp, vp]),
     "gpras_gp_set_stage_timing": (C.c_int, [vp, C.c_int]),
+    "gpras_sgpr_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gpras_sgpr_destroy": (C.c_int, [vp]),
+    "gpras_sgpr_set_data": (C.c_int, [vp, vp, vp, C.c_int]),
+    "gpras_sgpr_elbo_grad": (C.c_int, [vp, vp, vp, C.c_double, vp, vp, vp]),
+    "gpras_sgpr_condition": (C.c_int, [vp, vp, vp, C.c_double]),
+    "gpras_sgpr_predict": (C.c_int, [vp, vp, C.c_int, vp, vp]),
+    "gpras_sgpr_last_launches": (C.c_int, [vp]),
     "gpras_dgemm_tiles": (
         C.c_int,
         [vp, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double],

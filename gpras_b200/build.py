@@ -41,19 +41,33 @@ def needs_build() -> bool:
     return newest > LIB_PATH.stat().st_mtime
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into ``libgpras_b200.so``; returns its path."""
-    if not force and not needs_build():
-        return LIB_PATH
-    srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *srcs]
+def _compile(src: Path, obj: Path, verbose: bool) -> str:
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "-shared"], "-c", "-o", str(obj), str(src)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return res.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a (one object per translation unit, in parallel) and link
+    ``libgpras_b200.so``; returns its path."""
+    if not force and not needs_build():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
+    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+    objs = [CSRC / (s.stem + ".o") for s in srcs]
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        logs = list(ex.map(lambda so: _compile(so[0], so[1], verbose), zip(srcs, objs)))
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return LIB_PATH
 
 

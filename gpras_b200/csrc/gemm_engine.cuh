@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(cons
 }
 
 // out[e] = sum_z part[z * stride + e]  (fixed order -> deterministic), e < count
-__global__ void splitk_reduce_kernel(const double* __restrict__ part, long stride, int nz, long count,
+static __global__ void splitk_reduce_kernel(const double* __restrict__ part, long stride, int nz, long count,
                                      double* __restrict__ out) {
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;

@@ -18,7 +18,7 @@ constexpr int CT_LD = CT + 2;     // shared pitch of the transposed feature tile
 constexpr int PT_THREADS = 256;   // 16 x 16 threads; each owns 4 x 4 entries in each 64 x 64 quadrant
 
 // Xs[i][d] = X[i][d] / l_d for i < n, 0 for padding rows.
-__global__ void scale_features_kernel(const double* __restrict__ X, double* __restrict__ Xs, int n, int n_pad, int D,
+static __global__ void scale_features_kernel(const double* __restrict__ X, double* __restrict__ Xs, int n, int n_pad, int D,
                                       const double* __restrict__ theta) {
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long)n_pad * D) return;
@@ -58,7 +58,7 @@ template <int KID>
 __global__ void __launch_bounds__(PT_THREADS) cov_kernel(const double* __restrict__ Xs1, int n1, const double* __restrict__ Xs2,
                                                          int n2, int D, const double* __restrict__ theta,
                                                          double* __restrict__ out, long ldo, int n_tiles_x, int tri,
-                                                         int square) {
+                                                         int square, double jitter) {
   extern __shared__ __align__(16) double smem[];
   double* s1 = smem;
   double* s2 = smem + (long)D * CT_LD;
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(PT_THREADS) cov_kernel(const double* __restric
   stage_features(s1, Xs1, ti * CT, D, tid);
   stage_features(s2, Xs2, tj * CT, D, tid);
   __syncthreads();
-  const double variance = theta[0], noise = theta[1];
+  // square mode adds the likelihood noise (jitter < 0) or a fixed jitter (sparse model's Kuu) on the diagonal
+  const double variance = theta[0], noise = jitter < 0.0 ? theta[1] : jitter;
 #pragma unroll 1
   for (int quad = 0; quad < 4; quad++) {
     const int ro = 64 * (quad >> 1) + 4 * ty, co = 64 * (quad & 1) + 4 * tx;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(PT_THREADS) grad_kernel(const double* __restri
 
 // out[c] = sum_r part[r][c]: one 256-thread CTA per column; strided partial sums then a fixed-shape tree, so the
 // result is bitwise repeatable.
-__global__ void colsum_kernel(const double* __restrict__ part, int rows, int cols, long ld, double* __restrict__ out) {
+static __global__ void colsum_kernel(const double* __restrict__ part, int rows, int cols, long ld, double* __restrict__ out) {
   __shared__ double red[256];
   const int c = blockIdx.x;
   if (c >= cols) return;
@@ -238,7 +239,7 @@ __global__ void colsum_kernel(const double* __restrict__ part, int rows, int col
 }
 
 // Per-CTA sum of squares of a (rows x cols) block with pitch ld -> part[blockIdx.x].
-__global__ void sumsq_partial_kernel(const double* __restrict__ U, int rows, int cols, long ld, double* __restrict__ part) {
+static __global__ void sumsq_partial_kernel(const double* __restrict__ U, int rows, int cols, long ld, double* __restrict__ part) {
   __shared__ double red[8];
   double s = 0.0;
   const long total = (long)rows * cols;
@@ -259,7 +260,7 @@ __global__ void sumsq_partial_kernel(const double* __restrict__ U, int rows, int
 }
 
 // result = [lml, dLML/dlog variance, dLML/dlog noise, dLML/dlog l_0 .. l_{D-1}]
-__global__ void finalize_kernel(const double* __restrict__ usq_part, int n_usq, const double* __restrict__ logdet_part,
+static __global__ void finalize_kernel(const double* __restrict__ usq_part, int n_usq, const double* __restrict__ logdet_part,
                                 int n_logdet, const double* __restrict__ gsum, const double* __restrict__ theta, int n,
                                 int P, int D, int want_grad, double* __restrict__ result) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -276,7 +277,7 @@ __global__ void finalize_kernel(const double* __restrict__ usq_part, int n_usq, 
 }
 
 // var[t] = variance + noise - sum_r part[r][t]   (predict_y semantics, gpras/gpr.py:337)
-__global__ void predict_var_kernel(const double* __restrict__ part, int rows, int T, long ld,
+static __global__ void predict_var_kernel(const double* __restrict__ part, int rows, int T, long ld,
                                    const double* __restrict__ theta, double* __restrict__ var) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;

@@ -45,10 +45,10 @@ __host__ __device__ constexpr LeafTileTable make_leaf_table() {
   t.off[16] = (unsigned char)n;
   return t;
 }
-__constant__ LeafTileTable c_leaf_tiles = make_leaf_table();
+static __constant__ LeafTileTable c_leaf_tiles = make_leaf_table();
 
 #ifdef LEAF_TIMING
-__device__ long long* g_leaf_timing;
+static __device__ long long* g_leaf_timing;
 #define LT_DECL long long lt_acc[16] = {0}; const unsigned lt_sa = (unsigned)__cvta_generic_to_shared(smem); long long lt_prev = clock64(), lt_start = lt_prev
 // the shared load + dependent predicate makes the clock read wait for a preceding barrier's RELEASE
 #define LT_MARK(i) do { unsigned lt_d; long long lt_now; \
@@ -208,7 +208,7 @@ __device__ __forceinline__ void leaf_inverse_level(double* S, const double* dvec
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
+static __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_inv_kernel(double* __restrict__ A, long lda, double* __restrict__ W, long ldw,
                       double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
   extern __shared__ __align__(16) double smem[];

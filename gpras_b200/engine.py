@@ -150,3 +150,66 @@ class ExactGP:
         ms = np.zeros(7)
         check(self.lib.gpras_gp_last_stage_ms(self._h, ptr(ms)))
         return dict(zip(["cov", "potrf", "trtri", "lauum", "alpha", "grad", "total"], ms.tolist()))
+
+
+class SparseGP:
+    """One sparse (inducing-point) model on one GPU: GPflow ``SGPR`` semantics (``gpras/gpr.py:293-308``) behind
+    ``gpras_sgpr_*``: collapsed bound + analytic gradient w.r.t. hyperparameters and inducing inputs, ``predict_y``."""
+
+    def __init__(self, kernel: str, n: int, d: int, m: int, r: int = 1, device: int = 0):
+        self.lib = _lib.load()
+        if self.lib.gpras_device_count() <= 0:
+            raise _lib.GprasError("no CUDA device visible: gpras_b200 has no CPU fallback")
+        self.kernel, self.n, self.d, self.m, self.r, self.device = kernel, int(n), int(d), int(m), int(r), int(device)
+        h = C.c_void_p()
+        check(self.lib.gpras_sgpr_create(C.byref(h), device, KERNEL_IDS[kernel], self.n, self.d, self.m, self.r))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.gpras_sgpr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_data(self, x, y) -> None:
+        x, y = _f64(x), _f64(y)
+        if x.shape != (self.n, self.d) or y.shape != (self.n, self.r):
+            raise ValueError(f"expected x {(self.n, self.d)} and y {(self.n, self.r)}, got {x.shape}, {y.shape}")
+        check(self.lib.gpras_sgpr_set_data(self._h, ptr(x), ptr(y), 0))
+
+    def theta_vector(self, variance: float, noise: float, lengthscales) -> np.ndarray:
+        ls = np.asarray(lengthscales, np.float64).reshape(-1)
+        if ls.size == 1:
+            ls = np.full(self.d, ls[0])
+        return np.concatenate([[float(variance), float(noise)], ls])
+
+    def elbo_grad(self, theta, z, jitter: float = 1e-6, want_grad: bool = True):
+        """(ELBO, d/dlog theta [2 + D], d/dZ [M, D]); gradients are None when ``want_grad`` is False."""
+        theta, z = _f64(theta), _f64(z)
+        if z.shape != (self.m, self.d):
+            raise ValueError(f"expected inducing inputs {(self.m, self.d)}, got {z.shape}")
+        elbo = C.c_double()
+        gt = np.empty(2 + self.d) if want_grad else None
+        gz = np.empty((self.m, self.d)) if want_grad else None
+        check(self.lib.gpras_sgpr_elbo_grad(self._h, ptr(theta), ptr(z), float(jitter), C.byref(elbo),
+                                            ptr(gt) if want_grad else None, ptr(gz) if want_grad else None))
+        return elbo.value, gt, gz
+
+    def condition(self, theta, z, jitter: float = 1e-6) -> None:
+        theta, z = _f64(theta), _f64(z)
+        check(self.lib.gpras_sgpr_condition(self._h, ptr(theta), ptr(z), float(jitter)))
+
+    def predict(self, xs):
+        xs = _f64(xs)
+        t = xs.shape[0]
+        mean, var = np.empty((t, self.r)), np.empty((t, self.r))
+        check(self.lib.gpras_sgpr_predict(self._h, ptr(xs), t, ptr(mean), ptr(var)))
+        return mean, var
+
+    def last_launches(self) -> int:
+        return int(self.lib.gpras_sgpr_last_launches(self._h))

@@ -1,0 +1,137 @@
+"""Sparse (inducing-point) model objects: the reference's own model family.
+
+``gpras/gpr.py:293-308`` builds one ``gpflow.models.SGPR`` per target column with shared initial inducing inputs,
+LogNormal(0, 1) priors on the three constrained hyperparameters and trainable ``Z``.  ``SparseModel`` exposes the same
+attribute names the reference's recipes touch (``kernel.variance / .lengthscales``, ``likelihood.variance``,
+``inducing_variable.Z``, ``data``, ``trainable_variables``, ``training_loss()``) and evaluates
+``training_loss = -(ELBO + log prior)`` with its gradient on the GPU (``gpras_sgpr_elbo_grad``).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import SparseGP
+from .gpr import _Inducing, _Kernel, _Likelihood, _softplus
+
+JITTER = 1e-6  # gpflow.config.default_jitter()
+
+_HANDLES: dict = {}
+
+
+def _handle(kernel: str, n: int, d: int, m: int, r: int, device: int) -> SparseGP:
+    """One device handle per problem shape; per-column models take turns on it (they run sequentially, gpr.py:273-274)."""
+    key = (kernel, n, d, m, r, device)
+    if key not in _HANDLES:
+        _HANDLES[key] = {"gp": SparseGP(kernel, n, d, m, r, device=device), "owner": None}
+    return _HANDLES[key]
+
+
+class SparseModel:
+    supports_z_training = True
+
+    def __init__(self, kernel_name, x, y, z, lengthscales, device: int = 0, priors: bool = True):
+        self.x, self.y = x, y
+        self.data = (x, y)
+        self.device = device
+        self.kernel = _Kernel(kernel_name, 1.0, lengthscales)
+        self.likelihood = _Likelihood(1.0)
+        self.inducing_variable = _Inducing(z, trainable=True)
+        if not priors:
+            self.kernel.variance.prior = self.kernel.lengthscales.prior = self.likelihood.variance.prior = None
+        self.n_evals = 0
+
+    # -- device plumbing --
+    def _gp(self) -> SparseGP:
+        n, d = self.x.shape
+        slot = _handle(self.kernel.name, n, d, self.inducing_variable.Z.shape[0], self.y.shape[1], self.device)
+        if slot["owner"] is not self:
+            slot["gp"].set_data(self.x, self.y)
+            slot["owner"] = self
+        return slot["gp"]
+
+    # -- parameter plumbing (same protocol as ExactModel) --
+    @property
+    def parameters(self):
+        return [self.kernel.variance, self.likelihood.variance, self.kernel.lengthscales]
+
+    @property
+    def trainable_variables(self):
+        out = [p.unconstrained for p in self.parameters if p.trainable]
+        if self.inducing_variable.trainable:
+            out.append(self.inducing_variable.Z)
+        return out
+
+    def set_trainable(self, flag: bool, hypers: bool = True) -> None:
+        if hypers:
+            for p in self.parameters:
+                p.trainable = flag
+
+    def get_u(self):
+        parts = [p.unconstrained for p in self.parameters if p.trainable]
+        if self.inducing_variable.trainable:
+            parts.append(np.asarray(self.inducing_variable.Z, np.float64).ravel())
+        return np.concatenate(parts) if parts else np.zeros(0)
+
+    def set_u(self, u) -> None:
+        u = np.asarray(u, np.float64)
+        o = 0
+        for p in self.parameters:
+            if p.trainable:
+                p.unconstrained = u[o : o + p.size].copy()
+                o += p.size
+        if self.inducing_variable.trainable:
+            z = self.inducing_variable.Z
+            self.inducing_variable.Z = u[o : o + z.size].reshape(z.shape).copy()
+
+    def theta(self):
+        d = self.x.shape[1]
+        ls = np.atleast_1d(self.kernel.lengthscales.numpy())
+        if ls.size == 1:
+            ls = np.full(d, ls[0])
+        return np.concatenate([[self.kernel.variance.numpy(), self.likelihood.variance.numpy()], ls])
+
+    def _log_prior(self) -> float:
+        return sum(p.log_prior() for p in self.parameters if p.trainable)
+
+    # -- objective --
+    def training_loss(self) -> float:
+        elbo, _, _ = self._gp().elbo_grad(self.theta(), np.asarray(self.inducing_variable.Z, np.float64), JITTER, want_grad=False)
+        self.n_evals += 1
+        return -(elbo + self._log_prior())
+
+    def loss_and_grad(self, u=None):
+        if u is not None:
+            self.set_u(u)
+        elbo, gt, gz = self._gp().elbo_grad(self.theta(), np.asarray(self.inducing_variable.Z, np.float64), JITTER)
+        self.n_evals += 1
+        g_ls = gt[2:] if self.kernel.lengthscales.size > 1 else np.array([gt[2:].sum()])
+        parts = []
+        for p, gl in ((self.kernel.variance, np.array([gt[0]])), (self.likelihood.variance, np.array([gt[1]])),
+                      (self.kernel.lengthscales, g_ls)):
+            if p.trainable:
+                v = _softplus(p.unconstrained) + p.lower
+                parts.append(-((gl / v + p.dlog_prior_dvalue()) * p.dvalue_du()))
+        if self.inducing_variable.trainable:
+            parts.append(-gz.ravel())
+        return -(elbo + self._log_prior()), (np.concatenate(parts) if parts else np.zeros(0))
+
+    # -- prediction --
+    def predict_y(self, xs):
+        gp = self._gp()
+        gp.condition(self.theta(), np.asarray(self.inducing_variable.Z, np.float64), JITTER)
+        return gp.predict(np.asarray(xs, np.float64))
+
+    def parameter_dict(self) -> dict:
+        return {
+            ".kernel.variance": np.asarray(self.kernel.variance.numpy()),
+            ".kernel.lengthscales": np.asarray(self.kernel.lengthscales.numpy()),
+            ".likelihood.variance": np.asarray(self.likelihood.variance.numpy()),
+            ".inducing_variable.Z": np.asarray(self.inducing_variable.Z),
+        }
+
+    def assign_parameters(self, d: dict) -> None:
+        self.kernel.variance.assign(d[".kernel.variance"])
+        self.kernel.lengthscales.assign(d[".kernel.lengthscales"])
+        self.likelihood.variance.assign(d[".likelihood.variance"])
+        self.inducing_variable.Z = np.asarray(d[".inducing_variable.Z"], np.float64)

@@ -88,6 +88,22 @@ int gpras_gp_last_launches(gpras_gp* h);
 int gpras_gp_last_stage_ms(gpras_gp* h, double* ms7);
 int gpras_gp_set_stage_timing(gpras_gp* h, int enabled);
 
+/* ---- sparse (inducing-point) model: replaces gpflow.models.SGPR as built at gpr.py:293-308 ---------- */
+typedef struct gpras_sgpr gpras_sgpr;
+/* n rows, d features, m inducing points, r output columns sharing the model (1 in the reference). */
+int gpras_sgpr_create(gpras_sgpr** out, int device, int kernel_id, int n, int d, int m, int r);
+int gpras_sgpr_destroy(gpras_sgpr* h);
+int gpras_sgpr_set_data(gpras_sgpr* h, const double* x, const double* y, int on_device);
+/* Collapsed bound (ELBO) of SGPR.training_loss (gpr.py:154,199; priors are host logic) and its gradient:
+ * theta (2 + d) and z (m x d) are host arrays; grad_theta (2 + d) is d/dlog theta, grad_z (m x d) is d/dz.
+ * Either gradient pointer may be NULL; both NULL skips the backward pass (differential evolution, gpr.py:62). */
+int gpras_sgpr_elbo_grad(gpras_sgpr* h, const double* theta, const double* z, double jitter, double* elbo,
+                         double* grad_theta, double* grad_z);
+/* predict_y (gpr.py:337): condition at (theta, z), then mean (t x r) and variance (t x r, noise included). */
+int gpras_sgpr_condition(gpras_sgpr* h, const double* theta, const double* z, double jitter);
+int gpras_sgpr_predict(gpras_sgpr* h, const double* xs, int t, double* mean, double* var);
+int gpras_sgpr_last_launches(gpras_sgpr* h);
+
 /* ---- stand-alone building blocks on device pointers (tests, composition) ------------------ */
 /* C = alpha * A(.)B(.) + beta * C on the DMMA tile engine.  shape: 0 = 128x128 CTA tile (all four layouts),
  * 1 = 128x64 (row-major A, n-major B only), 2 = 128x32 (k-major B only).  m % 128 == 0, n % tile == 0, k % 32 == 0;

@@ -309,3 +309,86 @@ def test_full_size_properties(cuda, n, d, p):
     np.testing.assert_allclose(mean, data.y[:256] - s * alpha[:256], rtol=1e-8, atol=1e-8)
     assert np.all(var > s * (1 - 1e-9)) and np.all(var < v + s)
     gp.close()
+
+
+# ---- sparse (inducing-point) model: GPflow SGPR semantics --------------------------------------------
+@pytest.mark.parametrize(
+    "kernel,ard,n,d,m",
+    [("RBF", False, 300, 4, 20), ("Matern52", True, 1000, 10, 50), ("Matern32", False, 257, 3, 130),
+     ("Matern12", True, 500, 5, 64), ("Exponential", False, 400, 2, 300)],
+)
+def test_sgpr_bound_gradient_and_prediction_match_oracle(cuda, kernel, ard, n, d, m):
+    import torch
+
+    from gpras_b200.engine import SparseGP
+    from gpras_b200.synth import make_gp_data
+    from oracle import sgpr
+
+    data = make_gp_data(n, d, 1, 200, seed=n + m)
+    rng = np.random.default_rng(m)
+    z = data.x[rng.choice(n, m, replace=False)] + 0.05 * rng.standard_normal((m, d))
+    var, noise = 1.3, 0.2
+    ls = rng.uniform(1.0, 3.0, d) if ard else np.array([1.7])
+    gp = SparseGP(kernel, n, d, m, 1)
+    gp.set_data(data.x, data.y)
+    th = gp.theta_vector(var, noise, ls)
+    elbo, gt, gz = gp.elbo_grad(th, z)
+    t = lambda a, g=False: torch.tensor(np.asarray(a, np.float64), requires_grad=g)  # noqa: E731
+    tv, tl, tn, tz = t(var, True), t(ls, True), t(noise, True), t(z, True)
+    e = sgpr.elbo(kernel, t(data.x), t(data.y), tz, tv, tl, tn)
+    gv, gl, gn, gzz = torch.autograd.grad(e, [tv, tl, tn, tz])
+    assert abs(elbo - float(e.detach())) <= LML_RTOL * abs(float(e.detach()))
+    assert abs(gt[0] - float(gv) * var) <= 1e-6 * max(1.0, abs(float(gv) * var))
+    assert abs(gt[1] - float(gn) * noise) <= 1e-6 * max(1.0, abs(float(gn) * noise))
+    gl_ref = gl.numpy() * ls
+    got_ls = gt[2:] if ard else np.array([gt[2:].sum()])
+    np.testing.assert_allclose(got_ls, gl_ref, rtol=1e-6, atol=1e-6 * max(1.0, np.abs(gl_ref).max()))
+    np.testing.assert_allclose(gz, gzz.numpy(), rtol=1e-6, atol=1e-7 * max(1.0, np.abs(gzz.numpy()).max()))
+    elbo_only, _, _ = gp.elbo_grad(th, z, want_grad=False)
+    assert elbo_only == elbo
+    gp.condition(th, z)
+    mean, v = gp.predict(data.x_test)
+    om, ov = sgpr.predict_y(kernel, data.x, data.y, z, var, ls, noise, data.x_test)
+    np.testing.assert_allclose(mean, om, rtol=MEAN_RTOL, atol=MEAN_RTOL * np.abs(om).max())
+    np.testing.assert_allclose(np.sqrt(v), np.sqrt(ov), rtol=STD_RTOL)
+    gp.close()
+
+
+def test_gpras_sparse_fit_like_the_reference(cuda, tmp_path):
+    from gpras_b200 import GPRAS
+    from gpras_b200.synth import make_gp_data
+    from oracle import sgpr
+
+    data = make_gp_data(400, 4, 2, 30, seed=7)
+    g = GPRAS("Matern52")
+    g.fit(data.x, data.y, 16, "kmeans", "two-stage", max_iter=15)  # the reference's default recipe
+    assert len(g.models) == 2 and g.models[0].inducing_variable.Z.shape == (16, 4)
+    mean, var = g.predict(data.x_test)
+    assert mean.shape == (30, 2) and np.all(var > 0)
+    for i, m in enumerate(g.models):
+        om, ov = sgpr.predict_y("Matern52", data.x, data.y[:, i : i + 1], m.inducing_variable.Z, m.kernel.variance.numpy(),
+                                m.kernel.lengthscales.numpy(), m.likelihood.variance.numpy(), data.x_test)
+        np.testing.assert_allclose(mean[:, i : i + 1], om, rtol=1e-7, atol=1e-8)
+        np.testing.assert_allclose(np.sqrt(var[:, i : i + 1]), np.sqrt(ov), rtol=STD_RTOL)
+    # training loss (with priors) equals the oracle's at the fitted parameters
+    m0 = g.models[0]
+    from gpras_b200.gpr import _softplus_inv
+
+    o = sgpr.training_loss_and_grads("Matern52", data.x, data.y[:, :1], m0.inducing_variable.Z,
+                                     _softplus_inv(m0.kernel.variance.numpy()), _softplus_inv(np.atleast_1d(m0.kernel.lengthscales.numpy())),
+                                     _softplus_inv(m0.likelihood.variance.numpy() - 1e-6))
+    loss, grad = m0.loss_and_grad()
+    assert abs(loss - o["loss"]) <= 1e-8 * abs(o["loss"])
+    ref = np.concatenate([np.atleast_1d(o["u_var"]), np.atleast_1d(o["u_noise"]), np.atleast_1d(o["u_ls"]), o["z"].ravel()])
+    np.testing.assert_allclose(grad, ref, rtol=1e-6, atol=1e-6 * np.abs(ref).max())
+    path = tmp_path / "sparse.pkl"
+    g.to_file(path)
+    g2 = GPRAS.from_file(path)
+    m2, v2 = g2.predict(data.x_test)
+    np.testing.assert_allclose(m2, mean, rtol=1e-8, atol=1e-10)
+    # L-BFGS-B polish improves the loss (three-stage style)
+    before = m0.training_loss()
+    from gpras_b200.gpr import _optimize_bfgs
+
+    _optimize_bfgs(m0, 20)
+    assert m0.training_loss() < before
