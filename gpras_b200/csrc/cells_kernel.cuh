@@ -1,0 +1,109 @@
+// Modes -> mesh-cells expansion (PreProcessor.reverse_transform, gpras/preprocess.py:1052-1094) as one streaming
+// kernel: the step that turns (T x P) predictions into "cell-depths".
+//
+//   cell_mean[t][c] = sum_p M[t][p] E[p][c] + bias[c]          (DMMA, k = P <= 64)
+//   cell_var [t][c] = var[t] * S[c],   S[c] = sum_p E[p][c]^2  (all P columns share theta, so the variance is rank one)
+//
+// The output is 16 bytes per cell-depth against ~2P flops: HBM-write bound.  A CTA owns one 128-cell column tile,
+// keeps its E tile in shared memory and its bias / S fragments in registers, and streams row tiles of 128 events
+// through a double-buffered cp.async ring, so E is read once per CTA and the only steady-state traffic is the
+// (tiny) mode-space input and the cell-space output.  Two CTAs per SM overlap one tile's stores with the next tile's
+// DMMAs.  Rows wrap modulo `ring_rows` when the caller does not keep the T x C result.
+#pragma once
+#include "common.cuh"
+
+namespace gpras {
+
+constexpr int CELLS_THREADS = 256;
+
+template <int P16>
+struct CellsCfg {
+  static constexpr int LDE = 128 + 4;   // k-major E tile [P16][132]
+  static constexpr int LDA = P16 + 4;   // row-major mode tile [128][P16 + 4]
+  static constexpr int SMEM_DOUBLES = P16 * LDE + 2 * 128 * LDA + 2 * 128;
+  static constexpr int SMEM_BYTES = SMEM_DOUBLES * (int)sizeof(double);
+};
+
+template <int P16>
+__global__ void __launch_bounds__(CELLS_THREADS, 2)
+cells_kernel(const double* __restrict__ M, long ldm, const double* __restrict__ var, const double* __restrict__ E, long lde,
+             const double* __restrict__ bias, const double* __restrict__ S, double* __restrict__ out_m,
+             double* __restrict__ out_v, long ldo, int t_tiles, int tiles_per_cta, int ring_rows) {
+  using Cfg = CellsCfg<P16>;
+  extern __shared__ __align__(16) double smem[];
+  double* sE = smem;                        // [P16][LDE]
+  double* sA = sE + P16 * Cfg::LDE;         // [2][128][LDA]
+  double* sV = sA + 2 * 128 * Cfg::LDA;     // [2][128]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int tj = blockIdx.x;
+  const int t_begin = blockIdx.y * tiles_per_cta;
+  int t_end = t_begin + tiles_per_cta;
+  if (t_end > t_tiles) t_end = t_tiles;
+  if (t_begin >= t_end) return;
+
+  auto load_rows = [&](int buf, int tt) {
+    // 128 rows x P16 doubles, 16-byte chunks
+    constexpr int CPR = P16 / 2;
+    for (int c = tid; c < 128 * CPR; c += CELLS_THREADS) {
+      const int row = c / CPR, kc = c - row * CPR;
+      cp_async16(sA + (buf * 128 + row) * Cfg::LDA + 2 * kc, M + (long)(tt * 128 + row) * ldm + 2 * kc);
+    }
+    if (tid < 64) cp_async16(sV + buf * 128 + 2 * tid, var + (long)tt * 128 + 2 * tid);
+  };
+  // E tile + first row tile
+  for (int c = tid; c < P16 * 64; c += CELLS_THREADS) {
+    const int kr = c >> 6, mc = c & 63;
+    cp_async16(sE + kr * Cfg::LDE + 2 * mc, E + (long)kr * lde + (long)tj * 128 + 2 * mc);
+  }
+  load_rows(0, t_begin);
+  cp_async_commit();
+  double bs[4][2], ss[4][2];
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    const long c = (long)tj * 128 + wn + 8 * h + 2 * q;
+    bs[h][0] = bias[c], bs[h][1] = bias[c + 1];
+    ss[h][0] = S[c], ss[h][1] = S[c + 1];
+  }
+  for (int tt = t_begin; tt < t_end; tt++) {
+    const int buf = (tt - t_begin) & 1;
+    cp_async_wait<0>();
+    __syncthreads();
+    if (tt + 1 < t_end) load_rows(buf ^ 1, tt + 1);
+    cp_async_commit();
+    double acc[8][4][2];
+#pragma unroll
+    for (int f = 0; f < 8; f++)
+#pragma unroll
+      for (int h = 0; h < 4; h++) acc[f][h][0] = bs[h][0], acc[f][h][1] = bs[h][1];
+    const double* a0 = sA + buf * 128 * Cfg::LDA;
+#pragma unroll
+    for (int ks = 0; ks < P16 / 4; ks++) {
+      double a[8], b[4];
+#pragma unroll
+      for (int f = 0; f < 8; f++) a[f] = a0[(wm + 8 * f + g) * Cfg::LDA + 4 * ks + q];
+#pragma unroll
+      for (int h = 0; h < 4; h++) b[h] = sE[(4 * ks + q) * Cfg::LDE + wn + 8 * h + g];
+#pragma unroll
+      for (int f = 0; f < 8; f++)
+#pragma unroll
+        for (int h = 0; h < 4; h++) dmma(acc[f][h][0], acc[f][h][1], a[f], b[h]);
+    }
+    const long row0 = ((long)tt * 128) % ring_rows;
+#pragma unroll
+    for (int f = 0; f < 8; f++) {
+      const int r = wm + 8 * f + g;
+      const double vr = sV[buf * 128 + r];
+      double* pm = out_m + (row0 + r) * ldo + (long)tj * 128 + wn + 2 * q;
+      double* pv = out_v + (row0 + r) * ldo + (long)tj * 128 + wn + 2 * q;
+#pragma unroll
+      for (int h = 0; h < 4; h++) {
+        *reinterpret_cast<double2*>(pm + 8 * h) = make_double2(acc[f][h][0], acc[f][h][1]);
+        *reinterpret_cast<double2*>(pv + 8 * h) = make_double2(vr * ss[h][0], vr * ss[h][1]);
+      }
+    }
+  }
+}
+
+}  // namespace gpras

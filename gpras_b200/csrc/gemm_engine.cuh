@@ -6,7 +6,7 @@
 //
 //   C[i, j] (op)= alpha * sum_{k in [k_begin, k_end)} A(i, k) * B(k, j)
 //
-// * 256 threads = 8 warps arranged WARPS_M x WARPS_N over a BM x BN CTA tile; every warp owns
+// * 8 or 16 warps arranged WARPS_M x WARPS_N over a BM x BN CTA tile; every warp owns
 //   MF x NF DMMA.8x8x4 accumulators.  Three tile shapes are instantiated:
 //       CfgL 128x128, warp 64x32, BK 32, 3 stages, 1 CTA/SM  -- long-k products (LAUUM, TRTRI, predictor)
 //       CfgS 128x64,  warp 32x32, 3 stages, 2 CTA/SM  -- short-k rank-128 updates of the Cholesky, where a
@@ -29,23 +29,24 @@
 
 namespace gpras {
 
-constexpr int GEMM_THREADS = 256;
 constexpr int K_ALIGN = 32;  // every k extent / clip point handed to the engine is a multiple of this (>= any BK)
 
 template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_, int MINB_>
 struct TileCfg {
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_, MINB = MINB_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
   static constexpr int MF = WM / 8, NF = WN / 8;
   static constexpr int LD_RM = BK + 4;  // row / n-major tile [rows][BK + 4] (k contiguous); == 4 mod 16
   static constexpr int A_DOUBLES = BM * LD_RM > BK * (BM + 4) ? BM * LD_RM : BK * (BM + 4);
   static constexpr int B_DOUBLES = BN * LD_RM > BK * (BN + 4) ? BN * LD_RM : BK * (BN + 4);
   static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
-  static_assert(WARPS_M * WARPS_N == 8, "8 warps per CTA");
+  static_assert(THREADS == 256 || THREADS == 512, "8 or 16 warps per CTA");
   static_assert(BK % 16 == 0 && BK <= K_ALIGN, "BK");
 };
 using CfgL = TileCfg<128, 128, 64, 32, 32, 3, 1>;  // 216 KiB: three 72 KiB stages, one barrier per 256 DMMAs / warp
+// (16 warps of 32x32 on the same tile measured 2% slower on LAUUM: the loop is not barrier-skew bound)
 using CfgS = TileCfg<128, 64, 32, 32, 16, 3, 2>;
 using CfgN = TileCfg<128, 32, 16, 32, 16, 4, 2>;
 using CfgP = TileCfg<64, 128, 32, 32, 16, 3, 2>;   // in-place Cholesky panel: full 128-column width per CTA (no tri mode)
@@ -68,12 +69,13 @@ struct GemmDesc {
   int kb_mode, ke_mode;
   int tri;              // 1: only tiles whose columns start at or below the row tile's last row
   int reverse;          // 1: launch order reversed (heaviest tiles first for LPT scheduling)
+  int colmajor;         // 1: non-tri tiles enumerate rows fastest (use when the work depends on the column tile)
   int epilogue;
   double alpha, beta;
 };
 
 // ROWS x BK tile, global -> shared.  Row-major: ROWS rows of BK doubles; k-major: BK rows of ROWS doubles.
-template <bool KMAJOR, int ROWS, int BK>
+template <bool KMAJOR, int ROWS, int BK, int GEMM_THREADS>
 __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ g, long ld, int tid) {
   constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks in the tile
   constexpr int LD_RM = BK + 4;
@@ -96,7 +98,7 @@ __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* 
 }
 
 template <typename Cfg, bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(const GemmDesc d) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_tile_kernel(const GemmDesc d) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, MF = Cfg::MF, NF = Cfg::NF, STAGES = Cfg::STAGES, BK = Cfg::BK;
   constexpr int LD_RM = Cfg::LD_RM;
   constexpr int LDA_KM = BM + 4, LDB_KM = BN + 4, RATIO = BM >= BN ? BM / BN : 1;
@@ -115,6 +117,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(cons
     while ((long)RATIO * (ti + 1) * (ti + 2) / 2 <= t) ti++;
     while ((long)RATIO * ti * (ti + 1) / 2 > t) ti--;
     tj = t - (int)((long)RATIO * ti * (ti + 1) / 2);
+  } else if (d.colmajor) {
+    tj = t / d.m_tiles;
+    ti = t - tj * d.m_tiles;
   } else {
     ti = t / d.n_tiles;
     tj = t - ti * d.n_tiles;
@@ -145,8 +150,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(cons
   for (int s = 0; s < STAGES - 1; s++) {
     if (s < nk) {
       double* sA = smem + s * Cfg::STAGE_DOUBLES;
-      load_tile<A_KMAJOR, BM, BK>(sA, gA + s * stepA, d.lda, tid);
-      load_tile<B_KMAJOR, BN, BK>(sA + Cfg::A_DOUBLES, gB + s * stepB, d.ldb, tid);
+      load_tile<A_KMAJOR, BM, BK, Cfg::THREADS>(sA, gA + s * stepA, d.lda, tid);
+      load_tile<B_KMAJOR, BN, BK, Cfg::THREADS>(sA + Cfg::A_DOUBLES, gB + s * stepB, d.ldb, tid);
     }
     cp_async_commit();
   }
@@ -179,8 +184,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, Cfg::MINB) gemm_tile_kernel(cons
       const int nx = kt + STAGES - 1;
       if (nx < nk) {
         double* sA = smem + (nx % STAGES) * Cfg::STAGE_DOUBLES;
-        load_tile<A_KMAJOR, BM, BK>(sA, gA + nx * stepA, d.lda, tid);
-        load_tile<B_KMAJOR, BN, BK>(sA + Cfg::A_DOUBLES, gB + nx * stepB, d.ldb, tid);
+        load_tile<A_KMAJOR, BM, BK, Cfg::THREADS>(sA, gA + nx * stepA, d.lda, tid);
+        load_tile<B_KMAJOR, BN, BK, Cfg::THREADS>(sA + Cfg::A_DOUBLES, gB + nx * stepB, d.ldb, tid);
       }
       cp_async_commit();
     }

@@ -1,6 +1,7 @@
 // C ABI of gpras_b200, exact-GP part (see include/gpras_b200.h): host-side orchestration of the sm_100a kernels.
 // No CPU compute path exists in this file: every entry point either launches CUDA work or fails.
 #include "host_common.cuh"
+#include "cells_kernel.cuh"
 
 namespace {
 
@@ -404,30 +405,35 @@ int gpras_gp_predict(gpras_gp* h, const double* xs, int t, double* mean, double*
 
 int gpras_gp_set_cell_map(gpras_gp* h, const double* e_mean, const double* bias, int c) {
   if (!h || !e_mean || !bias || c <= 0) return fail(GPRAS_E_ARG, "bad argument");
+  if (h->p > 64) return fail(GPRAS_E_ARG, "more than 64 modes are not supported by the cell expansion");
   DeviceGuard guard(h->device);
   double* olds[] = {h->E1, h->E2, h->bias, h->zbias, h->ring_m, h->ring_v};
   for (double* b : olds)
     if (b) cudaFree(b);
   h->E1 = h->E2 = h->bias = h->zbias = h->ring_m = h->ring_v = nullptr;
-  h->c = c, h->c_pad = round_up(c, 128), h->p16 = round_up(h->p, 32);
+  h->c = c, h->c_pad = round_up(c, 128), h->p16 = h->p <= 32 ? 32 : 64;
   const size_t ne = (size_t)h->p16 * h->c_pad;
   int r;
-  if ((r = dalloc(&h->E1, ne)) || (r = dalloc(&h->E2, ne)) || (r = dalloc(&h->bias, h->c_pad)) ||
-      (r = dalloc(&h->zbias, h->c_pad)))
-    return r;
-  std::vector<double> e1(ne, 0.0), e2(ne, 0.0), b(h->c_pad, 0.0);
+  // E2 holds S[c] = sum_p E[p][c]^2: every mode shares theta, so cell variance = var[t] * S[c]
+  if ((r = dalloc(&h->E1, ne)) || (r = dalloc(&h->E2, h->c_pad)) || (r = dalloc(&h->bias, h->c_pad))) return r;
+  std::vector<double> e1(ne, 0.0), sq(h->c_pad, 0.0), b(h->c_pad, 0.0);
   for (int pp = 0; pp < h->p; pp++)
     for (int cc = 0; cc < c; cc++) {
-      double v = e_mean[(size_t)pp * c + cc];
+      const double v = e_mean[(size_t)pp * c + cc];
       e1[(size_t)pp * h->c_pad + cc] = v;
-      e2[(size_t)pp * h->c_pad + cc] = v * v;
+      sq[cc] += v * v;
     }
   memcpy(b.data(), bias, sizeof(double) * c);
   CU(cudaMemcpyAsync(h->E1, e1.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->E2, e2.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->E2, sq.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->bias, b.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemsetAsync(h->zbias, 0, sizeof(double) * h->c_pad, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  static bool attr_done[64] = {};
+  if (h->device < 64 && !attr_done[h->device]) {
+    if ((r = opt_in_smem(cells_kernel<32>, CellsCfg<32>::SMEM_BYTES)) || (r = opt_in_smem(cells_kernel<64>, CellsCfg<64>::SMEM_BYTES)))
+      return r;
+    attr_done[h->device] = true;
+  }
   return 0;
 }
 
@@ -438,7 +444,8 @@ int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_devic
   if (!h || !xs || t < 0) return fail(GPRAS_E_ARG, "bad argument");
   if (!h->conditioned) return fail(GPRAS_E_STATE, "condition() has not been called");
   if (!h->E1) return fail(GPRAS_E_STATE, "set_cell_map() has not been called");
-  if ((cell_mean || cell_var) && ldc < h->c_pad) return fail(GPRAS_E_ARG, "ldc smaller than gpras_gp_cell_pitch()");
+  if ((cell_mean != nullptr) != (cell_var != nullptr)) return fail(GPRAS_E_ARG, "pass both cell_mean and cell_var, or neither");
+  if (cell_mean && ldc < h->c_pad) return fail(GPRAS_E_ARG, "ldc smaller than gpras_gp_cell_pitch()");
   DeviceGuard guard(h->device);
   int r;
   if ((r = ensure_predict_buffers(h))) return r;
@@ -463,20 +470,24 @@ int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_devic
     if (mode_var)
       CU(cudaMemcpy2DAsync(mode_var + (size_t)t0 * h->p, sizeof(double) * h->p, h->varm, sizeof(double) * h->p_pad,
                            sizeof(double) * h->p, tb, cudaMemcpyDeviceToHost, s));
-    // modes -> cells, CELL_TB rows at a time: cells = modes @ E (+ bias), one DMMA GEMM each for mean and variance
-    for (int c0 = 0; c0 < tb_pad; c0 += CELL_TB) {
-      const int cb = tb_pad - c0 < CELL_TB ? tb_pad - c0 : CELL_TB;
-      double* om = cell_mean ? cell_mean + (size_t)(t0 + c0) * ldc : h->ring_m;
-      double* ov = cell_var ? cell_var + (size_t)(t0 + c0) * ldc : h->ring_v;
-      const long ldo_m = cell_mean ? ldc : h->c_pad, ldo_v = cell_var ? ldc : h->c_pad;
-      GemmDesc gm = make_desc(h->mean + (size_t)c0 * h->p_pad, h->p_pad, h->E1, h->c_pad, om, ldo_m, cb / 128,
-                              h->c_pad / 128, h->p16);
-      gm.epilogue = EPI_BIAS, gm.bias = h->bias;
-      if ((r = launch_gemm(s, false, true, gm, 1, &h->launches))) return r;
-      GemmDesc gv = make_desc(h->varm + (size_t)c0 * h->p_pad, h->p_pad, h->E2, h->c_pad, ov, ldo_v, cb / 128,
-                              h->c_pad / 128, h->p16);
-      gv.epilogue = EPI_BIAS, gv.bias = h->zbias;
-      if ((r = launch_gemm(s, false, true, gv, 1, &h->launches))) return r;
+    // modes -> cells: one streaming kernel per batch (column tile per CTA, row tiles streamed)
+    {
+      const bool keep = cell_mean != nullptr && cell_var != nullptr;
+      double* om = keep ? cell_mean + (size_t)t0 * ldc : h->ring_m;
+      double* ov = keep ? cell_var + (size_t)t0 * ldc : h->ring_v;
+      const long ldo = keep ? ldc : h->c_pad;
+      const int ring_rows = keep ? (1 << 30) : CELL_TB;
+      const int t_tiles = tb_pad / 128;
+      const int per_cta = (t_tiles + 1) / 2;
+      dim3 grid(h->c_pad / 128, (t_tiles + per_cta - 1) / per_cta);
+      if (h->p16 == 32)
+        cells_kernel<32><<<grid, CELLS_THREADS, CellsCfg<32>::SMEM_BYTES, s>>>(h->mean, h->p_pad, h->var, h->E1, h->c_pad, h->bias,
+                                                                             h->E2, om, ov, ldo, t_tiles, per_cta, ring_rows);
+      else
+        cells_kernel<64><<<grid, CELLS_THREADS, CellsCfg<64>::SMEM_BYTES, s>>>(h->mean, h->p_pad, h->var, h->E1, h->c_pad, h->bias,
+                                                                             h->E2, om, ov, ldo, t_tiles, per_cta, ring_rows);
+      h->launches++;
+      CU(cudaGetLastError());
     }
     if (!xs_on_device) CU(cudaStreamSynchronize(s));
   }

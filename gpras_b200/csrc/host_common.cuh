@@ -93,7 +93,7 @@ int launch_cfg(cudaStream_t s, const GemmDesc& d, int batch, int nz) {
   constexpr int ratio = Cfg::BM / Cfg::BN;
   long tiles = d.tri ? (long)ratio * d.m_tiles * (d.m_tiles + 1) / 2 : (long)d.m_tiles * d.n_tiles;
   dim3 grid((unsigned)tiles, (unsigned)batch, (unsigned)nz);
-  gemm_tile_kernel<Cfg, AKM, BKM><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(d);
+  gemm_tile_kernel<Cfg, AKM, BKM><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(d);
   CU(cudaGetLastError());
   return 0;
 }
@@ -256,6 +256,7 @@ int trtri_impl(cudaStream_t s, const double* L, long ldl, double* W, long ldw, d
       // T = L21 W11   (A row-major full; B = W11 k-major, lower: k >= tj)
       GemmDesc g1 = make_desc(L + rb * ldl + r0, ldl, W + r0 * (ldw + 1), ldw, T + rb * ldt + r0, ldt, m2, b, b * 128);
       g1.kb_mode = KB_TJ;
+      g1.colmajor = 1;  // k range shrinks with the column tile: heaviest columns first
       g1.batchA = bsL, g1.batchB = bsW, g1.batchC = bsT;
       int r = launch_gemm(s, false, true, g1, batch, launches);
       if (r) return r;
