@@ -5,22 +5,24 @@
 //   cell_var [t][c] = var[t] * S[c],   S[c] = sum_p E[p][c]^2  (all P columns share theta, so the variance is rank one)
 //
 // The output is 16 bytes per cell-depth against ~2P flops: HBM-write bound.  A CTA owns one 128-cell column tile,
-// keeps its E tile in shared memory and its bias / S fragments in registers, and streams row tiles of 128 events
+// keeps its E tile in shared memory and its bias / S fragments in registers, and streams row tiles of 64 events
 // through a double-buffered cp.async ring, so E is read once per CTA and the only steady-state traffic is the
 // (tiny) mode-space input and the cell-space output.  Two CTAs per SM overlap one tile's stores with the next tile's
-// DMMAs.  Rows wrap modulo `ring_rows` when the caller does not keep the T x C result.
+// DMMAs (row tiles of 64 keep the accumulators at 64 registers, so two CTAs fit without spills).  Rows wrap modulo
+// `ring_rows` when the caller does not keep the T x C result.
 #pragma once
 #include "common.cuh"
 
 namespace gpras {
 
 constexpr int CELLS_THREADS = 256;
+constexpr int CELLS_ROWS = 64;  // events per row tile
 
 template <int P16>
 struct CellsCfg {
   static constexpr int LDE = 128 + 4;   // k-major E tile [P16][132]
   static constexpr int LDA = P16 + 4;   // row-major mode tile [128][P16 + 4]
-  static constexpr int SMEM_DOUBLES = P16 * LDE + 2 * 128 * LDA + 2 * 128;
+  static constexpr int SMEM_DOUBLES = P16 * LDE + 2 * CELLS_ROWS * LDA + 2 * CELLS_ROWS;
   static constexpr int SMEM_BYTES = SMEM_DOUBLES * (int)sizeof(double);
 };
 
@@ -32,11 +34,11 @@ cells_kernel(const double* __restrict__ M, long ldm, const double* __restrict__ 
   using Cfg = CellsCfg<P16>;
   extern __shared__ __align__(16) double smem[];
   double* sE = smem;                        // [P16][LDE]
-  double* sA = sE + P16 * Cfg::LDE;         // [2][128][LDA]
-  double* sV = sA + 2 * 128 * Cfg::LDA;     // [2][128]
+  double* sA = sE + P16 * Cfg::LDE;               // [2][CELLS_ROWS][LDA]
+  double* sV = sA + 2 * CELLS_ROWS * Cfg::LDA;    // [2][CELLS_ROWS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
   const int tj = blockIdx.x;
   const int t_begin = blockIdx.y * tiles_per_cta;
   int t_end = t_begin + tiles_per_cta;
@@ -44,13 +46,13 @@ cells_kernel(const double* __restrict__ M, long ldm, const double* __restrict__ 
   if (t_begin >= t_end) return;
 
   auto load_rows = [&](int buf, int tt) {
-    // 128 rows x P16 doubles, 16-byte chunks
+    // CELLS_ROWS rows x P16 doubles, 16-byte chunks
     constexpr int CPR = P16 / 2;
-    for (int c = tid; c < 128 * CPR; c += CELLS_THREADS) {
+    for (int c = tid; c < CELLS_ROWS * CPR; c += CELLS_THREADS) {
       const int row = c / CPR, kc = c - row * CPR;
-      cp_async16(sA + (buf * 128 + row) * Cfg::LDA + 2 * kc, M + (long)(tt * 128 + row) * ldm + 2 * kc);
+      cp_async16(sA + (buf * CELLS_ROWS + row) * Cfg::LDA + 2 * kc, M + (long)(tt * CELLS_ROWS + row) * ldm + 2 * kc);
     }
-    if (tid < 64) cp_async16(sV + buf * 128 + 2 * tid, var + (long)tt * 128 + 2 * tid);
+    if (tid < CELLS_ROWS / 2) cp_async16(sV + buf * CELLS_ROWS + 2 * tid, var + (long)tt * CELLS_ROWS + 2 * tid);
   };
   // E tile + first row tile
   for (int c = tid; c < P16 * 64; c += CELLS_THREADS) {
@@ -72,35 +74,50 @@ cells_kernel(const double* __restrict__ M, long ldm, const double* __restrict__ 
     __syncthreads();
     if (tt + 1 < t_end) load_rows(buf ^ 1, tt + 1);
     cp_async_commit();
-    double acc[8][4][2];
+    double acc[4][4][2];
 #pragma unroll
-    for (int f = 0; f < 8; f++)
+    for (int f = 0; f < 4; f++)
 #pragma unroll
       for (int h = 0; h < 4; h++) acc[f][h][0] = bs[h][0], acc[f][h][1] = bs[h][1];
-    const double* a0 = sA + buf * 128 * Cfg::LDA;
+    const double* a0 = sA + buf * CELLS_ROWS * Cfg::LDA;
 #pragma unroll
     for (int ks = 0; ks < P16 / 4; ks++) {
-      double a[8], b[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int f = 0; f < 8; f++) a[f] = a0[(wm + 8 * f + g) * Cfg::LDA + 4 * ks + q];
+      for (int f = 0; f < 4; f++) a[f] = a0[(wm + 8 * f + g) * Cfg::LDA + 4 * ks + q];
 #pragma unroll
       for (int h = 0; h < 4; h++) b[h] = sE[(4 * ks + q) * Cfg::LDE + wn + 8 * h + g];
 #pragma unroll
-      for (int f = 0; f < 8; f++)
+      for (int f = 0; f < 4; f++)
 #pragma unroll
         for (int h = 0; h < 4; h++) dmma(acc[f][h][0], acc[f][h][1], a[f], b[h]);
     }
-    const long row0 = ((long)tt * 128) % ring_rows;
+    // Stores are arranged so that every warp instruction writes whole 128-byte lines (4 rows x 128 B): lanes g and
+    // g^1 swap one 16-byte chunk by shuffle, then the 8 lanes of a row pair cover one row's 128-byte half-row.
+    // (Writing each line as two 64-byte halves from separate instructions doubled the DRAM write traffic.)
+    const long row0 = ((long)tt * CELLS_ROWS) % ring_rows;
+    const int godd = g & 1;
 #pragma unroll
-    for (int f = 0; f < 8; f++) {
-      const int r = wm + 8 * f + g;
-      const double vr = sV[buf * 128 + r];
-      double* pm = out_m + (row0 + r) * ldo + (long)tj * 128 + wn + 2 * q;
-      double* pv = out_v + (row0 + r) * ldo + (long)tj * 128 + wn + 2 * q;
+    for (int f = 0; f < 4; f++) {
 #pragma unroll
-      for (int h = 0; h < 4; h++) {
-        *reinterpret_cast<double2*>(pm + 8 * h) = make_double2(acc[f][h][0], acc[f][h][1]);
-        *reinterpret_cast<double2*>(pv + 8 * h) = make_double2(vr * ss[h][0], vr * ss[h][1]);
+      for (int w = 0; w < 2; w++) {
+        double2 mine0 = make_double2(acc[f][2 * w][0], acc[f][2 * w][1]);
+        double2 mine1 = make_double2(acc[f][2 * w + 1][0], acc[f][2 * w + 1][1]);
+        double2 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, mine1.x, 4);
+        recv.y = __shfl_xor_sync(0xffffffffu, mine1.y, 4);
+#pragma unroll
+        for (int sft = 0; sft < 2; sft++) {
+          // sft = 0: the even row of the pair is written; sft = 1: the odd row
+          const int rl = wm + 8 * f + (sft ? (g | 1) : (g & ~1));
+          const bool own = (godd == sft);
+          const int hh = 2 * w + (own ? 0 : 1);
+          const double2 mv = own ? mine0 : recv;
+          const double vr = sV[buf * CELLS_ROWS + rl];
+          const long off = (row0 + rl) * ldo + (long)tj * 128 + wn + 8 * hh + 2 * q;
+          *reinterpret_cast<double2*>(out_m + off) = mv;
+          *reinterpret_cast<double2*>(out_v + off) = make_double2(vr * ss[hh][0], vr * ss[hh][1]);
+        }
       }
     }
   }

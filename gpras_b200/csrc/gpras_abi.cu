@@ -477,7 +477,7 @@ int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_devic
       double* ov = keep ? cell_var + (size_t)t0 * ldc : h->ring_v;
       const long ldo = keep ? ldc : h->c_pad;
       const int ring_rows = keep ? (1 << 30) : CELL_TB;
-      const int t_tiles = tb_pad / 128;
+      const int t_tiles = tb_pad / CELLS_ROWS;
       const int per_cta = (t_tiles + 1) / 2;
       dim3 grid(h->c_pad / 128, (t_tiles + per_cta - 1) / per_cta);
       if (h->p16 == 32)
