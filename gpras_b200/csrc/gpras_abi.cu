@@ -1,5 +1,7 @@
 // C ABI of gpras_b200, exact-GP part (see include/gpras_b200.h): host-side orchestration of the sm_100a kernels.
 // No CPU compute path exists in this file: every entry point either launches CUDA work or fails.
+#include <cstdlib>
+
 #include "host_common.cuh"
 #include "cells_kernel.cuh"
 
@@ -71,6 +73,10 @@ struct gpras_gp {
   cudaEvent_t ev[8] = {};
   double stage_ms[7] = {};
   LookAhead la;
+  // CUDA-graph replay of the evaluation (index: want_grad)
+  bool use_graphs = true, graph_failed = false, eager_done[2] = {false, false};
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  int graph_launches[2] = {0, 0};
 };
 
 namespace {
@@ -119,14 +125,11 @@ int factorise(gpras_gp* h, bool need_alpha, bool need_kinv) {
   return 0;
 }
 
-int enqueue_eval(gpras_gp* h, const double* theta, int want_grad) {
-  if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
+// Enqueue every operation of one evaluation on h->stream (theta is already in the pinned staging buffer).
+int record_eval(gpras_gp* h, int want_grad) {
   cudaStream_t s = h->stream;
   const int n = h->n, n_pad = h->n_pad, D = h->d, P = h->p;
   int r;
-  h->launches = 0;
-  h->conditioned = false;
-  memcpy(h->h_theta, theta, sizeof(double) * (2 + D));
   CU(cudaMemcpyAsync(h->theta, h->h_theta, sizeof(double) * (2 + D), cudaMemcpyHostToDevice, s));
   if ((r = factorise(h, want_grad != 0, want_grad != 0))) return r;
   sumsq_partial_kernel<<<USQ_PARTS, 256, 0, s>>>(h->U, n_pad, P, h->p_pad, h->usq);
@@ -149,6 +152,53 @@ int enqueue_eval(gpras_gp* h, const double* theta, int want_grad) {
   mark(h, 6);
   CU(cudaMemcpyAsync(h->h_result, h->result, sizeof(double) * (3 + D), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(h->h_info, h->info, sizeof(int), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// One evaluation = ~20 + 5 N/128 launches over two streams.  theta lives in device memory, so the whole sequence
+// is captured once per (handle, want_grad) into a CUDA graph and replayed: one launch per evaluation instead of
+// hundreds (the first evaluation runs eagerly: it creates streams / events and sets kernel attributes).
+int enqueue_eval(gpras_gp* h, const double* theta, int want_grad) {
+  if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
+  cudaStream_t s = h->stream;
+  h->conditioned = false;
+  memcpy(h->h_theta, theta, sizeof(double) * (2 + h->d));
+  const int g = want_grad ? 1 : 0;
+  int r;
+  if (h->use_graphs && !h->stage_timing && h->graph[g]) {
+    h->launches = h->graph_launches[g];
+    CU(cudaGraphLaunch(h->graph[g], s));
+  } else if (h->use_graphs && !h->stage_timing && h->eager_done[g] && !h->graph_failed) {
+    h->launches = 0;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    r = record_eval(h, want_grad);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (r != 0 || e != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      h->graph_failed = true;  // fall back to eager launches (still the CUDA path, never a CPU one)
+      h->launches = 0;
+      if ((r = record_eval(h, want_grad))) return r;
+    } else {
+      e = cudaGraphInstantiate(&h->graph[g], graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        h->graph[g] = nullptr;
+        h->graph_failed = true;
+        h->launches = 0;
+        if ((r = record_eval(h, want_grad))) return r;
+      } else {
+        h->graph_launches[g] = h->launches;
+        CU(cudaGraphLaunch(h->graph[g], s));
+      }
+    }
+  } else {
+    h->launches = 0;
+    if ((r = record_eval(h, want_grad))) return r;
+    h->eager_done[g] = true;
+  }
   h->pending = true;
   h->pending_grad = want_grad != 0;
   return 0;
@@ -206,6 +256,9 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
   h->n_pad = round_up(n, 128), h->p_pad = round_up(p, 32), h->nt = h->n_pad / 128;
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
+  // graph replay pays off while the evaluation is launch/latency bound (measured: +6..10% for N <= 4096, -3% at
+  // N = 8192 with two evaluations in flight, where eager launches interleave better across handles)
+  h->use_graphs = h->n_pad <= 4096 && !getenv("GPRAS_B200_NO_GRAPHS");
   const size_t nn = (size_t)h->n_pad * h->n_pad, np = (size_t)h->n_pad * h->p_pad;
   const int ntile = h->nt * (h->nt + 1) / 2;
   if ((r = dalloc(&h->X, (size_t)h->n_pad * d)) || (r = dalloc(&h->Xs, (size_t)h->n_pad * d)) || (r = dalloc(&h->Y, np)) ||
@@ -246,6 +299,8 @@ int gpras_gp_destroy(gpras_gp* h) {
   if (h->h_info) cudaFreeHost(h->h_info);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& g : h->graph)
+    if (g) cudaGraphExecDestroy(g);
   h->la.destroy();
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;

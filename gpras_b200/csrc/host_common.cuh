@@ -196,10 +196,10 @@ int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, lo
     GemmDesc p = make_desc(pn, lda, wjj, ldw, pn, lda, 2 * rem, 1, 128);
     return launch_gemm(st, false, false, p, 1, launches, SHAPE_P);
   };
+  if ((r = leaf(s, 0))) return r;
+  if (nt == 1) return 0;  // single block: nothing to overlap, the side stream stays out of it
   CU(cudaEventRecord(evFork, s));
   CU(cudaStreamWaitEvent(s2, evFork, 0));
-  if ((r = leaf(s, 0))) return r;
-  if (nt == 1) return 0;
   if ((r = panel(s, 0))) return r;
   CU(cudaEventRecord(evPanel[0], s));
   for (int j = 0; j + 1 < nt; j++) {
