@@ -247,6 +247,8 @@ def run_ours(args) -> None:
     dense_ms = float(np.mean([s["potrf"] + s["trtri"] + s["lauum"] + s["alpha"] for s in stage]))
     stage_mean = {k: float(np.mean([s[k] for s in stage])) for k in stage[0]}
     achieved = f_eval(n, p) / (dense_ms * 1e-3) * 1e-12
+    third = float(n) ** 3 / 3.0
+    per_stage = {k: third / (stage_mean[k] * 1e-3) * 1e-12 for k in ("potrf", "trtri", "lauum")}
 
     # ---- end to end through the host-buffer C-ABI entry point ------------------------------------
     xp = torch.from_numpy(data.x).pin_memory().numpy()
@@ -309,7 +311,11 @@ def run_ours(args) -> None:
             "gpu_launches": launches_per_eval * K,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_DGEMM_TFLOPS, "traffic": None, "kernel": "gemm_tile_kernel (DMMA engine) + leaf, dense stages of one eval",
-                         "flops_per_eval": f_eval(n, p), "dense_ms_per_eval": dense_ms, "peak_source": FP64_PEAK_SOURCE},
+                         "flops_per_eval": f_eval(n, p), "dense_ms_per_eval": dense_ms, "peak_source": FP64_PEAK_SOURCE,
+                         "stage_tflops": per_stage,
+                         "ncu": {"source": "profiles/r01/ncu_full_final.json (one launch each, cold cache)",
+                                 "lauum_launch": {"dram_bytes": 1.631e9, "algorithmic_bytes": 8.0 * n * n, "dmma_pipe_active_pct": 88.4},
+                                 "syrk_launch": {"dram_bytes": 4.668e8, "algorithmic_bytes": 2 * 1953 * 128 * 128 * 8.0, "dmma_pipe_active_pct": 75.8}}},
             "stage_ms": stage_mean,
             "cpu_baseline": cpu,
             "predict": predict,
