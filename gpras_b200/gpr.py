@@ -24,6 +24,7 @@ constrained hyperparameters (``gpr.py:303-305``) counted only while the paramete
 from __future__ import annotations
 
 import pickle
+import threading
 from pathlib import Path
 from typing import Any, Literal
 
@@ -141,24 +142,32 @@ class _Inducing:
 
 
 class _DeviceSlot:
-    """One shared device handle per (kernel, N, D, P): per-column models take turns on it."""
+    """Device handles of one GPRAS instance: one per calling thread and problem shape.  Per-column models take turns
+    on their thread's handle; with ``fit(n_jobs > 1)`` several threads keep several evaluations in flight on one GPU
+    (a handle is not thread-safe, ``include/gpras_b200.h``)."""
 
     def __init__(self):
-        self.gp: ExactGP | None = None
-        self.key = None
-        self.owner = None
+        self._per_thread: dict = {}
 
     def acquire(self, model: "ExactModel") -> ExactGP:
+        st = self._per_thread.setdefault(threading.get_ident(), {"gp": None, "key": None, "owner": None})
         key = (model.kernel.name, model.x.shape[0], model.x.shape[1], model.y.shape[1], model.device)
-        if self.gp is None or self.key != key:
-            if self.gp is not None:
-                self.gp.close()
-            self.gp = ExactGP(model.kernel.name, key[1], key[2], key[3], device=model.device)
-            self.key, self.owner = key, None
-        if self.owner is not model:
-            self.gp.set_data(model.x, model.y)
-            self.owner = model
-        return self.gp
+        if st["gp"] is None or st["key"] != key:
+            if st["gp"] is not None:
+                st["gp"].close()
+            st["gp"] = ExactGP(model.kernel.name, key[1], key[2], key[3], device=model.device)
+            st["key"], st["owner"] = key, None
+        if st["owner"] is not model:
+            st["gp"].set_data(model.x, model.y)
+            st["owner"] = model
+        return st["gp"]
+
+    def release_other_threads(self) -> None:
+        me = threading.get_ident()
+        for tid in [t for t in self._per_thread if t != me]:
+            st = self._per_thread.pop(tid)
+            if st["gp"] is not None:
+                st["gp"].close()
 
 
 class ExactModel:
@@ -458,6 +467,7 @@ class GPRAS:
         device: int = 0,
         initial_theta: NDArray[Any] | None = None,
         restarts: NDArray[Any] | None = None,
+        n_jobs: int = 1,
         **opt_kwargs: Any,
     ) -> None:
         """Fit the surrogate (``gpr.py:237-275``).  Positional arguments and ``**opt_kwargs`` are the reference's.
@@ -467,7 +477,9 @@ class GPRAS:
         ``priors=False`` drops the LogNormal priors (scikit-learn's objective); ``initial_theta``
         ([variance, noise, lengthscale(s)]) overrides the initial values; ``restarts`` ((R, 2 + n_ls) constrained
         start points, column order [variance, noise, lengthscale(s)]) runs the recipe from every start and keeps
-        the lowest final loss (sharded across ranks when ``torch.distributed`` is initialised).
+        the lowest final loss (sharded across ranks when ``torch.distributed`` is initialised); ``n_jobs > 1``
+        optimises that many per-column models concurrently on the GPU (host threads, one device handle each; the
+        reference loops sequentially, ``gpr.py:273-274``, and so does the default).
         """
         self.x = np.asarray(x).astype(np.float64)
         self.y = np.asarray(y).astype(np.float64)
@@ -477,7 +489,8 @@ class GPRAS:
         self._init_models(self.x, self.y, n_inducing, inducing_initializer)
         opt = OPTIMIZERS[optimization_method]  # KeyError on an unknown method, as the reference (gpr.py:272)
         unique = self.models[:1] if (shared_kernel and exact) else self.models
-        for model in unique:
+
+        def run_one(model) -> None:
             if initial_theta is not None:
                 _assign_theta(model, initial_theta)
             if restarts is None:
@@ -486,6 +499,20 @@ class GPRAS:
                 from .parallel import run_restarts
 
                 run_restarts(model, opt, np.asarray(restarts, np.float64), opt_kwargs)
+
+        if n_jobs > 1 and len(unique) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=int(n_jobs)) as ex:
+                list(ex.map(run_one, unique))
+            self._slot.release_other_threads()
+            if not exact:
+                from .sparse import release_other_threads
+
+                release_other_threads()
+        else:
+            for model in unique:
+                run_one(model)
 
     def _init_models(self, x, y, n_inducing, inducing_initializer: InductionInitializerType = "kmeans") -> None:
         """One model per spatial mode with the reference's initial values (``gpr.py:277-308``)."""

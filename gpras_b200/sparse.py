@@ -9,6 +9,8 @@ attribute names the reference's recipes touch (``kernel.variance / .lengthscales
 
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 
 from .engine import SparseGP
@@ -19,12 +21,19 @@ JITTER = 1e-6  # gpflow.config.default_jitter()
 _HANDLES: dict = {}
 
 
-def _handle(kernel: str, n: int, d: int, m: int, r: int, device: int) -> SparseGP:
-    """One device handle per problem shape; per-column models take turns on it (they run sequentially, gpr.py:273-274)."""
-    key = (kernel, n, d, m, r, device)
+def _handle(kernel: str, n: int, d: int, m: int, r: int, device: int) -> dict:
+    """One device handle per calling thread and problem shape; per-column models take turns on it (they run
+    sequentially in the reference, gpr.py:273-274; ``fit(n_jobs > 1)`` uses one thread and handle per model in flight)."""
+    key = (threading.get_ident(), kernel, n, d, m, r, device)
     if key not in _HANDLES:
         _HANDLES[key] = {"gp": SparseGP(kernel, n, d, m, r, device=device), "owner": None}
     return _HANDLES[key]
+
+
+def release_other_threads() -> None:
+    me = threading.get_ident()
+    for key in [k for k in _HANDLES if k[0] != me]:
+        _HANDLES.pop(key)["gp"].close()
 
 
 class SparseModel:

@@ -392,3 +392,20 @@ def test_gpras_sparse_fit_like_the_reference(cuda, tmp_path):
 
     _optimize_bfgs(m0, 20)
     assert m0.training_loss() < before
+
+
+def test_fit_n_jobs_matches_sequential(cuda):
+    from gpras_b200 import GPRAS
+    from gpras_b200.synth import make_gp_data
+
+    data = make_gp_data(300, 4, 4, 10, seed=11)
+    res = []
+    for jobs in (1, 3):
+        g = GPRAS("Matern32")
+        g.fit(data.x, data.y, 12, "grid", "L-BFGS-B", max_iter=15, n_jobs=jobs)
+        res.append(np.concatenate([np.concatenate([[m.kernel.variance.numpy(), m.likelihood.variance.numpy()],
+                                                   np.atleast_1d(m.kernel.lengthscales.numpy()), m.inducing_variable.Z.ravel()])
+                                   for m in g.models]))
+        mean, var = g.predict(data.x_test)
+        assert np.all(np.isfinite(mean)) and np.all(var > 0)
+    np.testing.assert_array_equal(res[0], res[1])  # deterministic kernels: thread scheduling cannot change results
