@@ -75,13 +75,15 @@ struct GemmDesc {
 };
 
 // ROWS x BK tile, global -> shared.  Row-major: ROWS rows of BK doubles; k-major: BK rows of ROWS doubles.
-template <bool KMAJOR, int ROWS, int BK, int GEMM_THREADS>
+// PART / NPARTS issues only every NPARTS-th chunk of the thread, so the main loop can trickle the next stage's
+// cp.async between its DMMA groups instead of stalling the tensor pipe behind a burst of LDGSTS after the barrier.
+template <bool KMAJOR, int ROWS, int BK, int GEMM_THREADS, int PART = 0, int NPARTS = 1>
 __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ g, long ld, int tid) {
   constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks in the tile
   constexpr int LD_RM = BK + 4;
   constexpr int PER_THREAD = (CHUNKS + GEMM_THREADS - 1) / GEMM_THREADS;
 #pragma unroll
-  for (int q = 0; q < PER_THREAD; q++) {
+  for (int q = PART; q < PER_THREAD; q += NPARTS) {
     const int c = tid + GEMM_THREADS * q;
     if (CHUNKS % GEMM_THREADS == 0 || c < CHUNKS) {
       if (!KMAJOR) {
@@ -95,6 +97,14 @@ __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* 
       }
     }
   }
+}
+
+// compile-time loop over the parts (PART is a template argument of load_tile)
+template <bool AK, bool BK_, typename Cfg, int KS>
+__device__ __forceinline__ void load_stage_part(double* sA, const double* gA, long lda, const double* gB, long ldb, int tid) {
+  constexpr int NP = Cfg::BK / 4;
+  load_tile<AK, Cfg::BM, Cfg::BK, Cfg::THREADS, KS, NP>(sA, gA, lda, tid);
+  load_tile<BK_, Cfg::BN, Cfg::BK, Cfg::THREADS, KS, NP>(sA + Cfg::A_DOUBLES, gB, ldb, tid);
 }
 
 template <typename Cfg, bool A_KMAJOR, bool B_KMAJOR>
@@ -180,31 +190,39 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_tile_kernel(cons
   for (int kt = 0; kt < nk; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int nx = kt + STAGES - 1;
-      if (nx < nk) {
-        double* sA = smem + (nx % STAGES) * Cfg::STAGE_DOUBLES;
-        load_tile<A_KMAJOR, BM, BK, Cfg::THREADS>(sA, gA + nx * stepA, d.lda, tid);
-        load_tile<B_KMAJOR, BN, BK, Cfg::THREADS>(sA + Cfg::A_DOUBLES, gB + nx * stepB, d.ldb, tid);
-      }
-      cp_async_commit();
-    }
+    // stage (kt + STAGES - 1) % STAGES was consumed in iteration kt - 1: refill it while computing, one slice of
+    // the cp.async burst after each k4 group of DMMAs
+    const int nx = kt + STAGES - 1;
+    const bool refill = nx < nk;
+    double* nA = smem + (nx % STAGES) * Cfg::STAGE_DOUBLES;
+    const double* ngA = gA + nx * stepA;
+    const double* ngB = gB + nx * stepB;
     const double* sA = smem + (kt % STAGES) * Cfg::STAGE_DOUBLES;
     const double* sB = sA + Cfg::A_DOUBLES;
-#pragma unroll
-    for (int ks = 0; ks < BK / 4; ks++) {
-      double a[MF], b[NF];
-#pragma unroll
-      for (int f = 0; f < MF; f++)
-        a[f] = A_KMAJOR ? sA[(4 * ks + q) * LDA_KM + wm + 8 * f + g] : sA[(wm + 8 * f + g) * LD_RM + 4 * ks + q];
-#pragma unroll
-      for (int h = 0; h < NF; h++)
-        b[h] = B_KMAJOR ? sB[(4 * ks + q) * LDB_KM + wn + 8 * h + g] : sB[(wn + 8 * h + g) * LD_RM + 4 * ks + q];
-#pragma unroll
-      for (int f = 0; f < MF; f++)
-#pragma unroll
-        for (int h = 0; h < NF; h++) dmma(acc[f][h][0], acc[f][h][1], a[f], b[h]);
+#define GPRAS_K4_GROUP(KS)                                                                                           \
+    {                                                                                                                \
+      constexpr int ks = KS;                                                                                         \
+      double a[MF], b[NF];                                                                                           \
+      _Pragma("unroll") for (int f = 0; f < MF; f++)                                                                 \
+        a[f] = A_KMAJOR ? sA[(4 * ks + q) * LDA_KM + wm + 8 * f + g] : sA[(wm + 8 * f + g) * LD_RM + 4 * ks + q];    \
+      _Pragma("unroll") for (int h = 0; h < NF; h++)                                                                 \
+        b[h] = B_KMAJOR ? sB[(4 * ks + q) * LDB_KM + wn + 8 * h + g] : sB[(wn + 8 * h + g) * LD_RM + 4 * ks + q];    \
+      _Pragma("unroll") for (int f = 0; f < MF; f++)                                                                 \
+        _Pragma("unroll") for (int h = 0; h < NF; h++) dmma(acc[f][h][0], acc[f][h][1], a[f], b[h]);                 \
+      if (refill) load_stage_part<A_KMAJOR, B_KMAJOR, Cfg, KS>(nA, ngA, d.lda, ngB, d.ldb, tid);                     \
     }
+    GPRAS_K4_GROUP(0)
+    GPRAS_K4_GROUP(1)
+    GPRAS_K4_GROUP(2)
+    GPRAS_K4_GROUP(3)
+    if (BK > 16) {
+      GPRAS_K4_GROUP(4)
+      GPRAS_K4_GROUP(5)
+      GPRAS_K4_GROUP(6)
+      GPRAS_K4_GROUP(7)
+    }
+#undef GPRAS_K4_GROUP
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
