@@ -12,7 +12,9 @@
 //       CfgS 128x64,  warp 32x32, 3 stages, 2 CTA/SM  -- short-k rank-128 updates of the Cholesky, where a
 //                                                        second resident CTA hides prologue / epilogue
 //       CfgN 128x32,  warp 16x32, 4 stages, 2 CTA/SM  -- skinny right-hand sides (P <= 32 columns), split-k
-//       CfgP 64x128,  warp 32x32, 3 stages, 2 CTA/SM  -- the in-place Cholesky panel L21 = A21 W_jj^T
+//       CfgP 64x128,  warp 32x32, 3 stages, 2 CTA/SM  -- the in-place Cholesky panel L21 = A21 W_jj^T (first panel)
+//       CfgT 64x32,   warp 16x16, 3 stages, 4 CTA/SM  -- the chain: next block column update and out-of-place panel;
+//                                                        16x more CTAs than CfgL so a 128-wide product finishes in a few us
 // * Operand tiles stream global -> shared with 16-byte cp.async in a multi-stage ring (BK = 16, or 32 for CfgL).
 // * A is either row-major A[i][k] or k-major A[k][i]; B either n-major B[j][k] or k-major B[k][j];
 //   shared tiles are padded (+4 doubles) so every fragment LDS.64 is bank-conflict free.
@@ -50,6 +52,7 @@ using CfgL = TileCfg<128, 128, 64, 32, 32, 3, 1>;  // 216 KiB: three 72 KiB stag
 using CfgS = TileCfg<128, 64, 32, 32, 16, 3, 2>;
 using CfgN = TileCfg<128, 32, 16, 32, 16, 4, 2>;
 using CfgP = TileCfg<64, 128, 32, 32, 16, 3, 2>;   // in-place Cholesky panel: full 128-column width per CTA (no tri mode)
+using CfgT = TileCfg<64, 32, 16, 16, 16, 3, 4>;    // latency-critical rank-128 products of the Cholesky chain: many small CTAs
 
 enum KBegin { KB_ZERO = 0, KB_TI = 1, KB_TJ = 2 };   // k_begin = 0 | ti*BM | tj*BN
 enum KEnd { KE_FULL = 0, KE_TI = 1, KE_TJ = 2 };     // k_end   = K | (ti+1)*BM | (tj+1)*BN
@@ -60,6 +63,8 @@ struct GemmDesc {
   const double* B;
   double* C;            // EPI_STORE / EPI_BIAS: output; EPI_COLSUMSQ: partials [m_tiles][ldc]
   const double* bias;   // EPI_BIAS: per-column bias (length n_tiles*BN)
+  const double* Cin;    // beta != 0: source of the beta * C term (pitch ldcin); NULL = C itself
+  long ldcin;
   long lda, ldb, ldc;
   long batchA, batchB, batchC;  // element strides between batch entries (grid.y)
   long splitC;          // element stride between k-split partial outputs (grid.z)
@@ -172,11 +177,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_tile_kernel(cons
   const double alpha = d.alpha;
   if (d.epilogue == EPI_STORE && d.beta != 0.0) {
     const double scale = d.beta / alpha;
+    const double* Cs = d.Cin ? d.Cin + by * d.batchC + (long)(ti * BM + wm) * d.ldcin + (long)tj * BN + wn : Ct;
+    const long ldcs = d.Cin ? d.ldcin : d.ldc;
 #pragma unroll
     for (int f = 0; f < MF; f++)
 #pragma unroll
       for (int h = 0; h < NF; h++) {
-        const double2 o = *reinterpret_cast<const double2*>(Ct + (long)(8 * f + g) * d.ldc + 8 * h + 2 * q);
+        const double2 o = *reinterpret_cast<const double2*>(Cs + (long)(8 * f + g) * ldcs + 8 * h + 2 * q);
         acc[f][h][0] = scale * o.x;
         acc[f][h][1] = scale * o.y;
       }

@@ -64,6 +64,7 @@ int prepare_device() {
   if ((r = opt_in_smem(gemm_tile_kernel<CfgL, true, true>, CfgL::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(gemm_tile_kernel<CfgS, false, false>, CfgS::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(gemm_tile_kernel<CfgP, false, false>, CfgP::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(gemm_tile_kernel<CfgT, false, false>, CfgT::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(gemm_tile_kernel<CfgN, false, true>, CfgN::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(gemm_tile_kernel<CfgN, true, true>, CfgN::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(leaf_potrf_inv_kernel, LEAF_SMEM_BYTES))) return r;
@@ -86,7 +87,7 @@ GemmDesc make_desc(const double* A, long lda, const double* B, long ldb, double*
   return d;
 }
 
-enum TileShape { SHAPE_L = 0, SHAPE_S = 1, SHAPE_N = 2, SHAPE_P = 3 };
+enum TileShape { SHAPE_L = 0, SHAPE_S = 1, SHAPE_N = 2, SHAPE_P = 3, SHAPE_T = 4 };
 
 template <typename Cfg, bool AKM, bool BKM>
 int launch_cfg(cudaStream_t s, const GemmDesc& d, int batch, int nz) {
@@ -98,7 +99,7 @@ int launch_cfg(cudaStream_t s, const GemmDesc& d, int batch, int nz) {
   return 0;
 }
 
-// m_tiles counts BM-row tiles (128; 64 for SHAPE_P); n_tiles counts BN-column tiles of the chosen shape.
+// m_tiles counts BM-row tiles (128; 64 for SHAPE_P / SHAPE_T); n_tiles counts BN-column tiles of the chosen shape.
 int launch_gemm(cudaStream_t s, bool akm, bool bkm, const GemmDesc& d, int batch, int* launches, int shape = SHAPE_L,
                 int nz = 1) {
   if (d.m_tiles <= 0 || d.n_tiles <= 0 || batch <= 0) return 0;
@@ -112,6 +113,10 @@ int launch_gemm(cudaStream_t s, bool akm, bool bkm, const GemmDesc& d, int batch
   if (shape == SHAPE_S) {
     if (!akm && !bkm) return launch_cfg<CfgS, false, false>(s, d, batch, nz);
     return fail(GPRAS_E_ARG, "CfgS is instantiated for the NT layout only");
+  }
+  if (shape == SHAPE_T) {
+    if (!akm && !bkm && !d.tri) return launch_cfg<CfgT, false, false>(s, d, batch, nz);
+    return fail(GPRAS_E_ARG, "CfgT is instantiated for the NT layout, non-triangular, only");
   }
   if (shape == SHAPE_P) {
     if (!akm && !bkm && !d.tri) return launch_cfg<CfgP, false, false>(s, d, batch, nz);
@@ -147,6 +152,17 @@ constexpr int SKINNY_MAX_SLABS = 16;
 struct LookAhead {
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> ev;
+  double* scratch = nullptr;  // n x 128 column block of the Cholesky chain
+  size_t scratch_count = 0;
+  int ensure_scratch(size_t count) {
+    if (count <= scratch_count) return 0;
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr, scratch_count = 0;
+    cudaError_t e = cudaMalloc((void**)&scratch, count * sizeof(double));
+    if (e != cudaSuccess) return fail(GPRAS_E_NOMEM, "cudaMalloc (Cholesky scratch)", e);
+    scratch_count = count;
+    return 0;
+  }
   int ensure(size_t n) {
     if (!side) {
       int lo = 0, hi = 0;
@@ -165,58 +181,68 @@ struct LookAhead {
     ev.clear();
     if (side) cudaStreamDestroy(side);
     side = nullptr;
+    if (scratch) cudaFree(scratch);
+    scratch = nullptr, scratch_count = 0;
   }
 };
 
 // Right-looking blocked Cholesky, panel width 128, with one panel of look-ahead on a high-priority side stream:
 //   leaf   (1 CTA)   potrf + inverse of the diagonal block  -> L_jj, W_jj
-//   panel  (CfgP)    L21 = A21 W_jj^T, in place
-//   col    (CfgS)    block column j+1 of the trailing matrix -= panel_j panel_j^T        [side stream]
+//   panel  (CfgT)    L21 = A21 W_jj^T, from the scratch column block S into A (first panel: CfgP, in place)
+//   col    (CfgT)    S = block column j+1 of the trailing matrix - panel_j panel_j^T      [side stream]
 //   rest   (CfgS)    the trailing triangle right of block column j+1 -= panel_j panel_j^T  [main stream]
-// so leaf(j+1) and panel(j+1) run while rest(j) occupies the machine.
+// so leaf(j+1) and panel(j+1) run while rest(j) occupies the machine.  The chain col -> leaf -> panel is what bounds
+// the factorisation once rest(j) gets short, so its two products use 64x32 tiles (16x the CTAs of a 128x128 tiling)
+// and go through the scratch block S (n x 128): out of place, any tile shape is race free.
 int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, long ldw, int n, double* logdet_parts,
                int* info, int* launches) {
   const int nt = n / 128;
   int r;
   if ((r = la.ensure(2 * (size_t)nt + 2))) return r;
+  if ((r = la.ensure_scratch((size_t)n * 128))) return r;
+  double* S = la.scratch;  // S[i][0..127] = updated block column for global row i
   cudaStream_t s2 = la.side;
   cudaEvent_t* evPanel = la.ev.data();        // [nt]
   cudaEvent_t* evRest = la.ev.data() + nt;    // [nt]
   cudaEvent_t evFork = la.ev[2 * nt], evJoin = la.ev[2 * nt + 1];
-  auto leaf = [&](cudaStream_t st, int jb) -> int {
-    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(A, lda, W, ldw, logdet_parts, info, jb);
+  auto leaf = [&](cudaStream_t st, int jb, const double* in, long ldin) -> int {
+    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(in, ldin, A, lda, W, ldw, logdet_parts, info, jb);
     if (launches) ++*launches;
     CU(cudaGetLastError());
     return 0;
   };
-  auto panel = [&](cudaStream_t st, int jb) -> int {  // rows of tiles jb+1.. , columns of block jb
-    const int rem = nt - jb - 1;
-    double* pn = A + (long)(jb + 1) * 128 * lda + (long)jb * 128;
-    const double* wjj = W + (long)jb * 128 * ldw + (long)jb * 128;
-    GemmDesc p = make_desc(pn, lda, wjj, ldw, pn, lda, 2 * rem, 1, 128);
-    return launch_gemm(st, false, false, p, 1, launches, SHAPE_P);
-  };
-  if ((r = leaf(s, 0))) return r;
+  if ((r = leaf(s, 0, A, lda))) return r;
   if (nt == 1) return 0;  // single block: nothing to overlap, the side stream stays out of it
   CU(cudaEventRecord(evFork, s));
   CU(cudaStreamWaitEvent(s2, evFork, 0));
-  if ((r = panel(s, 0))) return r;
+  {  // first panel, in place (rows of tiles 1.., columns of block 0)
+    double* pn = A + (long)128 * lda;
+    GemmDesc p = make_desc(pn, lda, W, ldw, pn, lda, 2 * (nt - 1), 1, 128);
+    if ((r = launch_gemm(s, false, false, p, 1, launches, SHAPE_P))) return r;
+  }
   CU(cudaEventRecord(evPanel[0], s));
   for (int j = 0; j + 1 < nt; j++) {
     const int rem = nt - j - 1;  // tiles below / right of block j
     double* pn = A + (long)(j + 1) * 128 * lda + (long)j * 128;  // panel j, rows from tile j+1
-    // ---- side stream: block column j+1, then the next diagonal block and panel ----
+    // ---- side stream: block column j+1 -> S, then the next diagonal block and panel ----
     CU(cudaStreamWaitEvent(s2, evPanel[j], 0));
     if (j > 0) CU(cudaStreamWaitEvent(s2, evRest[j - 1], 0));
+    double* Sj = S + (long)(j + 1) * 128 * 128;  // rows from tile j+1
     {
-      double* col = A + (long)(j + 1) * 128 * (lda + 1);
-      GemmDesc c = make_desc(pn, lda, pn, lda, col, lda, rem, 2, 128);
+      const double* col = A + (long)(j + 1) * 128 * (lda + 1);
+      GemmDesc c = make_desc(pn, lda, pn, lda, Sj, 128, 2 * rem, 4, 128);
       c.alpha = -1.0, c.beta = 1.0;
-      if ((r = launch_gemm(s2, false, false, c, 1, launches, SHAPE_S))) return r;
+      c.Cin = col, c.ldcin = lda;
+      if ((r = launch_gemm(s2, false, false, c, 1, launches, SHAPE_T))) return r;
     }
-    if ((r = leaf(s2, j + 1))) return r;
+    if ((r = leaf(s2, j + 1, Sj, 128))) return r;
     if (rem > 1) {
-      if ((r = panel(s2, j + 1))) return r;
+      {  // panel j+1: rows of tiles j+2.. of S times W_{j+1}^T -> A
+        const double* wjj = W + (long)(j + 1) * 128 * (ldw + 1);
+        double* out = A + (long)(j + 2) * 128 * lda + (long)(j + 1) * 128;
+        GemmDesc p = make_desc(Sj + (long)128 * 128, 128, wjj, ldw, out, lda, 2 * (rem - 1), 4, 128);
+        if ((r = launch_gemm(s2, false, false, p, 1, launches, SHAPE_T))) return r;
+      }
       CU(cudaEventRecord(evPanel[j + 1], s2));
       // ---- main stream: the rest of the trailing triangle ----
       if (j > 0) CU(cudaStreamWaitEvent(s, evPanel[j], 0));

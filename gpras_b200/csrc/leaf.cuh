@@ -209,14 +209,17 @@ __device__ __forceinline__ void leaf_inverse_level(double* S, const double* dvec
 }
 
 static __global__ void __launch_bounds__(LEAF_THREADS, 1)
-leaf_potrf_inv_kernel(double* __restrict__ A, long lda, double* __restrict__ W, long ldw,
-                      double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
+leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* __restrict__ W,
+                      long ldw, double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double logred[4];
   double* S = smem;
   double* dvec = smem + LEAF_N * LEAF_LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
+  // In points at the 128 x 128 block to factor (pitch ldin): the diagonal block of A itself, or the chain's scratch
+  // column block; L goes to the diagonal block jb of A, W = L^-1 to that of W.
+  if (In == A) In += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
   A += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
   W += (long)jb * LEAF_N * ldw + (long)jb * LEAF_N;
 
@@ -229,7 +232,7 @@ leaf_potrf_inv_kernel(double* __restrict__ A, long lda, double* __restrict__ W, 
     for (int u = 0; u < 8; u++) {
       const int e = e0 + u * LEAF_THREADS, r = e >> 6, c2 = (e & 63) * 2;
       v[u] = make_double2(0.0, 0.0);
-      if (c2 <= r) v[u] = *reinterpret_cast<const double2*>(A + (long)r * lda + c2);
+      if (c2 <= r) v[u] = *reinterpret_cast<const double2*>(In + (long)r * ldin + c2);
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) {

@@ -18,7 +18,7 @@ int main() {
     cudaMemcpy(dA, a.data(), n * n * 8, cudaMemcpyHostToDevice);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES>>>(dA, n, dW, n, dld, dinfo, 0);
+    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES>>>(dA, n, dA, n, dW, n, dld, dinfo, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     long long t[64]; cudaMemcpy(t, dt, sizeof t, cudaMemcpyDeviceToHost);
