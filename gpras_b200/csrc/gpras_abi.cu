@@ -278,6 +278,7 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
   CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->n_pad * d, h->stream));
   CU(cudaMemsetAsync(h->Y, 0, sizeof(double) * np, h->stream));
   CU(cudaMemsetAsync(h->gsum, 0, sizeof(double) * (2 + d), h->stream));
+  CU(cudaMemsetAsync(h->W, 0, sizeof(double) * nn, h->stream));  // the leaves never write above the diagonal
   CU(cudaStreamSynchronize(h->stream));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
   *out = h;

@@ -155,7 +155,8 @@ __device__ __forceinline__ void leaf_factor_panel(double* S, double* dvec, int j
 // tiles (TB = B/8) and is served by TB warps; warp u of the pair takes tiles (n, (u + n) mod TB), n < TB, so every
 // warp sees each row index and each column index once and the triangular k ranges balance.
 template <int B>
-__device__ __forceinline__ void leaf_inverse_level(double* S, const double* dvec, int warp, int g, int q) {
+__device__ __forceinline__ void leaf_inverse_level(double* S, const double* dvec, int warp, int g, int q,
+                                                   double* __restrict__ Wg = nullptr, long ldw = 0) {
   constexpr int TB = B / 8;
   const int p = warp / TB, u = warp % TB, r0 = 2 * B * p;
   int i0[TB], jj0[TB];
@@ -199,6 +200,13 @@ __device__ __forceinline__ void leaf_inverse_level(double* S, const double* dvec
       }
     }
   }
+  if (B == 64) {
+    // last level: W21 (rows 64.., columns ..63) goes straight to global memory, nothing reads it from S any more
+#pragma unroll
+    for (int n = 0; n < TB; n++)
+      *reinterpret_cast<double2*>(Wg + (long)(B + i0[n] + g) * ldw + jj0[n] + 2 * q) = make_double2(-c0[n], -c1[n]);
+    return;
+  }
   __syncthreads();
 #pragma unroll
   for (int n = 0; n < TB; n++) {
@@ -224,23 +232,15 @@ leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* 
   W += (long)jb * LEAF_N * ldw + (long)jb * LEAF_N;
 
   LT_DECL;
-  // ---- load (lower triangle; upper zeroed), eight independent 16-byte loads in flight per thread ----
-#pragma unroll 1
-  for (int e0 = tid; e0 < LEAF_N * (LEAF_N / 2); e0 += 8 * LEAF_THREADS) {
-    double2 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int e = e0 + u * LEAF_THREADS, r = e >> 6, c2 = (e & 63) * 2;
-      v[u] = make_double2(0.0, 0.0);
-      if (c2 <= r) v[u] = *reinterpret_cast<const double2*>(In + (long)r * ldin + c2);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int e = e0 + u * LEAF_THREADS, r = e >> 6, c2 = (e & 63) * 2;
-      if (c2 + 1 > r) v[u].y = 0.0;
-      *reinterpret_cast<double2*>(S + r * LEAF_LD + c2) = v[u];
-    }
+  // ---- load: every 16-byte chunk that touches the lower triangle, all in flight at once (cp.async).  The strictly
+  //      upper part of S is never read before it is overwritten (panel rows are masked on write-back, tile updates
+  //      only propagate within an entry), so it is left as it is ----
+  for (int e = tid; e < LEAF_N * (LEAF_N / 2); e += LEAF_THREADS) {
+    const int r = e >> 6, c2 = (e & 63) * 2;
+    if (c2 <= r) cp_async16(S + r * LEAF_LD + c2, In + (long)r * ldin + c2);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   LT_MARK(0);
 
@@ -301,24 +301,29 @@ leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* 
   LT_MARK(9);
   leaf_inverse_level<32>(S, dvec, warp, g, q);
   LT_MARK(10);
-  leaf_inverse_level<64>(S, dvec, warp, g, q);
+  leaf_inverse_level<64>(S, dvec, warp, g, q, W, ldw);
   LT_MARK(11);
 
-  // ---- 3. write back: L by rows (16-byte stores); W in 8 x 4 element blocks (32-byte sectors, transposed
-  //         conflict-free reads of the upper triangle) ----
+  // ---- 3. write back.  L: the chunks that touch the lower triangle (the strictly upper part of L's diagonal block
+  //         is unspecified: no kernel reads it).  W: 8 x 4 element blocks of the two diagonal 64 x 64 triangles,
+  //         transposed conflict-free reads; blocks above the diagonal are never written (the W buffer is zero-initialised
+  //         once and the engine relies on those zeros), the lower-left 64 x 64 block is already in global memory ----
 #pragma unroll 8
   for (int e = tid; e < LEAF_N * (LEAF_N / 2); e += LEAF_THREADS) {
     const int r = e >> 6, c2 = (e & 63) * 2;
-    double2 v = *reinterpret_cast<const double2*>(S + r * LEAF_LD + c2);
-    if (c2 > r) v.x = 0.0;
-    if (c2 + 1 > r) v.y = 0.0;
-    *reinterpret_cast<double2*>(A + (long)r * lda + c2) = v;
+    if (c2 <= r) {
+      double2 v = *reinterpret_cast<const double2*>(S + r * LEAF_LD + c2);
+      if (c2 + 1 > r) v.y = 0.0;
+      *reinterpret_cast<double2*>(A + (long)r * lda + c2) = v;
+    }
   }
-#pragma unroll 8
+#pragma unroll 4
   for (int blk = warp; blk < 16 * 32; blk += 8) {  // 16 row groups of 8 x 32 column groups of 4
     const int rb = 8 * (blk >> 5), cb = 4 * (blk & 31);
-    const int r = rb + g, c = cb + q;
-    W[(long)r * ldw + c] = leaf_getW(S, dvec, r, c);
+    if (cb <= rb + 7 && !(rb >= 64 && cb < 64)) {
+      const int r = rb + g, c = cb + q;
+      W[(long)r * ldw + c] = leaf_getW(S, dvec, r, c);
+    }
   }
 #ifdef LEAF_TIMING
   __syncthreads();

@@ -202,6 +202,8 @@ int gpras_sgpr_create(gpras_sgpr** out, int device, int kernel_id, int n, int d,
   CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->n_pad * d, h->stream));
   CU(cudaMemsetAsync(h->Z, 0, sizeof(double) * h->m_pad * d, h->stream));
   CU(cudaMemsetAsync(h->Y, 0, sizeof(double) * h->n_pad * h->r_pad, h->stream));
+  CU(cudaMemsetAsync(h->WL, 0, sizeof(double) * mm, h->stream));  // the leaves never write above the diagonal
+  CU(cudaMemsetAsync(h->WB, 0, sizeof(double) * mm, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   *out = h;
   return 0;

@@ -110,7 +110,9 @@ int gpras_sgpr_last_launches(gpras_sgpr* h);
  * layout flags select row-major A[i][k] / k-major A[k][i] and n-major B[j][k] / k-major B[k][j]. */
 int gpras_dgemm_tiles(void* cuda_stream, int shape, int a_kmajor, int b_kmajor, const double* A, long lda, const double* B,
                       long ldb, double* C, long ldc, int m, int n, int k, double alpha, double beta);
-/* In-place lower Cholesky of the n x n (n % 128 == 0) device matrix A, W = L^-1 diagonal blocks as by-product;
+/* In-place lower Cholesky of the n x n (n % 128 == 0) device matrix A (the strictly upper part of the result is
+ * unspecified); the diagonal 128-blocks of W = L^-1 come out as a by-product.  W must be zero-initialised by the caller
+ * (only its lower triangle is ever written; the engine relies on the zeros above the diagonal).
  * info_dev: device int, logdet_parts_dev: n/128 device doubles. */
 int gpras_dpotrf(void* cuda_stream, double* A, long lda, double* W, long ldw, int n, double* logdet_parts_dev,
                  int* info_dev);
