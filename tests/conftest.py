@@ -18,6 +18,28 @@ def golden():
     return np.load(ROOT / "tests" / "golden" / "exact_gp_sklearn.npz")
 
 
+@pytest.fixture(scope="session")
+def pre_golden():
+    """Outputs of the reference's own PreProcessor (tests/golden/make_golden_reference.py)."""
+    return np.load(ROOT / "tests" / "golden" / "preprocess_reference.npz")
+
+
+@pytest.fixture(scope="session")
+def met_golden():
+    """Outputs of the reference's own gpras/metrics.py (tests/golden/make_golden_reference.py)."""
+    return np.load(ROOT / "tests" / "golden" / "metrics_reference.npz")
+
+
+PRE_CASES = ["wse_fixed", "depth_fixed", "wse_north", "velocity"]
+MET_CASES = ["small", "ragged", "one_step"]
+
+
+def sub(npz, name):
+    """All arrays of one golden case as a dict."""
+    pre = name + "."
+    return {k[len(pre):]: npz[k] for k in npz.files if k.startswith(pre)}
+
+
 GOLDEN_CASES = ["rbf_iso", "rbf_ard", "m12_iso", "m32_ard", "m52_ard", "m52_iso_dup"]
 
 
