@@ -47,6 +47,30 @@ SYMBOLS = {
     "gpras_sgpr_condition": (C.c_int, [vp, vp, vp, C.c_double]),
     "gpras_sgpr_predict": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "gpras_sgpr_last_launches": (C.c_int, [vp]),
+    "gpras_metrics_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_long]),
+    "gpras_metrics_destroy": (C.c_int, [vp]),
+    "gpras_metrics_set_elevations": (C.c_int, [vp, vp, vp]),
+    "gpras_metrics_reset": (C.c_int, [vp, C.c_double]),
+    "gpras_metrics_update": (C.c_int, [vp, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int, C.c_int]),
+    "gpras_gp_predict_metrics": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, C.c_long, C.c_int, vp, vp]),
+    "gpras_metrics_finalize": (C.c_int, [vp, C.c_double, vp, vp, vp]),
+    "gpras_metrics_timesteps": (C.c_long, [vp]),
+    "gpras_metrics_last_launches": (C.c_int, [vp]),
+    "gpras_metrics_fidelity": (C.c_int, [vp, C.c_long, vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp]),
+    "gpras_pre_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_double]),
+    "gpras_pre_destroy": (C.c_int, [vp]),
+    "gpras_pre_fit": (C.c_int, [vp, vp, C.c_long, C.c_int, C.c_int, vp, vp, C.c_int, C.c_double, C.c_int]),
+    "gpras_pre_set_modes": (C.c_int, [vp, C.c_int]),
+    "gpras_pre_set_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]),
+    "gpras_pre_get": (C.c_int, [vp, C.c_int, vp]),
+    "gpras_pre_modes": (C.c_int, [vp]),
+    "gpras_pre_eigen_count": (C.c_int, [vp]),
+    "gpras_pre_iterations": (C.c_int, [vp]),
+    "gpras_pre_transform": (C.c_int, [vp, vp, C.c_long, C.c_int, C.c_int, vp]),
+    "gpras_pre_reverse": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    "gpras_pre_last_launches": (C.c_int, [vp]),
+    "gpras_pre_last_stage_ms": (C.c_int, [vp, vp]),
+    "gpras_dsyev128": (C.c_int, [vp, vp, vp, vp]),
     "gpras_dgemm_tiles": (
         C.c_int,
         [vp, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double],

@@ -1,5 +1,6 @@
 // C ABI of gpras_b200, exact-GP part (see include/gpras_b200.h): host-side orchestration of the sm_100a kernels.
 // No CPU compute path exists in this file: every entry point either launches CUDA work or fails.
+#include <cmath>
 #include <cstdlib>
 
 #include "host_common.cuh"
@@ -69,7 +70,7 @@ struct gpras_gp {
          *varm = nullptr;
   // cell map
   int c = 0, c_pad = 0, p16 = 0;
-  double *E1 = nullptr, *E2 = nullptr, *bias = nullptr, *zbias = nullptr, *ring_m = nullptr, *ring_v = nullptr;
+  double *E1 = nullptr, *E2 = nullptr, *rootS = nullptr, *bias = nullptr, *zbias = nullptr, *ring_m = nullptr, *ring_v = nullptr;
   cudaEvent_t ev[8] = {};
   double stage_ms[7] = {};
   LookAhead la;
@@ -291,7 +292,7 @@ int gpras_gp_destroy(gpras_gp* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   double* bufs[] = {h->X,    h->Xs,  h->Y,   h->K,  h->W,     h->Kinv, h->U,    h->alpha, h->theta, h->logdet, h->gpart,
                     h->gsum, h->usq, h->result, h->skinny, h->Xt, h->Xts, h->Ks,   h->mean, h->vpart, h->var,   h->varm,   h->E1,
-                    h->E2,   h->bias, h->zbias, h->ring_m, h->ring_v};
+                    h->E2,   h->bias, h->zbias, h->ring_m, h->ring_v, h->rootS};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->info) cudaFree(h->info);
@@ -463,16 +464,18 @@ int gpras_gp_set_cell_map(gpras_gp* h, const double* e_mean, const double* bias,
   if (!h || !e_mean || !bias || c <= 0) return fail(GPRAS_E_ARG, "bad argument");
   if (h->p > 64) return fail(GPRAS_E_ARG, "more than 64 modes are not supported by the cell expansion");
   DeviceGuard guard(h->device);
-  double* olds[] = {h->E1, h->E2, h->bias, h->zbias, h->ring_m, h->ring_v};
+  double* olds[] = {h->E1, h->E2, h->bias, h->zbias, h->ring_m, h->ring_v, h->rootS};
   for (double* b : olds)
     if (b) cudaFree(b);
-  h->E1 = h->E2 = h->bias = h->zbias = h->ring_m = h->ring_v = nullptr;
+  h->E1 = h->E2 = h->bias = h->zbias = h->ring_m = h->ring_v = h->rootS = nullptr;
   h->c = c, h->c_pad = round_up(c, 128), h->p16 = h->p <= 32 ? 32 : 64;
   const size_t ne = (size_t)h->p16 * h->c_pad;
   int r;
   // E2 holds S[c] = sum_p E[p][c]^2: every mode shares theta, so cell variance = var[t] * S[c]
-  if ((r = dalloc(&h->E1, ne)) || (r = dalloc(&h->E2, h->c_pad)) || (r = dalloc(&h->bias, h->c_pad))) return r;
-  std::vector<double> e1(ne, 0.0), sq(h->c_pad, 0.0), b(h->c_pad, 0.0);
+  if ((r = dalloc(&h->E1, ne)) || (r = dalloc(&h->E2, h->c_pad)) || (r = dalloc(&h->bias, h->c_pad)) ||
+      (r = dalloc(&h->rootS, h->c_pad)))
+    return r;
+  std::vector<double> e1(ne, 0.0), sq(h->c_pad, 0.0), b(h->c_pad, 0.0), rt(h->c_pad, 0.0);
   for (int pp = 0; pp < h->p; pp++)
     for (int cc = 0; cc < c; cc++) {
       const double v = e_mean[(size_t)pp * c + cc];
@@ -480,6 +483,8 @@ int gpras_gp_set_cell_map(gpras_gp* h, const double* e_mean, const double* bias,
       sq[cc] += v * v;
     }
   memcpy(b.data(), bias, sizeof(double) * c);
+  for (int cc = 0; cc < c; cc++) rt[cc] = sqrt(sq[cc]);
+  CU(cudaMemcpyAsync(h->rootS, rt.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->E1, e1.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->E2, sq.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->bias, b.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice, h->stream));
@@ -627,3 +632,5 @@ int gpras_dlauum(void* cuda_stream, const double* W, long ldw, double* Kinv, lon
 }
 
 }  // extern "C"
+
+#include "metrics_abi.cuh"

@@ -1,0 +1,361 @@
+// Streaming accuracy metrics (gpras/metrics.py) fused with the modes -> cells expansion: the consumer that makes the
+// T x C cell-space prediction unnecessary to materialise (the 3.2 TB output of config 5).
+//
+// Every metric of gpras/metrics.py:85-324 is a function of a few running reductions over the (timesteps x cells)
+// truth x, prediction y and confidence conf of one event:
+//     per cell      sum(x-y)  sum((x-y)^2)  sum(conf)  max_t x  max_t y      (x[argmax_t x] == max_t x)
+//     per timestep  sum_c(x-y)  sum_c((x-y)^2)  sum_c(conf)  sum_c|x-y|  count_c(|x-y| <= v_tol)
+// One kernel accumulates all of them in a single pass.  A CTA owns a 128-cell column tile and streams 64-row tiles:
+//   FUSED  : y = max(M[t,:] E[:,c] + bias[c] - elev_y[c], 0)  on the DMMA pipe (E tile resident in shared memory),
+//            conf = sqrt(var[t]) * sqrt(S[c])                 (shared theta: the cell variance is rank one),
+//            so the only HBM stream is the truth x (8 B per cell-timestep; nothing at all when there is no truth);
+//   !FUSED : y and conf are read from (T x C) arrays (24 B per cell-timestep), for callers that hold them.
+// Depth conversion (PreProcessor.wse_2_depth, preprocess.py:1041-1045; pipeline.py:265-274) is applied on the fly when
+// elevation vectors are supplied.  Reductions have a fixed shape (no atomics): results are bitwise repeatable.
+#pragma once
+#include "common.cuh"
+
+namespace gpras {
+
+constexpr int MET_THREADS = 256;
+constexpr int MET_ROWS = 32;   // timesteps per row tile
+constexpr int MET_CELLQ = 5;   // per cell: sum e, sum e^2, sum conf, max x, max y
+constexpr int MET_ROWQ = 5;    // per row : sum e, sum e^2, sum conf, sum |e|, count(|e| <= v_tol)
+
+struct MetricsArgs {
+  // FUSED prediction source
+  const double* M;      // (t_pad x ldm) mode-space means
+  long ldm;
+  const double* var;    // (t_pad) mode-space variance (noise included), shared by all modes
+  const double* E;      // (P16 x lde) folded EOF map, zero on dry / padded cells
+  long lde;
+  const double* bias;   // (c_pad)
+  const double* rootS;  // (c_pad) sqrt(sum_p E[p][c]^2)
+  // !FUSED prediction source
+  const double* Y;
+  long ldy;
+  const double* CONF;
+  long ldconf;
+  // truth (NULL: x == 0)
+  const double* X;
+  long ldx;
+  const double* elev_x;  // NULL: truth used as is; else x = max(X - elev_x, 0)
+  const double* elev_y;  // NULL: prediction used as is; else y = max(y - elev_y, 0)
+  int t_rows;            // valid rows of this block
+  int c;                 // valid cells
+  int t_tiles, tiles_per_cta;
+  double v_tol;
+  double* cell_part;     // [gridDim.y][MET_CELLQ][c_pad]
+  long c_pad;
+  double* row_part;      // [MET_ROWQ][t_tiles * MET_ROWS][n_ctile]
+  int n_ctile;
+};
+
+template <int P16>
+struct MetCfg {
+  static constexpr int LDE = 128 + 4;
+  static constexpr int LDA = P16 + 4;
+  // E tile, two row tiles of modes, two variance vectors, row-reduction scratch [8 warps][MET_ROWS][MET_ROWQ]
+  static constexpr int RED_DOUBLES = 8 * MET_ROWS * MET_ROWQ;
+  static constexpr int SMEM_DOUBLES = P16 * LDE + 2 * MET_ROWS * LDA + 2 * MET_ROWS + RED_DOUBLES;
+  static constexpr int SMEM_BYTES = SMEM_DOUBLES * (int)sizeof(double);
+};
+constexpr int MET_PLAIN_SMEM_BYTES = 8 * MET_ROWS * MET_ROWQ * (int)sizeof(double);
+
+// Thread layout: warp w owns the 16 columns [16w, 16w+16) of the CTA's 128-cell tile for all 32 rows of a row tile
+// (4 x 2 DMMA accumulator tiles); a thread holds rows 8f+g (f < 4) and columns 16w + 8h + 2q + {0,1} (h < 2).
+template <int P16, bool FUSED>
+__global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const MetricsArgs a) {
+  using Cfg = MetCfg<P16>;
+  extern __shared__ __align__(16) double smem[];
+  double* sE = smem;
+  double* sA = sE + (FUSED ? P16 * Cfg::LDE : 0);
+  double* sV = sA + (FUSED ? 2 * MET_ROWS * Cfg::LDA : 0);
+  double* sRed = sV + (FUSED ? 2 * MET_ROWS : 0);  // [8 warps][MET_ROWS][MET_ROWQ]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int wn = warp * 16;
+  const int tj = blockIdx.x;
+  const int t_begin = blockIdx.y * a.tiles_per_cta;
+  int t_end = t_begin + a.tiles_per_cta;
+  if (t_end > a.t_tiles) t_end = a.t_tiles;
+  const long col0 = (long)tj * 128 + wn + 2 * q;  // column of (h = 0, w = 0); (h, w) adds 8h + w
+
+  double ex[2][2], ey[2][2], rs[2][2];
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      const long c = col0 + 8 * h + w;
+      const bool ok = c < a.c;
+      ex[h][w] = (a.elev_x && ok) ? a.elev_x[c] : 0.0;
+      ey[h][w] = (a.elev_y && ok) ? a.elev_y[c] : 0.0;
+      rs[h][w] = FUSED ? a.rootS[c] : 0.0;
+    }
+  double c_e[2][2], c_e2[2][2], c_cf[2][2], c_mx[2][2], c_my[2][2];
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      c_e[h][w] = c_e2[h][w] = c_cf[h][w] = 0.0;
+      c_mx[h][w] = c_my[h][w] = -INFINITY;
+    }
+
+  auto load_rows = [&](int buf, int tt) {
+    constexpr int CPR = P16 / 2;
+    for (int c = tid; c < MET_ROWS * CPR; c += MET_THREADS) {
+      const int row = c / CPR, kc = c - row * CPR;
+      cp_async16(sA + (buf * MET_ROWS + row) * Cfg::LDA + 2 * kc, a.M + (long)(tt * MET_ROWS + row) * a.ldm + 2 * kc);
+    }
+    if (tid < MET_ROWS / 2) cp_async16(sV + buf * MET_ROWS + 2 * tid, a.var + (long)tt * MET_ROWS + 2 * tid);
+  };
+  if (FUSED && t_begin < t_end) {
+    for (int c = tid; c < P16 * 64; c += MET_THREADS) {
+      const int kr = c >> 6, mc = c & 63;
+      cp_async16(sE + kr * Cfg::LDE + 2 * mc, a.E + (long)kr * a.lde + (long)tj * 128 + 2 * mc);
+    }
+    load_rows(0, t_begin);
+    cp_async_commit();
+  }
+
+  for (int tt = t_begin; tt < t_end; tt++) {
+    const int buf = (tt - t_begin) & 1;
+    const int row_base = tt * MET_ROWS;
+    // truth for this tile: issued first, consumed after the DMMA loop
+    double xv[4][2][2];
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const int row = row_base + 8 * f + g;
+      const bool rok = a.X != nullptr && row < a.t_rows;
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+          const long c = col0 + 8 * h + w;
+          xv[f][h][w] = (rok && c < a.c) ? __ldg(a.X + (long)row * a.ldx + c) : 0.0;
+        }
+    }
+    double acc[4][2][2], cf[FUSED ? 1 : 4][2][2];
+    if (FUSED) {
+      cp_async_wait<0>();
+      __syncthreads();
+      if (tt + 1 < t_end) load_rows(buf ^ 1, tt + 1);
+      cp_async_commit();
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const double b0 = a.bias[col0 + 8 * h], b1 = a.bias[col0 + 8 * h + 1];
+#pragma unroll
+        for (int f = 0; f < 4; f++) acc[f][h][0] = b0, acc[f][h][1] = b1;
+      }
+      const double* a0 = sA + buf * MET_ROWS * Cfg::LDA;
+#pragma unroll
+      for (int ks = 0; ks < P16 / 4; ks++) {
+        double av[4], bv[2];
+#pragma unroll
+        for (int f = 0; f < 4; f++) av[f] = a0[(8 * f + g) * Cfg::LDA + 4 * ks + q];
+#pragma unroll
+        for (int h = 0; h < 2; h++) bv[h] = sE[(4 * ks + q) * Cfg::LDE + wn + 8 * h + g];
+#pragma unroll
+        for (int f = 0; f < 4; f++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) dmma(acc[f][h][0], acc[f][h][1], av[f], bv[h]);
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        const int row = row_base + 8 * f + g;
+        const bool rok = row < a.t_rows;
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int w = 0; w < 2; w++) {
+            const long c = col0 + 8 * h + w;
+            const bool ok = rok && c < a.c;
+            acc[f][h][w] = ok ? __ldg(a.Y + (long)row * a.ldy + c) : 0.0;
+            cf[FUSED ? 0 : f][h][w] = (ok && a.CONF) ? __ldg(a.CONF + (long)row * a.ldconf + c) : 0.0;
+          }
+      }
+    }
+    // ---- elementwise + reductions, one row at a time ----
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const int row = row_base + 8 * f + g;
+      const bool rok = row < a.t_rows;
+      const double sv = FUSED ? sqrt(sV[buf * MET_ROWS + 8 * f + g]) : 0.0;
+      double r_e = 0.0, r_e2 = 0.0, r_cf = 0.0, r_ab = 0.0, r_ct = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+          const bool ok = rok && (col0 + 8 * h + w < a.c);
+          double x = xv[f][h][w], y = acc[f][h][w];
+          if (a.elev_x) x = fmax(x - ex[h][w], 0.0);
+          if (a.elev_y) y = fmax(y - ey[h][w], 0.0);
+          const double e = ok ? x - y : 0.0;
+          const double cfv = ok ? (FUSED ? sv * rs[h][w] : cf[FUSED ? 0 : f][h][w]) : 0.0;
+          c_e[h][w] += e;
+          c_e2[h][w] += e * e;
+          c_cf[h][w] += cfv;
+          if (ok) {
+            c_mx[h][w] = fmax(c_mx[h][w], x);
+            c_my[h][w] = fmax(c_my[h][w], y);
+          }
+          r_e += e;
+          r_e2 += e * e;
+          r_cf += cfv;
+          r_ab += fabs(e);
+          r_ct += (ok && fabs(e) <= a.v_tol) ? 1.0 : 0.0;
+        }
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        r_e += __shfl_xor_sync(0xffffffffu, r_e, o);
+        r_e2 += __shfl_xor_sync(0xffffffffu, r_e2, o);
+        r_cf += __shfl_xor_sync(0xffffffffu, r_cf, o);
+        r_ab += __shfl_xor_sync(0xffffffffu, r_ab, o);
+        r_ct += __shfl_xor_sync(0xffffffffu, r_ct, o);
+      }
+      if (q == 0) {
+        double* r = sRed + ((warp * MET_ROWS) + 8 * f + g) * MET_ROWQ;
+        r[0] = r_e, r[1] = r_e2, r[2] = r_cf, r[3] = r_ab, r[4] = r_ct;
+      }
+    }
+    __syncthreads();
+    if (tid < MET_ROWS * MET_ROWQ) {
+      const int row = tid / MET_ROWQ, qq = tid - row * MET_ROWQ;
+      double s = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; w8++) s += sRed[(w8 * MET_ROWS + row) * MET_ROWQ + qq];
+      a.row_part[((long)qq * a.t_tiles * MET_ROWS + row_base + row) * a.n_ctile + tj] = s;
+    }
+    __syncthreads();
+  }
+
+  // ---- per-cell partials of this CTA's row range: reduce over g (8 lanes); every warp owns its columns ----
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      double v0 = c_e[h][w], v1 = c_e2[h][w], v2 = c_cf[h][w], v3 = c_mx[h][w], v4 = c_my[h][w];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        v3 = fmax(v3, __shfl_xor_sync(0xffffffffu, v3, o));
+        v4 = fmax(v4, __shfl_xor_sync(0xffffffffu, v4, o));
+      }
+      if (g == 0) {
+        double* o = a.cell_part + (long)blockIdx.y * MET_CELLQ * a.c_pad + col0 + 8 * h + w;
+        o[0] = v0, o[a.c_pad] = v1, o[2 * a.c_pad] = v2, o[3 * a.c_pad] = v3, o[4 * a.c_pad] = v4;
+      }
+    }
+}
+
+// state[q][c] (+)= fold over the row-range partials, fixed order.  first != 0: the state is (re)initialised.
+static __global__ void metrics_fold_cells_kernel(const double* __restrict__ part, int nsplit, long c_pad, double* __restrict__ state,
+                                                 int first) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c_pad) return;
+#pragma unroll
+  for (int qq = 0; qq < MET_CELLQ; qq++) {
+    double s = first ? (qq < 3 ? 0.0 : -INFINITY) : state[(long)qq * c_pad + c];
+    for (int z = 0; z < nsplit; z++) {
+      const double v = part[((long)z * MET_CELLQ + qq) * c_pad + c];
+      s = qq < 3 ? s + v : fmax(s, v);
+    }
+    state[(long)qq * c_pad + c] = s;
+  }
+}
+
+// rows_out[q][t0 + t] = sum over column tiles of row_part[q][t][:]: one warp per (q, t), fixed order.
+static __global__ void metrics_fold_rows_kernel(const double* __restrict__ part, int t_rows, long t_pitch, int n_ctile,
+                                                double* __restrict__ rows_out, long t_cap, long t0) {
+  const int lane = threadIdx.x & 31;
+  const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= (long)MET_ROWQ * t_rows) return;
+  const int qq = (int)(w / t_rows);
+  const long t = w - (long)qq * t_rows;
+  const double* p = part + ((long)qq * t_pitch + t) * n_ctile;
+  double s = 0.0;
+  for (int j = lane; j < n_ctile; j += 32) s += p[j];
+  s = warp_sum(s);
+  if (lane == 0) rows_out[(long)qq * t_cap + t0 + t] = s;
+}
+
+// Scalars of one event from the folded state (single CTA, fixed order).
+//   out[0..4]  = sum_c cell{e, e^2, conf},  sum_t row{|e|, count}
+//   out[5..8]  = peaks: sum d, sum d^2, sum xm, sum (xm - mean xm)^2      with d = max_t x - max_t y
+//   out[9..11] = counts at depth_threshold: hits (x>=thr & y>=thr), misses (x>=thr & y<thr), false alarms
+//   out[12..14]= the same three counts at threshold 0 (f2 / f3 defaults)
+constexpr int MET_SCALARS = 15;
+static __global__ void __launch_bounds__(1024) metrics_finalize_kernel(const double* __restrict__ state, long c_pad, int c,
+                                                                       const double* __restrict__ rows, long t_cap, long t_total,
+                                                                       double thr, double* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ double bc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto block_sum = [&](double v) -> double {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      double s = red[lane];
+      s = warp_sum(s);
+      if (lane == 0) bc = s;
+    }
+    __syncthreads();
+    return bc;
+  };
+  double acc[MET_SCALARS];
+#pragma unroll
+  for (int i = 0; i < MET_SCALARS; i++) acc[i] = 0.0;
+  for (long j = tid; j < c; j += 1024) {
+    acc[0] += state[j], acc[1] += state[c_pad + j], acc[2] += state[2 * c_pad + j];
+    const double xm = state[3 * c_pad + j], ym = state[4 * c_pad + j], d = xm - ym;
+    acc[5] += d, acc[6] += d * d, acc[7] += xm;
+    const bool hx = xm >= thr, hy = ym >= thr, zx = xm >= 0.0, zy = ym >= 0.0;
+    acc[9] += (hx && hy), acc[10] += (hx && !hy), acc[11] += (!hx && hy);
+    acc[12] += (zx && zy), acc[13] += (zx && !zy), acc[14] += (!zx && zy);
+  }
+  for (long t = tid; t < t_total; t += 1024) acc[3] += rows[3 * t_cap + t], acc[4] += rows[4 * t_cap + t];
+#pragma unroll
+  for (int i = 0; i < MET_SCALARS; i++)
+    if (i != 8) acc[i] = block_sum(acc[i]);
+  const double mean_xm = acc[7] / (double)c;
+  double v = 0.0;
+  for (long j = tid; j < c; j += 1024) {
+    const double u = state[3 * c_pad + j] - mean_xm;
+    v += u * u;
+  }
+  acc[8] = block_sum(v);
+  if (tid == 0)
+    for (int i = 0; i < MET_SCALARS; i++) out[i] = acc[i];
+}
+
+// fi_aoi_toi with a time tolerance (metrics.py:203-212) on device-resident (t x c) arrays: count of matching entries.
+// match[t][c] = OR_{i=0..t_tol, t+i<T} ( |y[t]-x[t+i]| <= v  or  |x[t]-y[t+i]| <= v )
+static __global__ void metrics_fidelity_kernel(const double* __restrict__ X, long ldx, const double* __restrict__ Y, long ldy, int t,
+                                               int c, int t_tol, double v_tol, double* __restrict__ part) {
+  __shared__ double red[8];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  double m = 0.0;
+  if (col < c) {
+    const double x0 = X[(long)row * ldx + col], y0 = Y[(long)row * ldy + col];
+    bool ok = fabs(y0 - x0) <= v_tol;
+    for (int i = 1; i <= t_tol && row + i < t && !ok; i++)
+      ok = fabs(y0 - X[(long)(row + i) * ldx + col]) <= v_tol || fabs(x0 - Y[(long)(row + i) * ldy + col]) <= v_tol;
+    m = ok ? 1.0 : 0.0;
+  }
+  m = warp_sum(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += red[i];
+    part[(long)row * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+}  // namespace gpras

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GPRAS_B200_ABI_VERSION 1
+#define GPRAS_B200_ABI_VERSION 2
 
 /* kernel ids == KERNEL_FACTORY keys that are constructible in the reference (gpr.py:21-29, 298) */
 #define GPRAS_KERNEL_RBF 0
@@ -103,6 +103,78 @@ int gpras_sgpr_elbo_grad(gpras_sgpr* h, const double* theta, const double* z, do
 int gpras_sgpr_condition(gpras_sgpr* h, const double* theta, const double* z, double jitter);
 int gpras_sgpr_predict(gpras_sgpr* h, const double* xs, int t, double* mean, double* var);
 int gpras_sgpr_last_launches(gpras_sgpr* h);
+
+/* ---- streaming accuracy metrics: replaces gpras/metrics.py:85-324 (called from production/analysis/pipeline.py:281-286) -- */
+/* One accumulator = one event of up to t_capacity timesteps over c cells.  It keeps, per cell, sum(x-y), sum((x-y)^2),
+ * sum(conf), max_t x, max_t y and, per timestep, sum_c(x-y), sum_c((x-y)^2), sum_c(conf), sum_c|x-y|,
+ * count_c(|x-y| <= v_tol): every function of metrics.py (with t_tol == 0) is a closed form of these. */
+typedef struct gpras_metrics gpras_metrics;
+int gpras_metrics_create(gpras_metrics** out, int device, int c, long t_capacity);
+int gpras_metrics_destroy(gpras_metrics* m);
+/* Depth conversion on the fly (PreProcessor.wse_2_depth, preprocess.py:1041-1045, as applied at pipeline.py:265-274):
+ * truth <- max(truth - elev_truth, 0), prediction <- max(prediction - elev_pred, 0).  Host arrays of c doubles; NULL = none. */
+int gpras_metrics_set_elevations(gpras_metrics* m, const double* elev_truth, const double* elev_pred);
+/* Start a new event; v_tol is fi_aoi_toi's value tolerance (metrics.py:203). */
+int gpras_metrics_reset(gpras_metrics* m, double v_tol);
+/* Accumulate t timesteps held as (t x ld) arrays: truth x (may be NULL = 0), prediction y, confidence conf (may be NULL).
+ * on_device != 0: all three are device pointers. */
+int gpras_metrics_update(gpras_metrics* m, const double* x, long ldx, const double* y, long ldy, const double* conf, long ldconf,
+                         int t, int on_device);
+/* Predict t events with a conditioned model whose cell map is bound and accumulate them against the truth (t x ldx, NULL = no
+ * truth) WITHOUT materialising the t x c cell-space prediction: mean via the modes->cells map, conf = sqrt(cell variance).
+ * mode_mean / mode_var (t*p, host) may be NULL. */
+int gpras_gp_predict_metrics(gpras_gp* h, gpras_metrics* m, const double* xs, int t, int xs_on_device, const double* truth,
+                             long ldx, int truth_on_device, double* mode_mean, double* mode_var);
+/* scalars: 15 doubles = [sum e, sum e^2, sum conf, sum |e|, count(|e|<=v_tol), sum d, sum d^2, sum xm, sum (xm-mean xm)^2,
+ * hits, misses, false alarms at depth_threshold, the same three at threshold 0] with d = max_t x - max_t y, xm = max_t x;
+ * cells (5 x c) and rows (5 x timesteps) receive the raw per-cell / per-timestep reductions (host, may be NULL). */
+int gpras_metrics_finalize(gpras_metrics* m, double depth_threshold, double* scalars, double* cells, double* rows);
+long gpras_metrics_timesteps(gpras_metrics* m);
+int gpras_metrics_last_launches(gpras_metrics* m);
+/* fi_aoi_toi (metrics.py:203-212) with a time tolerance: number of matching entries of the (t x c) arrays (host or device). */
+int gpras_metrics_fidelity(const double* x, long ldx, const double* y, long ldy, int t, int c, int t_tol, double v_tol, int device,
+                           double* matching);
+
+/* ---- PreProcessor: replaces gpras/preprocess.py:947-1094 (cells <-> modes) ----------------------------------------- */
+typedef struct gpras_pre gpras_pre;
+#define GPRAS_HP_WSE 0
+#define GPRAS_HP_DEPTH 1
+#define GPRAS_HP_VELOCITY 2
+/* c cells; hydraulic = GPRAS_HP_* (PreProcessor(hydraulic_parameter=...)); wet_threshold as in the constructor. */
+int gpras_pre_create(gpras_pre** out, int device, int c, int hydraulic, double wet_threshold);
+int gpras_pre_destroy(gpras_pre* h);
+/* PreProcessor.fit (preprocess.py:947-1007): x is (n x ldx) samples x cells (host, or device when on_device), elevations
+ * and weights host arrays of c doubles.  modes > 0: number of EOFs to keep; modes <= 0: keep max_modes and let the caller apply
+ * North's rule to the eigenvalues.  After the call the handle holds wetness classes, input mean, EOFs, eigenvalues, score
+ * statistics.  tol: residual tolerance of the retained eigenpairs relative to the largest eigenvalue; max_iter: subspace
+ * iterations.  Returns 0, or GPRAS_E_STATE when the retained eigenpairs did not converge. */
+int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device, const double* elevations, const double* weights,
+                  int modes, double tol, int max_iter);
+/* Truncate the fitted model to its first `modes` EOFs (North's rule is host logic on gpras_pre_get(.., eigenvalues)). */
+int gpras_pre_set_modes(gpras_pre* h, int modes);
+/* Restore a fitted state (PreProcessor.from_file, preprocess.py:1154-1161): full-cell-space host arrays --
+ * dry (c bytes, 1 = always dry), input_mean (c), weights (c), eofs (p x c, zero on dry cells), x_mean (p), x_std (p),
+ * elevations (c). */
+int gpras_pre_set_state(gpras_pre* h, const unsigned char* dry, const double* input_mean, const double* weights,
+                        const double* eofs, const double* x_mean, const double* x_std, const double* elevations, int p);
+/* which: 0 wetness classes (c doubles: 0 unset, 1 AD, 2 TF, 3 AF), 1 input_mean (c), 2 weights incl. zero on dry cells (c),
+ * 3 eofs (p x c), 4 eigenvalues = explained variance (gpras_pre_eigen_count values), 5 x_mean (p), 6 x_std (p),
+ * 7 residuals of the eigenpairs relative to the largest eigenvalue (gpras_pre_eigen_count values). */
+int gpras_pre_get(gpras_pre* h, int which, double* out);
+int gpras_pre_modes(gpras_pre* h);
+int gpras_pre_eigen_count(gpras_pre* h);
+int gpras_pre_iterations(gpras_pre* h);
+/* PreProcessor.transform (preprocess.py:1009-1039): z (n x p, host or device like x) = standardised EOF scores of x. */
+int gpras_pre_transform(gpras_pre* h, const double* x, long ldx, int n, int on_device, double* z);
+/* PreProcessor.reverse_transform (preprocess.py:1052-1084): mean (t x p) [and var (t x p), may be NULL] -> cell space
+ * (t x c) host arrays; depth semantics follow the handle's hydraulic parameter. */
+int gpras_pre_reverse(gpras_pre* h, const double* mean, const double* var, int t, double* cell_mean, double* cell_var);
+int gpras_pre_last_launches(gpras_pre* h);
+/* CUDA-event milliseconds of the last fit: [column stats, centre+weight, Gram, subspace iteration, EOFs, scores, total]. */
+int gpras_pre_last_stage_ms(gpras_pre* h, double* ms7);
+/* Symmetric positive semi-definite 128 x 128 eigen-decomposition (one-sided Jacobi, one CTA): device pointers, pitch 128;
+ * lambda descending, eigenvectors as columns of V.  Building block of the PCA fit, exported for tests. */
+int gpras_dsyev128(void* cuda_stream, const double* H, double* lambda, double* V);
 
 /* ---- stand-alone building blocks on device pointers (tests, composition) ------------------ */
 /* C = alpha * A(.)B(.) + beta * C on the DMMA tile engine.  shape: 0 = 128x128 CTA tile (all four layouts),

@@ -1,0 +1,183 @@
+"""GPU (-m gpu): the streaming metrics kernels (``gpras_b200/metrics.py`` -> ``gpras_metrics_*`` C ABI) against golden vectors
+produced by the reference's own ``gpras/metrics.py`` (``tests/golden/metrics_reference.npz``), against the oracle at larger /
+ragged sizes, and -- fused with the predictor -- against metrics of the materialised cell-space prediction."""
+import numpy as np
+import pytest
+
+from conftest import MET_CASES, sub
+
+pytestmark = pytest.mark.gpu
+
+VEC = ("rmse_cell_toi", "err_cell_toi", "conf_cell_toi", "err_cell_mts", "rmse_aoi_ts", "err_aoi_ts", "conf_aoi_ts")
+SCA = ("rmse_aoi_toi", "mae_aoi_toi", "conf_aoi_toi", "err_aoi_toi", "rmse_aoi_mts", "err_aoi_mts", "nse_aoi_mts", "pod_mts",
+       "rfa_mts", "csi_mts", "f2_mts", "f3_mts")
+
+
+@pytest.fixture(scope="module")
+def cuda(lib):
+    import torch
+
+    assert torch.cuda.is_available() and lib.gpras_device_count() > 0, "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.mark.parametrize("name", MET_CASES)
+def test_summary_matches_reference_golden(cuda, met_golden, name):
+    from gpras_b200 import metrics as gm
+
+    c = sub(met_golden, name)
+    s = gm.summarise(c["x"], c["y"], c["conf"], float(c["depth_threshold"]), 0.0)
+    for k in VEC:
+        np.testing.assert_allclose(s[k], c[k], rtol=1e-12, atol=1e-14, err_msg=k)
+    for k in SCA:
+        np.testing.assert_allclose(s[k], float(c[k]), rtol=1e-12, atol=1e-14, err_msg=k)
+    assert s["fi_aoi_toi"] == float(c["fi_aoi_toi_0"])
+
+
+@pytest.mark.parametrize("name", MET_CASES)
+def test_reference_function_set(cuda, met_golden, name):
+    """Every function of gpras/metrics.py by name, with the reference's signatures."""
+    from gpras_b200 import metrics as gm
+
+    c = sub(met_golden, name)
+    x, y, conf = c["x"], c["y"], c["conf"]
+    thr, t_tol, v_tol = float(c["depth_threshold"]), int(c["t_tol"]), float(c["v_tol"])
+    xm, ym = c["x_mts"], c["y_mts"]
+    tol = dict(rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(gm.rmse_aoi_toi(x, y), float(c["rmse_aoi_toi"]), **tol)
+    np.testing.assert_allclose(gm.mae_aoi_toi(x, y), float(c["mae_aoi_toi"]), **tol)
+    np.testing.assert_allclose(gm.conf_aoi_toi(conf), float(c["conf_aoi_toi"]), **tol)
+    np.testing.assert_allclose(gm.rmse_aoi_ts(x, y), c["rmse_aoi_ts"], **tol)
+    np.testing.assert_allclose(gm.rmse_cell_toi(x, y), c["rmse_cell_toi"], **tol)
+    np.testing.assert_allclose(gm.rmse_aoi_mts(x, y, xm, ym), float(c["rmse_aoi_mts"]), **tol)
+    np.testing.assert_allclose(gm.err_cell_mts(x, y), c["err_cell_mts"], **tol)
+    np.testing.assert_allclose(gm.nse_aoi_mts(x, y), float(c["nse_aoi_mts"]), **tol)
+    np.testing.assert_allclose(gm.err_aoi_toi(x, y), float(c["err_aoi_toi"]), **tol)
+    np.testing.assert_allclose(gm.err_aoi_mts(x, y), float(c["err_aoi_mts"]), **tol)
+    np.testing.assert_allclose(gm.err_aoi_ts(x, y), c["err_aoi_ts"], **tol)
+    np.testing.assert_allclose(gm.conf_aoi_ts(conf), c["conf_aoi_ts"], **tol)
+    np.testing.assert_allclose(gm.err_cell_toi(x, y), c["err_cell_toi"], **tol)
+    np.testing.assert_allclose(gm.conf_cell_toi(conf), c["conf_cell_toi"], **tol)
+    assert gm.fi_aoi_toi(x, y, t_tol, v_tol) == float(c["fi_aoi_toi"])
+    assert gm.fi_aoi_toi(x, y, 0, 0) == float(c["fi_aoi_toi_0"])
+    np.testing.assert_allclose(gm.pod_mts(x, y, thr, xm, ym), float(c["pod_mts"]), **tol)
+    np.testing.assert_allclose(gm.rfa_mts(x, y, thr, xm, ym), float(c["rfa_mts"]), **tol)
+    np.testing.assert_allclose(gm.csi_mts(x, y, thr, xm, ym), float(c["csi_mts"]), **tol)
+    np.testing.assert_allclose(gm.f2_mts(x, y, 0, xm, ym), float(c["f2_mts"]), **tol)
+    np.testing.assert_allclose(gm.f3_mts(x, y, 0, xm, ym), float(c["f3_mts"]), **tol)
+    np.testing.assert_allclose(gm.f2_mts(x, y, xm, ym), float(c["f2_mts_as_called"]), **tol)
+    np.testing.assert_allclose(gm.f3_mts(x, y, xm, ym), float(c["f3_mts_as_called"]), **tol)
+
+
+@pytest.mark.parametrize("t,c,blocks", [(333, 1000, 1), (2500, 777, 3), (70, 40000, 2)])
+def test_streaming_updates_against_oracle(cuda, t, c, blocks):
+    """Several update() calls (host and device inputs), row / column counts that are not tile multiples, depth conversion."""
+    torch = cuda
+    from gpras_b200.metrics import MetricsAccumulator
+    from oracle import metrics as om
+
+    rng = np.random.default_rng(t + c)
+    elev = rng.uniform(0, 3, c)
+    x = elev + np.maximum(rng.standard_normal((t, c)) + 0.3, -0.5)
+    y = x + 0.3 * rng.standard_normal((t, c))
+    conf = rng.uniform(0.01, 0.4, (t, c))
+    acc = MetricsAccumulator(c, t)
+    acc.set_elevations(elev, elev)
+    acc.reset(0.05)
+    cuts = np.linspace(0, t, blocks + 1).astype(int)
+    for i in range(blocks):
+        sl = slice(cuts[i], cuts[i + 1])
+        if i % 2 == 0:
+            acc.update(x[sl], y[sl], conf[sl])
+        else:
+            acc.update(torch.from_numpy(x[sl]).cuda(), torch.from_numpy(y[sl]).cuda(), torch.from_numpy(conf[sl]).cuda())
+    s = acc.finalize(0.5)
+    ref = om.summarise(np.maximum(x - elev, 0), np.maximum(y - elev, 0), conf, 0.5, 0.05)
+    for k in VEC:
+        np.testing.assert_allclose(s[k], ref[k], rtol=1e-11, atol=1e-13, err_msg=k)
+    for k in SCA + ("fi_aoi_toi",):
+        np.testing.assert_allclose(s[k], ref[k], rtol=1e-11, atol=1e-13, err_msg=k)
+    # bitwise repeatable (fixed-shape reductions, no atomics)
+    acc.reset(0.05)
+    acc.update(x, y, conf)
+    s2 = acc.finalize(0.5)
+    acc.reset(0.05)
+    acc.update(x, y, conf)
+    s3 = acc.finalize(0.5)
+    for k in VEC + SCA:
+        np.testing.assert_array_equal(s2[k], s3[k])
+    acc.close()
+
+
+@pytest.mark.parametrize("p,with_truth", [(8, True), (32, True), (40, False)])
+def test_fused_predict_metrics_match_materialised_path(cuda, p, with_truth):
+    """predict -> cells -> metrics without materialising the cell-space prediction == metrics of the materialised one."""
+    torch = cuda
+    from gpras_b200.cells import fold_cell_map
+    from gpras_b200.engine import ExactGP
+    from gpras_b200.metrics import MetricsAccumulator
+    from gpras_b200.synth import fixed_theta, make_cell_map, make_gp_data
+    from oracle import metrics as om
+    from oracle.cells import reverse_transform
+
+    n, d, c, t = 300, 6, 3001, 1111
+    data = make_gp_data(n, d, p, t, seed=3)
+    cm = make_cell_map(p, c, seed=4)
+    e_mean, bias = fold_cell_map(cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices, cm.elevations)
+    gp = ExactGP("Matern52", n, d, p)
+    gp.set_data(data.x, data.y)
+    v, s, ls = fixed_theta(d, True)
+    gp.condition(gp.theta_vector(v, s, ls))
+    gp.set_cell_map(e_mean, bias)
+    mean, var = gp.predict(data.x_test)
+    cell_m, cell_v = reverse_transform(mean, var, cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices,
+                                       cm.elevations)
+    rng = np.random.default_rng(9)
+    truth = cell_m + 0.2 * rng.standard_normal(cell_m.shape) if with_truth else None
+    acc = MetricsAccumulator(c, t)
+    acc.set_elevations(cm.elevations if with_truth else None, cm.elevations)
+    acc.reset(0.1)
+    mm, mv = acc.predict_update(gp, data.x_test[:600], None if truth is None else truth[:600], want_modes=True)
+    acc.predict_update(gp, torch.from_numpy(data.x_test[600:]).cuda(), None if truth is None else torch.from_numpy(truth[600:]).cuda())
+    got = acc.finalize(0.5)
+    np.testing.assert_allclose(mm, mean[:600], rtol=1e-12, atol=1e-12)
+    y = np.maximum(cell_m - cm.elevations, 0)
+    x = np.maximum(truth - cm.elevations, 0) if with_truth else np.zeros_like(y)
+    ref = om.summarise(x, y, np.sqrt(cell_v), 0.5, 0.1)
+    for k in VEC:
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-11, err_msg=k)
+    for k in SCA + ("fi_aoi_toi",):
+        if np.isfinite(ref[k]):
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-11, err_msg=k)
+    assert acc.timesteps() == t
+    acc.close()
+    gp.close()
+
+
+def test_export_metric_summary_tables(cuda, tmp_path):
+    """Same sqlite tables / columns as gpras/metrics.py:75-82, values equal to the per-event summaries."""
+    import sqlite3
+
+    import pandas as pd
+
+    from gpras_b200 import metrics as gm
+
+    rng = np.random.default_rng(0)
+    idx = pd.MultiIndex.from_product([["e1", "e2"], range(12)], names=["event", "t"])
+    cols = [f"c{i}" for i in range(37)]
+    x = pd.DataFrame(np.maximum(rng.standard_normal((24, 37)) + 0.5, 0), index=idx, columns=cols)
+    y = pd.DataFrame(np.maximum(x.values + 0.2 * rng.standard_normal((24, 37)), 0), index=idx, columns=cols)
+    conf = pd.DataFrame(rng.uniform(0.1, 0.3, (24, 37)), index=idx, columns=cols)
+    out = tmp_path / "m.db"
+    gm.export_metric_summary(x, y, conf, out)
+    with sqlite3.connect(out) as con:
+        sc = pd.read_sql("select * from scalar_metrics", con)
+        ts = pd.read_sql("select * from timeseries_metrics", con)
+        ce = pd.read_sql("select * from cell_metrics", con)
+    assert list(sc.columns) == ["event", "rmse_aoi_toi", "mae_aoi_toi", "conf_aoi_toi", "rmse_aoi_mts", "nse_aoi_mts", "err_aoi_toi",
+                                "err_aoi_mts", "fi_aoi_toi", "pod_mts", "rfa_mts", "csi_mts", "f2_mts", "f3_mts"]
+    assert len(sc) == 2 and len(ts) == 24 and len(ce) == 74
+    e1 = x.loc["e1"].values - y.loc["e1"].values
+    np.testing.assert_allclose(sc.rmse_aoi_toi[0], np.sqrt((e1 ** 2).mean()), rtol=1e-12)
+    np.testing.assert_allclose(ts.err_aoi_ts[:12], e1.mean(axis=1), rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(ce.rmse_cell_toi[:37], np.sqrt((e1 ** 2).mean(axis=0)), rtol=1e-12)

@@ -1,0 +1,133 @@
+"""GPU (-m gpu): the device PreProcessor mirror (``gpras_b200/preprocess.py`` -> ``gpras_pre_*`` C ABI) against golden vectors
+produced by the reference's own ``PreProcessor`` (``tests/golden/preprocess_reference.npz``) and against the oracle at sizes
+the goldens do not cover.  FP64 throughout; tolerances: classes exact, means 1e-12, EOFs / scores 1e-8 (the PCA goes
+through the Gram matrix, whose eigenvectors carry ~eps * lambda_1 / gap), transform / reverse transform 1e-10."""
+import numpy as np
+import pytest
+
+from conftest import PRE_CASES, sub
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda(lib):
+    import torch
+
+    assert torch.cuda.is_available() and lib.gpras_device_count() > 0, "GPU tests need a CUDA device"
+    return torch
+
+
+def _fit(c):
+    from gpras_b200.preprocess import PreProcessor
+
+    hp = str(c["hydraulic_parameter"])
+    modes = None if int(c["modes_requested"]) < 0 else int(c["modes_requested"])
+    pp = PreProcessor(wet_threshold=0.03, hydraulic_parameter=hp)
+    pp.fit(c["x"].copy(), c["elevations"].copy(), c["weights"].copy(), modes)
+    return pp
+
+
+@pytest.mark.parametrize("name", PRE_CASES)
+def test_fit_matches_reference_golden(cuda, pre_golden, name):
+    c = sub(pre_golden, name)
+    pp = _fit(c)
+    assert list(pp.wetness_classes) == list(c["wetness_classes"])
+    assert pp.spatial_mode_count == int(c["spatial_mode_count"])
+    np.testing.assert_allclose(pp.input_mean, c["input_mean"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(pp.weights, c["fit_weights"])
+    k = len(pp.eigenvalues)
+    np.testing.assert_allclose(pp.eigenvalues, c["eigenvalues"][:k], rtol=1e-9, atol=1e-9 * c["eigenvalues"][0])
+    np.testing.assert_allclose(pp.eofs, c["eofs"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(pp.x_mean, c["x_mean"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(pp.x_std, c["x_std"], rtol=1e-9)
+    assert pp.n_samples_fit == int(c["n_samples_fit"])
+    pp.close()
+
+
+@pytest.mark.parametrize("name", PRE_CASES)
+def test_transform_and_reverse_match_reference_golden(cuda, pre_golden, name, tmp_path):
+    from gpras_b200.preprocess import PreProcessor
+
+    c = sub(pre_golden, name)
+    # state taken from the reference's fit: isolates transform / reverse_transform from the PCA
+    pp = PreProcessor(
+        spatial_mode_count=int(c["spatial_mode_count"]), input_mean=c["input_mean"], wet_threshold=0.03, elevations=c["elevations"],
+        hydraulic_parameter=str(c["hydraulic_parameter"]), wetness_classes=c["wetness_classes"], weights=c["fit_weights"],
+        eofs=c["eofs"], eigenvalues=c["eigenvalues"], n_samples_fit=int(c["n_samples_fit"]), x_mean=c["x_mean"], x_std=c["x_std"])
+    # persistence round trip with the reference's pickle keys
+    pp.to_file(tmp_path / "pp.pkl")
+    pp = PreProcessor.from_file(tmp_path / "pp.pkl")
+    z = pp.transform(c["x_new"].copy())
+    np.testing.assert_allclose(z, c["transformed"], rtol=1e-10, atol=1e-10)
+    m = pp.reverse_transform(c["mode_mean"])
+    np.testing.assert_allclose(m, c["reverse_mean_only"], rtol=1e-12, atol=1e-12)
+    for vk, rk in (("mode_var", "reverse_var"), ("mode_var_free", "reverse_var_free")):
+        m, v = pp.reverse_transform(c["mode_mean"], c[vk])
+        np.testing.assert_allclose(m, c["reverse_mean"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(v, c[rk], rtol=1e-12, atol=1e-14)
+    np.testing.assert_array_equal(pp.wse_2_depth(c["reverse_mean"].copy()), c["reverse_depth"])
+    pp.close()
+
+
+def test_fit_then_transform_device_tensor(cuda, pre_golden):
+    """CUDA-tensor inputs (no host staging) give the same result as host arrays."""
+    torch = cuda
+    c = sub(pre_golden, "wse_fixed")
+    pp = _fit(c)
+    z_host = pp.transform(c["x_new"].copy())
+    z_dev = pp.transform(torch.from_numpy(c["x_new"]).cuda())
+    np.testing.assert_array_equal(z_dev.cpu().numpy(), z_host)
+    np.testing.assert_allclose(z_host, c["transformed"], rtol=1e-7, atol=1e-7)
+    pp.close()
+
+
+@pytest.mark.parametrize("n,cells,k,modes,hp", [(700, 3000, 6, 6, "wse"), (1500, 1100, 5, 5, "depth"), (300, 5000, 8, None, "wse")])
+def test_fit_subspace_iteration_against_oracle(cuda, n, cells, k, modes, hp):
+    """More samples than one 128-block: the subspace iteration has to converge (not just diagonalise the whole Gram)."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    from make_golden_reference import flood_samples
+    from gpras_b200.preprocess import PreProcessor
+    from oracle import preprocess as opre
+
+    wse, elev, w = flood_samples(n, cells, k, seed=n + cells, noise=0.02)
+    f = opre.fit(wse, elev, w, modes, 0.03, hp)
+    pp = PreProcessor(wet_threshold=0.03, hydraulic_parameter=hp)
+    pp.fit(wse.copy(), elev, w, modes)
+    assert pp.spatial_mode_count == f.modes
+    np.testing.assert_array_equal(pp.dry_indices, f.dry)
+    np.testing.assert_allclose(pp.input_mean, f.input_mean, rtol=1e-12, atol=1e-12)
+    p = f.modes
+    np.testing.assert_allclose(pp.eigenvalues[:p], f.eigenvalues[:p], rtol=1e-9)
+    np.testing.assert_allclose(pp.eofs, f.eofs, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(pp.x_std, f.x_std, rtol=1e-9)
+    np.testing.assert_allclose(pp.transform(wse[:50].copy()), opre.transform(f, wse[:50], elev, hp), rtol=1e-8, atol=1e-8)
+    assert pp.fit_info["iterations"] >= 1
+    # round trip: reverse_transform(transform(x)) is the rank-P projector of the centred, weighted field
+    if hp == "wse":  # ("depth" clamps negative reconstructed depths on the way back in, so it is not a projector)
+        z = pp.transform(wse[:20].copy())
+        back = pp.reverse_transform(z)
+        z2 = pp.transform(back)
+        np.testing.assert_allclose(z2, z, rtol=1e-8, atol=1e-8)
+    pp.close()
+
+
+def test_dsyev128_against_lapack(cuda, lib):
+    torch = cuda
+    from gpras_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((128, 90))
+    h = a @ np.diag(np.logspace(0, -6, 90)) @ a.T
+    H = torch.from_numpy(h).cuda()
+    lam = torch.zeros(128, dtype=torch.float64, device="cuda")
+    V = torch.zeros(128, 128, dtype=torch.float64, device="cuda")
+    _lib.check(lib.gpras_dsyev128(torch.cuda.current_stream().cuda_stream, H.data_ptr(), lam.data_ptr(), V.data_ptr()))
+    w = np.linalg.eigvalsh(h)[::-1]
+    np.testing.assert_allclose(lam.cpu().numpy(), np.maximum(w, 0), rtol=0, atol=1e-13 * w[0])
+    v = V.cpu().numpy()[:, :40]
+    np.testing.assert_allclose(v.T @ v, np.eye(40), atol=1e-9)
+    np.testing.assert_allclose(h @ v, v * lam.cpu().numpy()[:40], atol=1e-12 * w[0])
