@@ -68,6 +68,7 @@ SYMBOLS = {
     "gpras_pre_iterations": (C.c_int, [vp]),
     "gpras_pre_transform": (C.c_int, [vp, vp, C.c_long, C.c_int, C.c_int, vp]),
     "gpras_pre_reverse": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    "gpras_pre_trim": (C.c_int, [vp]),
     "gpras_pre_last_launches": (C.c_int, [vp]),
     "gpras_pre_last_stage_ms": (C.c_int, [vp, vp]),
     "gpras_dsyev128": (C.c_int, [vp, vp, vp, vp]),

@@ -16,7 +16,7 @@ struct gpras_metrics {
   int launches = 0;
   cudaStream_t stream = nullptr;
   double *state = nullptr, *rows = nullptr, *cell_part = nullptr, *row_part = nullptr, *elev_x = nullptr, *elev_y = nullptr,
-         *scal = nullptr, *stage[3] = {nullptr, nullptr, nullptr};
+         *scal = nullptr, *scal2 = nullptr, *cta_part = nullptr, *stage[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -39,7 +39,8 @@ int metrics_block(gpras_metrics* m, cudaStream_t s, MetricsArgs a, int t, int p1
   const int per_cta = (t_tiles + splits - 1) / splits;
   splits = (t_tiles + per_cta - 1) / per_cta;
   a.t_rows = t, a.c = m->c, a.t_tiles = t_tiles, a.tiles_per_cta = per_cta, a.v_tol = m->v_tol;
-  a.cell_part = m->cell_part, a.c_pad = m->c_pad, a.row_part = m->row_part, a.n_ctile = m->n_ctile;
+  a.cell_part = m->cell_part, a.c_pad = m->c_pad, a.row_part = m->row_part, a.n_ctile = m->n_ctile, a.cta_part = m->cta_part;
+  a.x_vec = a.X && (a.ldx % 2 == 0) && ((uintptr_t)a.X % 16 == 0);
   a.elev_x = m->has_ex ? m->elev_x : nullptr;
   a.elev_y = m->has_ey ? m->elev_y : nullptr;
   dim3 grid(m->n_ctile, splits);
@@ -58,7 +59,9 @@ int metrics_block(gpras_metrics* m, cudaStream_t s, MetricsArgs a, int t, int p1
   metrics_fold_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(m->row_part, t, (long)t_tiles * MET_ROWS, m->n_ctile,
                                                                               m->rows, m->t_cap, m->t_seen);
   CU(cudaGetLastError());
-  m->launches += 3;
+  metrics_fold_cta_kernel<<<1, 32, 0, s>>>(m->cta_part, splits * m->n_ctile, m->scal2, m->first ? 1 : 0);
+  CU(cudaGetLastError());
+  m->launches += 4;
   m->first = false;
   m->t_seen += t;
   return 0;
@@ -91,7 +94,8 @@ int gpras_metrics_create(gpras_metrics** out, int device, int c, long t_capacity
   if ((r = dalloc(&m->state, (size_t)MET_CELLQ * m->c_pad)) || (r = dalloc(&m->rows, (size_t)MET_ROWQ * m->t_cap)) ||
       (r = dalloc(&m->cell_part, (size_t)MET_MAX_SPLIT * MET_CELLQ * m->c_pad)) ||
       (r = dalloc(&m->row_part, (size_t)MET_ROWQ * MET_TB * m->n_ctile)) || (r = dalloc(&m->elev_x, m->c_pad)) ||
-      (r = dalloc(&m->elev_y, m->c_pad)) || (r = dalloc(&m->scal, MET_SCALARS))) {
+      (r = dalloc(&m->elev_y, m->c_pad)) || (r = dalloc(&m->scal, MET_SCALARS)) || (r = dalloc(&m->scal2, MET_CTAQ)) ||
+      (r = dalloc(&m->cta_part, (size_t)MET_MAX_SPLIT * m->n_ctile * MET_CTAQ))) {
     gpras_metrics_destroy(m);
     return r;
   }
@@ -107,7 +111,7 @@ int gpras_metrics_destroy(gpras_metrics* m) {
   if (!m) return 0;
   DeviceGuard guard(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
-  double* bufs[] = {m->state, m->rows, m->cell_part, m->row_part, m->elev_x, m->elev_y, m->scal, m->stage[0], m->stage[1], m->stage[2]};
+  double* bufs[] = {m->state, m->rows, m->cell_part, m->row_part, m->elev_x, m->elev_y, m->scal, m->scal2, m->cta_part, m->stage[0], m->stage[1], m->stage[2]};
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -224,7 +228,7 @@ int gpras_metrics_finalize(gpras_metrics* m, double depth_threshold, double* sca
   if (m->t_seen <= 0) return fail(GPRAS_E_STATE, "no timesteps accumulated");
   DeviceGuard guard(m->device);
   cudaStream_t s = m->stream;
-  metrics_finalize_kernel<<<1, 1024, 0, s>>>(m->state, m->c_pad, m->c, m->rows, m->t_cap, m->t_seen, depth_threshold, m->scal);
+  metrics_finalize_kernel<<<1, 1024, 0, s>>>(m->state, m->c_pad, m->c, m->scal2, depth_threshold, m->scal);
   CU(cudaGetLastError());
   m->launches++;
   CU(cudaMemcpyAsync(scalars, m->scal, sizeof(double) * MET_SCALARS, cudaMemcpyDeviceToHost, s));

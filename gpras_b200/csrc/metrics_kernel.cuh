@@ -20,7 +20,8 @@ namespace gpras {
 constexpr int MET_THREADS = 256;
 constexpr int MET_ROWS = 32;   // timesteps per row tile
 constexpr int MET_CELLQ = 5;   // per cell: sum e, sum e^2, sum conf, max x, max y
-constexpr int MET_ROWQ = 5;    // per row : sum e, sum e^2, sum conf, sum |e|, count(|e| <= v_tol)
+constexpr int MET_ROWQ = 3;    // per row : sum e, sum e^2, sum conf
+constexpr int MET_CTAQ = 2;    // per CTA : sum |e|, count(|e| <= v_tol)
 
 struct MetricsArgs {
   // FUSED prediction source
@@ -39,6 +40,7 @@ struct MetricsArgs {
   // truth (NULL: x == 0)
   const double* X;
   long ldx;
+  int x_vec;             // truth rows are 16-byte aligned (ldx even, base aligned): 128-bit loads
   const double* elev_x;  // NULL: truth used as is; else x = max(X - elev_x, 0)
   const double* elev_y;  // NULL: prediction used as is; else y = max(y - elev_y, 0)
   int t_rows;            // valid rows of this block
@@ -48,6 +50,7 @@ struct MetricsArgs {
   double* cell_part;     // [gridDim.y][MET_CELLQ][c_pad]
   long c_pad;
   double* row_part;      // [MET_ROWQ][t_tiles * MET_ROWS][n_ctile]
+  double* cta_part;      // [gridDim.y][n_ctile][MET_CTAQ]
   int n_ctile;
 };
 
@@ -55,23 +58,29 @@ template <int P16>
 struct MetCfg {
   static constexpr int LDE = 128 + 4;
   static constexpr int LDA = P16 + 4;
-  // E tile, two row tiles of modes, two variance vectors, row-reduction scratch [8 warps][MET_ROWS][MET_ROWQ]
-  static constexpr int RED_DOUBLES = 8 * MET_ROWS * MET_ROWQ;
+  // E tile, two row tiles of modes, two variance vectors, reduction scratch
+  static constexpr int RED_DOUBLES = 2 * MET_ROWS * 33 + 16;
   static constexpr int SMEM_DOUBLES = P16 * LDE + 2 * MET_ROWS * LDA + 2 * MET_ROWS + RED_DOUBLES;
   static constexpr int SMEM_BYTES = SMEM_DOUBLES * (int)sizeof(double);
 };
-constexpr int MET_PLAIN_SMEM_BYTES = 8 * MET_ROWS * MET_ROWQ * (int)sizeof(double);
+constexpr int MET_PLAIN_SMEM_BYTES = (3 * MET_ROWS * 33 + 16) * (int)sizeof(double);
 
 // Thread layout: warp w owns the 16 columns [16w, 16w+16) of the CTA's 128-cell tile for all 32 rows of a row tile
 // (4 x 2 DMMA accumulator tiles); a thread holds rows 8f+g (f < 4) and columns 16w + 8h + 2q + {0,1} (h < 2).
+// Row sums go through shared memory (one slot per thread, then 32-way fixed-order sums); |e| and the match count are
+// only ever needed as event totals, so they stay in two per-thread scalars until the CTA ends.  In FUSED mode the
+// confidence is separable, conf[t][c] = sqrt(var[t]) * rootS[c]: its row sums are sqrt(var[t]) * sum_c rootS[c] and its
+// per-cell sums rootS[c] * sum_t sqrt(var[t]), so it costs no per-element work at all.
 template <int P16, bool FUSED>
-__global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const MetricsArgs a) {
+__global__ void __launch_bounds__(MET_THREADS, FUSED ? 2 : 1) metrics_stream_kernel(const MetricsArgs a) {
   using Cfg = MetCfg<P16>;
+  constexpr int NQ = FUSED ? 2 : 3;  // row quantities reduced through shared memory
   extern __shared__ __align__(16) double smem[];
   double* sE = smem;
   double* sA = sE + (FUSED ? P16 * Cfg::LDE : 0);
   double* sV = sA + (FUSED ? 2 * MET_ROWS * Cfg::LDA : 0);
-  double* sRed = sV + (FUSED ? 2 * MET_ROWS : 0);  // [8 warps][MET_ROWS][MET_ROWQ]
+  double* sRed = sV + (FUSED ? 2 * MET_ROWS : 0);  // [NQ][MET_ROWS][33]
+  double* sMisc = sRed + NQ * MET_ROWS * 33;       // [16]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int wn = warp * 16;
@@ -80,17 +89,18 @@ __global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const Me
   int t_end = t_begin + a.tiles_per_cta;
   if (t_end > a.t_tiles) t_end = a.t_tiles;
   const long col0 = (long)tj * 128 + wn + 2 * q;  // column of (h = 0, w = 0); (h, w) adds 8h + w
+  const bool cols_full = (long)tj * 128 + 128 <= a.c;
+  const bool has_ex = a.elev_x != nullptr, has_ey = a.elev_y != nullptr;
 
-  double ex[2][2], ey[2][2], rs[2][2];
+  double ex[2][2], rs[2][2];
 #pragma unroll
   for (int h = 0; h < 2; h++)
 #pragma unroll
     for (int w = 0; w < 2; w++) {
       const long c = col0 + 8 * h + w;
       const bool ok = c < a.c;
-      ex[h][w] = (a.elev_x && ok) ? a.elev_x[c] : 0.0;
-      ey[h][w] = (a.elev_y && ok) ? a.elev_y[c] : 0.0;
-      rs[h][w] = FUSED ? a.rootS[c] : 0.0;
+      ex[h][w] = (has_ex && ok) ? a.elev_x[c] : 0.0;
+      rs[h][w] = (FUSED && ok) ? a.rootS[c] : 0.0;
     }
   double c_e[2][2], c_e2[2][2], c_cf[2][2], c_mx[2][2], c_my[2][2];
 #pragma unroll
@@ -100,6 +110,7 @@ __global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const Me
       c_e[h][w] = c_e2[h][w] = c_cf[h][w] = 0.0;
       c_mx[h][w] = c_my[h][w] = -INFINITY;
     }
+  double s_ab = 0.0, s_ct = 0.0, s_sv = 0.0, rs_cta = 0.0;
 
   auto load_rows = [&](int buf, int tt) {
     constexpr int CPR = P16 / 2;
@@ -116,24 +127,56 @@ __global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const Me
     }
     load_rows(0, t_begin);
     cp_async_commit();
+    // sum of rootS over this CTA's valid columns (fixed order): warp partial, then 8 warps
+    double v = (rs[0][0] + rs[0][1]) + (rs[1][0] + rs[1][1]);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (lane == 0) sMisc[warp] = v;
+    __syncthreads();
+    rs_cta = ((sMisc[0] + sMisc[1]) + (sMisc[2] + sMisc[3])) + ((sMisc[4] + sMisc[5]) + (sMisc[6] + sMisc[7]));
   }
+  // prediction offset: the bias with the depth conversion's elevation folded in
+  double b0[2][2];
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      const long c = col0 + 8 * h + w;
+      b0[h][w] = FUSED ? a.bias[c] - ((has_ey && c < a.c) ? a.elev_y[c] : 0.0) : ((has_ey && c < a.c) ? a.elev_y[c] : 0.0);
+    }
 
   for (int tt = t_begin; tt < t_end; tt++) {
     const int buf = (tt - t_begin) & 1;
     const int row_base = tt * MET_ROWS;
+    const bool full = cols_full && row_base + MET_ROWS <= a.t_rows;
     // truth for this tile: issued first, consumed after the DMMA loop
     double xv[4][2][2];
+    if (a.X == nullptr) {
 #pragma unroll
-    for (int f = 0; f < 4; f++) {
-      const int row = row_base + 8 * f + g;
-      const bool rok = a.X != nullptr && row < a.t_rows;
+      for (int f = 0; f < 4; f++)
 #pragma unroll
-      for (int h = 0; h < 2; h++)
+        for (int h = 0; h < 2; h++) xv[f][h][0] = xv[f][h][1] = 0.0;
+    } else if (full && a.x_vec) {
 #pragma unroll
-        for (int w = 0; w < 2; w++) {
-          const long c = col0 + 8 * h + w;
-          xv[f][h][w] = (rok && c < a.c) ? __ldg(a.X + (long)row * a.ldx + c) : 0.0;
+      for (int f = 0; f < 4; f++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const double2 v = __ldg(reinterpret_cast<const double2*>(a.X + (long)(row_base + 8 * f + g) * a.ldx + col0 + 8 * h));
+          xv[f][h][0] = v.x, xv[f][h][1] = v.y;
         }
+    } else {
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        const int row = row_base + 8 * f + g;
+        const bool rok = row < a.t_rows;
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int w = 0; w < 2; w++) {
+            const long c = col0 + 8 * h + w;
+            xv[f][h][w] = (rok && c < a.c) ? __ldg(a.X + (long)row * a.ldx + c) : 0.0;
+          }
+      }
     }
     double acc[4][2][2], cf[FUSED ? 1 : 4][2][2];
     if (FUSED) {
@@ -142,11 +185,9 @@ __global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const Me
       if (tt + 1 < t_end) load_rows(buf ^ 1, tt + 1);
       cp_async_commit();
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const double b0 = a.bias[col0 + 8 * h], b1 = a.bias[col0 + 8 * h + 1];
+      for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int f = 0; f < 4; f++) acc[f][h][0] = b0, acc[f][h][1] = b1;
-      }
+        for (int f = 0; f < 4; f++) acc[f][h][0] = b0[h][0], acc[f][h][1] = b0[h][1];
       const double* a0 = sA + buf * MET_ROWS * Cfg::LDA;
 #pragma unroll
       for (int ks = 0; ks < P16 / 4; ks++) {
@@ -171,7 +212,7 @@ __global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const Me
           for (int w = 0; w < 2; w++) {
             const long c = col0 + 8 * h + w;
             const bool ok = rok && c < a.c;
-            acc[f][h][w] = ok ? __ldg(a.Y + (long)row * a.ldy + c) : 0.0;
+            acc[f][h][w] = (ok ? __ldg(a.Y + (long)row * a.ldy + c) : 0.0) - b0[h][w];
             cf[FUSED ? 0 : f][h][w] = (ok && a.CONF) ? __ldg(a.CONF + (long)row * a.ldconf + c) : 0.0;
           }
       }
@@ -179,58 +220,70 @@ __global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const Me
     // ---- elementwise + reductions, one row at a time ----
 #pragma unroll
     for (int f = 0; f < 4; f++) {
-      const int row = row_base + 8 * f + g;
-      const bool rok = row < a.t_rows;
-      const double sv = FUSED ? sqrt(sV[buf * MET_ROWS + 8 * f + g]) : 0.0;
-      double r_e = 0.0, r_e2 = 0.0, r_cf = 0.0, r_ab = 0.0, r_ct = 0.0;
+      const int rl = 8 * f + g;
+      const bool rok = full || row_base + rl < a.t_rows;
+      double r_e = 0.0, r_e2 = 0.0, r_cf = 0.0;
+      if (FUSED) {
+        const double sv = rok ? sqrt(sV[buf * MET_ROWS + rl]) : 0.0;
+        s_sv += sv;
+        if (warp == 0 && q == 0) a.row_part[((long)2 * a.t_tiles * MET_ROWS + row_base + rl) * a.n_ctile + tj] = sv * rs_cta;
+      }
 #pragma unroll
       for (int h = 0; h < 2; h++)
 #pragma unroll
         for (int w = 0; w < 2; w++) {
-          const bool ok = rok && (col0 + 8 * h + w < a.c);
           double x = xv[f][h][w], y = acc[f][h][w];
-          if (a.elev_x) x = fmax(x - ex[h][w], 0.0);
-          if (a.elev_y) y = fmax(y - ey[h][w], 0.0);
-          const double e = ok ? x - y : 0.0;
-          const double cfv = ok ? (FUSED ? sv * rs[h][w] : cf[FUSED ? 0 : f][h][w]) : 0.0;
-          c_e[h][w] += e;
-          c_e2[h][w] += e * e;
-          c_cf[h][w] += cfv;
-          if (ok) {
+          if (has_ex) x = fmax(x - ex[h][w], 0.0);
+          if (has_ey) y = fmax(y, 0.0);
+          double e = x - y;
+          if (full) {
             c_mx[h][w] = fmax(c_mx[h][w], x);
             c_my[h][w] = fmax(c_my[h][w], y);
+            s_ct += fabs(e) <= a.v_tol ? 1.0 : 0.0;
+          } else {
+            const bool ok = rok && (col0 + 8 * h + w < a.c);
+            e = ok ? e : 0.0;
+            if (ok) {
+              c_mx[h][w] = fmax(c_mx[h][w], x);
+              c_my[h][w] = fmax(c_my[h][w], y);
+              s_ct += fabs(e) <= a.v_tol ? 1.0 : 0.0;
+            }
           }
+          c_e[h][w] += e;
+          c_e2[h][w] = fma(e, e, c_e2[h][w]);
           r_e += e;
-          r_e2 += e * e;
-          r_cf += cfv;
-          r_ab += fabs(e);
-          r_ct += (ok && fabs(e) <= a.v_tol) ? 1.0 : 0.0;
+          r_e2 = fma(e, e, r_e2);
+          s_ab += fabs(e);
+          if (!FUSED) {
+            const double cfv = cf[FUSED ? 0 : f][h][w];  // already zero where masked
+            c_cf[h][w] += cfv;
+            r_cf += cfv;
+          }
         }
-#pragma unroll
-      for (int o = 1; o < 4; o <<= 1) {
-        r_e += __shfl_xor_sync(0xffffffffu, r_e, o);
-        r_e2 += __shfl_xor_sync(0xffffffffu, r_e2, o);
-        r_cf += __shfl_xor_sync(0xffffffffu, r_cf, o);
-        r_ab += __shfl_xor_sync(0xffffffffu, r_ab, o);
-        r_ct += __shfl_xor_sync(0xffffffffu, r_ct, o);
-      }
-      if (q == 0) {
-        double* r = sRed + ((warp * MET_ROWS) + 8 * f + g) * MET_ROWQ;
-        r[0] = r_e, r[1] = r_e2, r[2] = r_cf, r[3] = r_ab, r[4] = r_ct;
-      }
+      const int slot = warp * 4 + q;
+      sRed[(0 * MET_ROWS + rl) * 33 + slot] = r_e;
+      sRed[(1 * MET_ROWS + rl) * 33 + slot] = r_e2;
+      if (!FUSED) sRed[(2 * MET_ROWS + rl) * 33 + slot] = r_cf;
     }
     __syncthreads();
-    if (tid < MET_ROWS * MET_ROWQ) {
-      const int row = tid / MET_ROWQ, qq = tid - row * MET_ROWQ;
+    if (tid < NQ * MET_ROWS) {
+      const double* r = sRed + tid * 33;  // tid = quantity * MET_ROWS + row
       double s = 0.0;
 #pragma unroll
-      for (int w8 = 0; w8 < 8; w8++) s += sRed[(w8 * MET_ROWS + row) * MET_ROWQ + qq];
+      for (int k = 0; k < 32; k++) s += r[k];
+      const int qq = tid / MET_ROWS, row = tid - qq * MET_ROWS;
       a.row_part[((long)qq * a.t_tiles * MET_ROWS + row_base + row) * a.n_ctile + tj] = s;
     }
     __syncthreads();
   }
 
   // ---- per-cell partials of this CTA's row range: reduce over g (8 lanes); every warp owns its columns ----
+  if (FUSED) {
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int w = 0; w < 2; w++) c_cf[h][w] = rs[h][w] * s_sv;
+  }
 #pragma unroll
   for (int h = 0; h < 2; h++)
 #pragma unroll
@@ -249,6 +302,16 @@ __global__ void __launch_bounds__(MET_THREADS, 1) metrics_stream_kernel(const Me
         o[0] = v0, o[a.c_pad] = v1, o[2 * a.c_pad] = v2, o[3 * a.c_pad] = v3, o[4 * a.c_pad] = v4;
       }
     }
+  // ---- CTA scalars: sum |e| and the match count ----
+  s_ab = warp_sum(s_ab);
+  s_ct = warp_sum(s_ct);
+  __syncthreads();
+  if (lane == 0) sMisc[warp] = s_ab, sMisc[8 + warp] = s_ct;
+  __syncthreads();
+  if (tid < 2) {
+    const double* r = sMisc + 8 * tid;
+    a.cta_part[((long)blockIdx.y * a.n_ctile + tj) * MET_CTAQ + tid] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  }
 }
 
 // state[q][c] (+)= fold over the row-range partials, fixed order.  first != 0: the state is (re)initialised.
@@ -282,15 +345,27 @@ static __global__ void metrics_fold_rows_kernel(const double* __restrict__ part,
   if (lane == 0) rows_out[(long)qq * t_cap + t0 + t] = s;
 }
 
+// scal2[0..1] (+)= sum over the CTA partials of one block (fixed order, single warp).
+static __global__ void metrics_fold_cta_kernel(const double* __restrict__ part, int count, double* __restrict__ scal2, int first) {
+  const int lane = threadIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = lane; i < count; i += 32) s0 += part[(long)i * MET_CTAQ], s1 += part[(long)i * MET_CTAQ + 1];
+  s0 = warp_sum(s0), s1 = warp_sum(s1);
+  if (lane == 0) {
+    scal2[0] = (first ? 0.0 : scal2[0]) + s0;
+    scal2[1] = (first ? 0.0 : scal2[1]) + s1;
+  }
+}
+
 // Scalars of one event from the folded state (single CTA, fixed order).
-//   out[0..4]  = sum_c cell{e, e^2, conf},  sum_t row{|e|, count}
+//   out[0..4]  = sum_c cell{e, e^2, conf},  sum |e|, count(|e| <= v_tol) (running scalars scal2)
 //   out[5..8]  = peaks: sum d, sum d^2, sum xm, sum (xm - mean xm)^2      with d = max_t x - max_t y
 //   out[9..11] = counts at depth_threshold: hits (x>=thr & y>=thr), misses (x>=thr & y<thr), false alarms
 //   out[12..14]= the same three counts at threshold 0 (f2 / f3 defaults)
 constexpr int MET_SCALARS = 15;
 static __global__ void __launch_bounds__(1024) metrics_finalize_kernel(const double* __restrict__ state, long c_pad, int c,
-                                                                       const double* __restrict__ rows, long t_cap, long t_total,
-                                                                       double thr, double* __restrict__ out) {
+                                                                       const double* __restrict__ scal2, double thr,
+                                                                       double* __restrict__ out) {
   __shared__ double red[32];
   __shared__ double bc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -318,10 +393,10 @@ static __global__ void __launch_bounds__(1024) metrics_finalize_kernel(const dou
     acc[9] += (hx && hy), acc[10] += (hx && !hy), acc[11] += (!hx && hy);
     acc[12] += (zx && zy), acc[13] += (zx && !zy), acc[14] += (!zx && zy);
   }
-  for (long t = tid; t < t_total; t += 1024) acc[3] += rows[3 * t_cap + t], acc[4] += rows[4 * t_cap + t];
 #pragma unroll
   for (int i = 0; i < MET_SCALARS; i++)
-    if (i != 8) acc[i] = block_sum(acc[i]);
+    if (i != 8 && i != 3 && i != 4) acc[i] = block_sum(acc[i]);
+  acc[3] = scal2[0], acc[4] = scal2[1];
   const double mean_xm = acc[7] / (double)c;
   double v = 0.0;
   for (long j = tid; j < c; j += 1024) {

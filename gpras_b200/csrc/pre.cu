@@ -1,6 +1,8 @@
 // C ABI of the PreProcessor mirror (include/gpras_b200.h, "PreProcessor" section): cells <-> modes on the device.
 // Replaces the NumPy / scikit-learn arithmetic of gpras/preprocess.py:947-1094.  No CPU compute path exists here.
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 
 #include "host_common.cuh"
 #include "eig_kernels.cuh"
@@ -60,8 +62,8 @@ int launch_project(cudaStream_t s, const double* X, long ldx, int n, int c, cons
   const int n_pad = round_up(n, 128);
   const int row_tiles = n_pad / 128;
   const int k_stages = (int)(c_pad / PROJ_BK);
-  int nz = (2 * 148 + row_tiles - 1) / row_tiles;
-  if (nz > (k_stages + 7) / 8) nz = (k_stages + 7) / 8;
+  int nz = (8 * 148 + row_tiles - 1) / row_tiles;  // ~4 waves of 2 CTAs per SM: the tail stays below ~10%
+  if (nz > (k_stages + 31) / 32) nz = (k_stages + 31) / 32;
   if (nz < 1) nz = 1;
   const int per = (k_stages + nz - 1) / nz;
   nz = (k_stages + per - 1) / per;
@@ -75,14 +77,24 @@ int launch_project(cudaStream_t s, const double* X, long ldx, int n, int c, cons
 int project_splits_max(int n, long c_pad) {
   const int row_tiles = round_up(n, 128) / 128;
   const int k_stages = (int)(c_pad / PROJ_BK);
-  int nz = (2 * 148 + row_tiles - 1) / row_tiles;
-  if (nz > (k_stages + 7) / 8) nz = (k_stages + 7) / 8;
+  int nz = (8 * 148 + row_tiles - 1) / row_tiles;
+  if (nz > (k_stages + 31) / 32) nz = (k_stages + 31) / 32;
   return nz < 1 ? 1 : nz;
 }
 
 }  // namespace
 
+// Workspace pool: cudaMalloc / cudaFree cost hundreds of milliseconds next to multi-GB live allocations (measured: 293 ms
+// for the 160 MB of the subspace iteration at config-3 sizes), so workspaces are recycled across calls and only returned
+// to the driver by gpras_pre_trim / gpras_pre_destroy.
+struct PoolBlock {
+  void* ptr;
+  size_t bytes;
+  bool in_use;
+};
+
 struct gpras_pre {
+  std::vector<PoolBlock> pool;
   int device = 0, c = 0, hp = 0;
   long c_pad = 0;
   double wet_threshold = 0.03;
@@ -99,6 +111,51 @@ struct gpras_pre {
 
 namespace {
 
+int pool_take(gpras_pre* h, void** out, size_t bytes) {
+  if (bytes == 0) bytes = 8;
+  int best = -1;
+  for (int i = 0; i < (int)h->pool.size(); i++) {
+    const PoolBlock& b = h->pool[i];
+    if (!b.in_use && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096 && (best < 0 || b.bytes < h->pool[best].bytes)) best = i;
+  }
+  if (best >= 0) {
+    h->pool[best].in_use = true;
+    *out = h->pool[best].ptr;
+    return 0;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    // give unused blocks back to the driver and retry once
+    for (auto it = h->pool.begin(); it != h->pool.end();)
+      if (!it->in_use) {
+        cudaFree(it->ptr);
+        it = h->pool.erase(it);
+      } else {
+        ++it;
+      }
+    cudaGetLastError();
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(GPRAS_E_NOMEM, "cudaMalloc (workspace)", e);
+  }
+  h->pool.push_back({p, bytes, true});
+  *out = p;
+  return 0;
+}
+
+int palloc(gpras_pre* h, double** out, size_t count) { return pool_take(h, (void**)out, count * sizeof(double)); }
+
+void pfree(gpras_pre* h, void* p) {
+  if (!p) return;
+  for (auto& b : h->pool)
+    if (b.ptr == p) b.in_use = false;
+}
+
+void pool_release(gpras_pre* h) {
+  for (auto& b : h->pool) cudaFree(b.ptr);
+  h->pool.clear();
+}
+
 int pn_of(int p) { return p <= 8 ? 8 : (p <= 16 ? 16 : (p <= 32 ? 32 : 64)); }
 
 // Device copy of a (n x c) matrix with a 16-byte aligned pitch of c_pad columns; returns the input itself when it already
@@ -110,7 +167,7 @@ int stage_matrix(gpras_pre* h, const double* x, long ldx, int n, int on_device, 
     return 0;
   }
   int r;
-  if ((r = dalloc(owned, (size_t)n * h->c_pad))) return r;
+  if ((r = palloc(h, owned, (size_t)n * h->c_pad))) return r;
   CU(cudaMemcpy2DAsync(*owned, sizeof(double) * h->c_pad, x, sizeof(double) * ldx, sizeof(double) * h->c, n,
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
   *xd = *owned, *ldd = h->c_pad;
@@ -123,7 +180,7 @@ int run_project(gpras_pre* h, const double* xd, long ldd, int n, int pn, int p, 
   const int n_pad = round_up(n, 128);
   double* part = nullptr;
   int r, nz = 0;
-  if ((r = dalloc(&part, (size_t)project_splits_max(n, h->c_pad) * n_pad * pn))) return r;
+  if ((r = palloc(h, &part, (size_t)project_splits_max(n, h->c_pad) * n_pad * pn))) return r;
   const int clamp = h->hp == HP_DEPTH;
   switch (pn) {
     case 8: r = launch_project<8>(s, xd, ldd, n, h->c, h->elev, clamp, h->mean, h->wfull, h->E, h->c_pad, part, &nz); break;
@@ -139,7 +196,7 @@ int run_project(gpras_pre* h, const double* xd, long ldd, int n, int pn, int p, 
     h->launches += 2;
   }
   cudaStreamSynchronize(s);
-  cudaFree(part);
+  pfree(h, part);
   return r;
 }
 
@@ -158,20 +215,31 @@ int build_map(gpras_pre* h) {
 // Rayleigh-Ritz step per iteration.  On return U (n_pad x 128) holds the Ritz vectors, h->h_lambda / h_resid the values.
 int subspace_eig(gpras_pre* h, const double* G, int n, int n_pad, int kconv, double tol, int max_iter, double* U) {
   cudaStream_t s = h->stream;
+  const bool trace = getenv("GPRAS_B200_TRACE") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(s);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[subspace_eig] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+    t_start = now;
+  };
+  stamp("enter");
   const size_t nb = (size_t)n_pad * EIG_B, bb = (size_t)EIG_B * EIG_B;
   double *Q = nullptr, *Y = nullptr, *Z = nullptr, *small = nullptr, *skinny = nullptr, *logdet = nullptr;
   int* info = nullptr;
   int r = 0;
   auto cleanup = [&]() {
     cudaStreamSynchronize(s);
-    cudaFree(Q), cudaFree(Y), cudaFree(Z), cudaFree(small), cudaFree(skinny), cudaFree(logdet), cudaFree(info);
+    pfree(h, Q), pfree(h, Y), pfree(h, Z), pfree(h, small), pfree(h, skinny), pfree(h, logdet), pfree(h, info);
   };
-  if ((r = dalloc(&Q, nb)) || (r = dalloc(&Y, nb)) || (r = dalloc(&Z, nb)) || (r = dalloc(&small, 6 * bb)) ||
-      (r = dalloc(&skinny, (size_t)SKINNY_MAX_SLABS * nb)) || (r = dalloc(&logdet, 1)) ||
-      cudaMalloc((void**)&info, sizeof(int)) != cudaSuccess) {
+  if ((r = palloc(h, &Q, nb)) || (r = palloc(h, &Y, nb)) || (r = palloc(h, &Z, nb)) || (r = palloc(h, &small, 6 * bb)) ||
+      (r = palloc(h, &skinny, (size_t)SKINNY_MAX_SLABS * nb)) || (r = palloc(h, &logdet, 1)) ||
+      (r = pool_take(h, (void**)&info, sizeof(int)))) {
     cleanup();
-    return r ? r : fail(GPRAS_E_NOMEM, "cudaMalloc");
+    return r;
   }
+  stamp("alloc");
   double *H = small, *B = small + bb, *V = small + 2 * bb, *Vs = small + 3 * bb, *L = small + 4 * bb, *W = small + 5 * bb;
   const int mt = n_pad / 128;
   cudaMemsetAsync(W, 0, sizeof(double) * bb, s);  // the leaf never writes above the diagonal
@@ -194,6 +262,7 @@ int subspace_eig(gpras_pre* h, const double* G, int n, int n_pad, int kconv, dou
     cleanup();
     return r;
   }
+  stamp("init+orth");
   bool converged = false;
   h->iters = 0;
   for (int it = 0; it < max_iter && !converged; it++) {
@@ -223,8 +292,10 @@ int subspace_eig(gpras_pre* h, const double* G, int n, int n_pad, int kconv, dou
     for (int j = 0; j < kconv; j++)
       if (!(h->h_resid[j] <= tol)) converged = false;
     if (!converged && (r = orthonormalise(Z, Q))) break;
+    stamp("iteration");
   }
   cleanup();
+  stamp("cleanup");
   if (r) return r;
   return converged ? 0 : 1;
 }
@@ -276,6 +347,7 @@ int gpras_pre_destroy(gpras_pre* h) {
   for (double* b : bufs)
     if (b) cudaFree(b);
   if (h->cls) cudaFree(h->cls);
+  pool_release(h);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -302,7 +374,7 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
   double *owned = nullptr, *part = nullptr, *Xw = nullptr, *G = nullptr, *U = nullptr, *Ft = nullptr, *Zs = nullptr;
   auto cleanup = [&]() {
     cudaStreamSynchronize(s);
-    cudaFree(owned), cudaFree(part), cudaFree(Xw), cudaFree(G), cudaFree(U), cudaFree(Ft), cudaFree(Zs);
+    pfree(h, owned), pfree(h, part), pfree(h, Xw), pfree(h, G), pfree(h, U), pfree(h, Ft), pfree(h, Zs);
   };
 #define PRE_TRY(expr)          \
   do {                         \
@@ -328,7 +400,7 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
     if (splits < 1) splits = 1;
     const int rows_per = (n + splits - 1) / splits;
     splits = (n + rows_per - 1) / rows_per;
-    PRE_TRY(dalloc(&part, (size_t)splits * 3 * c_pad));
+    PRE_TRY(palloc(h, &part, (size_t)splits * 3 * c_pad));
     colstats_kernel<<<dim3(gx, splits), 128, 0, s>>>(xd, ldd, n, c, h->elev, clamp, rows_per, part, c_pad);
     PRE_CU(cudaGetLastError());
     colstats_finish_kernel<<<(unsigned)((c_pad + 255) / 256), 256, 0, s>>>(part, splits, c_pad, c, n, h->hp, h->elev, h->weights_in,
@@ -338,14 +410,14 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
   }
   PRE_CU(cudaEventRecord(h->ev[1], s));
   // ---- 2. centred, weighted samples ----
-  PRE_TRY(dalloc(&Xw, (size_t)n_pad * c_pad));
+  PRE_TRY(palloc(h, &Xw, (size_t)n_pad * c_pad));
   center_weight_kernel<<<dim3((unsigned)((c_pad + 255) / 256), n_pad), 256, 0, s>>>(xd, ldd, n, c, h->elev, clamp, h->mean, h->wfull, Xw,
                                                                                   c_pad);
   PRE_CU(cudaGetLastError());
   h->launches++;
   PRE_CU(cudaEventRecord(h->ev[2], s));
   // ---- 3. Gram matrix G = Xw Xw^T on the DMMA engine (lower tiles), mirrored to full storage ----
-  PRE_TRY(dalloc(&G, (size_t)n_pad * n_pad));
+  PRE_TRY(palloc(h, &G, (size_t)n_pad * n_pad));
   {
     GemmDesc g = make_desc(Xw, c_pad, Xw, c_pad, G, n_pad, n_pad / 128, n_pad / 128, (int)c_pad);
     g.tri = 1;
@@ -356,7 +428,7 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
   }
   PRE_CU(cudaEventRecord(h->ev[3], s));
   // ---- 4. leading eigenpairs ----
-  PRE_TRY(dalloc(&U, (size_t)n_pad * EIG_B));
+  PRE_TRY(palloc(h, &U, (size_t)n_pad * EIG_B));
   const int keep = modes > 0 ? modes : PRE_MAX_MODES;
   int kconv = keep < n - 1 ? keep : n - 1;
   if (kconv > c) kconv = c;
@@ -368,7 +440,7 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
   const bool converged = r == 0;
   PRE_CU(cudaEventRecord(h->ev[4], s));
   // ---- 5. EOFs: Ft = Xw^T U (c_pad x 64), scaled by 1 / singular value, sign-normalised ----
-  PRE_TRY(dalloc(&Ft, (size_t)c_pad * EIG_B));
+  PRE_TRY(palloc(h, &Ft, (size_t)c_pad * EIG_B));
   {
     GemmDesc g = make_desc(Xw, c_pad, U, EIG_B, Ft, EIG_B, (int)(c_pad / 128), PRE_MAX_MODES / 32, n_pad);
     PRE_TRY(launch_gemm(s, true, true, g, 1, &h->launches, SHAPE_N));
@@ -378,7 +450,7 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
   }
   PRE_CU(cudaEventRecord(h->ev[5], s));
   // ---- 6. raw scores of the training samples -> mean / population std per mode ----
-  PRE_TRY(dalloc(&Zs, (size_t)n * PRE_MAX_MODES));
+  PRE_TRY(palloc(h, &Zs, (size_t)n * PRE_MAX_MODES));
   PRE_TRY(run_project(h, xd, ldd, n, PRE_MAX_MODES, PRE_MAX_MODES, 0, Zs, PRE_MAX_MODES));
   score_stats_kernel<<<PRE_MAX_MODES, 256, 0, s>>>(Zs, PRE_MAX_MODES, n, h->x_mean, h->x_std);
   PRE_CU(cudaGetLastError());
@@ -477,6 +549,20 @@ int gpras_pre_get(gpras_pre* h, int which, double* out) {
   return fail(GPRAS_E_ARG, "which out of range");
 }
 
+int gpras_pre_trim(gpras_pre* h) {
+  if (!h) return fail(GPRAS_E_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  CU(cudaStreamSynchronize(h->stream));
+  for (auto it = h->pool.begin(); it != h->pool.end();)
+    if (!it->in_use) {
+      cudaFree(it->ptr);
+      it = h->pool.erase(it);
+    } else {
+      ++it;
+    }
+  return 0;
+}
+
 int gpras_pre_modes(gpras_pre* h) { return h ? h->p : 0; }
 int gpras_pre_eigen_count(gpras_pre* h) { return h ? h->n_eig : 0; }
 int gpras_pre_iterations(gpras_pre* h) { return h ? h->iters : 0; }
@@ -501,8 +587,8 @@ int gpras_pre_transform(gpras_pre* h, const double* x, long ldx, int n, int on_d
   if ((r = stage_matrix(h, x, ldx, n, on_device, &xd, &ldd, &owned))) return r;
   double* zout = z;
   if (!on_device) {
-    if ((r = dalloc(&zd, (size_t)n * h->p))) {
-      cudaFree(owned);
+    if ((r = palloc(h, &zd, (size_t)n * h->p))) {
+      pfree(h, owned);
       return r;
     }
     zout = zd;
@@ -511,7 +597,7 @@ int gpras_pre_transform(gpras_pre* h, const double* x, long ldx, int n, int on_d
   if (!r && !on_device && cudaMemcpy(z, zd, sizeof(double) * (size_t)n * h->p, cudaMemcpyDeviceToHost) != cudaSuccess)
     r = fail(GPRAS_E_CUDA, "copy of the scores", cudaGetLastError());
   cudaStreamSynchronize(s);
-  cudaFree(owned), cudaFree(zd);
+  pfree(h, owned), pfree(h, zd);
   return r;
 }
 
@@ -528,10 +614,10 @@ int gpras_pre_reverse(gpras_pre* h, const double* mean, const double* var, int t
   double *M = nullptr, *V = nullptr, *om = nullptr, *ov = nullptr;
   auto cleanup = [&]() {
     cudaStreamSynchronize(s);
-    cudaFree(M), cudaFree(V), cudaFree(om), cudaFree(ov);
+    pfree(h, M), pfree(h, V), pfree(h, om), pfree(h, ov);
   };
-  if ((r = dalloc(&M, (size_t)PRE_REV_TB * pk)) || (r = dalloc(&om, (size_t)PRE_REV_TB * c_pad)) ||
-      (var && ((r = dalloc(&V, (size_t)PRE_REV_TB * pk)) || (r = dalloc(&ov, (size_t)PRE_REV_TB * c_pad))))) {
+  if ((r = palloc(h, &M, (size_t)PRE_REV_TB * pk)) || (r = palloc(h, &om, (size_t)PRE_REV_TB * c_pad)) ||
+      (var && ((r = palloc(h, &V, (size_t)PRE_REV_TB * pk)) || (r = palloc(h, &ov, (size_t)PRE_REV_TB * c_pad))))) {
     cleanup();
     return r;
   }

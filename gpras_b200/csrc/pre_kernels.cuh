@@ -93,12 +93,12 @@ static __global__ void center_weight_kernel(const double* __restrict__ X, long l
 
 // ---- projection -------------------------------------------------------------------------------
 // part[z][i][p] = sum_{c in chunk z} (val(x[i][c]) - mean[c]) * wfull[c] * E[p][c]
-// CTA: 128 rows x PN modes, 8 warps of 16 rows; BK = 32 cells per stage, 3-stage cp.async ring carrying the x tile,
-// the E tile and the mean / weight / elevation slices.  X rows must be 16-byte aligned with c_pad readable columns
+// CTA: 128 rows x PN modes, 8 warps of 16 rows; BK = 16 cells per stage, 4-stage cp.async ring carrying the x tile,
+// the E tile and the mean / weight / elevation slices (24 KB per stage at PN = 32, so two CTAs share an SM).  X rows must be 16-byte aligned with c_pad readable columns
 // (the host stages the input into a padded buffer when that does not hold).
 constexpr int PROJ_THREADS = 256;
-constexpr int PROJ_BK = 32;
-constexpr int PROJ_STAGES = 3;
+constexpr int PROJ_BK = 16;
+constexpr int PROJ_STAGES = 4;
 
 template <int PN>
 struct ProjCfg {
@@ -109,7 +109,7 @@ struct ProjCfg {
 };
 
 template <int PN>
-__global__ void __launch_bounds__(PROJ_THREADS, 1)
+__global__ void __launch_bounds__(PROJ_THREADS, PN <= 32 ? 2 : 1)
 project_kernel(const double* __restrict__ X, long ldx, int n, int c, const double* __restrict__ elev, int clamp,
                const double* __restrict__ mean, const double* __restrict__ wfull, const double* __restrict__ E, long lde,
                int k_stages_total, int stages_per_split, double* __restrict__ part, long n_pad) {

@@ -122,7 +122,7 @@ class MetricsAccumulator:
         t = self.timesteps()
         scal = np.zeros(_SCALARS)
         cells = np.zeros((5, self.c))
-        rows = np.zeros((5, t))
+        rows = np.zeros((3, t))
         check(self.lib.gpras_metrics_finalize(self._h, float(depth_threshold), ptr(scal), ptr(cells), ptr(rows)))
         return _summary(scal, cells, rows, t, self.c)
 

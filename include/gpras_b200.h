@@ -127,7 +127,7 @@ int gpras_gp_predict_metrics(gpras_gp* h, gpras_metrics* m, const double* xs, in
                              long ldx, int truth_on_device, double* mode_mean, double* mode_var);
 /* scalars: 15 doubles = [sum e, sum e^2, sum conf, sum |e|, count(|e|<=v_tol), sum d, sum d^2, sum xm, sum (xm-mean xm)^2,
  * hits, misses, false alarms at depth_threshold, the same three at threshold 0] with d = max_t x - max_t y, xm = max_t x;
- * cells (5 x c) and rows (5 x timesteps) receive the raw per-cell / per-timestep reductions (host, may be NULL). */
+ * cells (5 x c) and rows (3 x timesteps) receive the raw per-cell / per-timestep reductions (host, may be NULL). */
 int gpras_metrics_finalize(gpras_metrics* m, double depth_threshold, double* scalars, double* cells, double* rows);
 long gpras_metrics_timesteps(gpras_metrics* m);
 int gpras_metrics_last_launches(gpras_metrics* m);
@@ -169,6 +169,8 @@ int gpras_pre_transform(gpras_pre* h, const double* x, long ldx, int n, int on_d
 /* PreProcessor.reverse_transform (preprocess.py:1052-1084): mean (t x p) [and var (t x p), may be NULL] -> cell space
  * (t x c) host arrays; depth semantics follow the handle's hydraulic parameter. */
 int gpras_pre_reverse(gpras_pre* h, const double* mean, const double* var, int t, double* cell_mean, double* cell_var);
+/* Workspaces (staged input, centred samples, Gram matrix ...) are recycled across calls; trim returns them to the driver. */
+int gpras_pre_trim(gpras_pre* h);
 int gpras_pre_last_launches(gpras_pre* h);
 /* CUDA-event milliseconds of the last fit: [column stats, centre+weight, Gram, subspace iteration, EOFs, scores, total]. */
 int gpras_pre_last_stage_ms(gpras_pre* h, double* ms7);
