@@ -292,6 +292,34 @@ def run_ours(args) -> None:
             "events_per_s": t_events / (float(pms.item()) * 1e-3), "cells": c, "events_per_rank": int(xt.shape[0]),
             "output": "mean+variance per cell written to a device ring buffer (T*C*16 B cannot be kept)",
         }
+        # the same sweep with the consumer fused: depth conversion + every metric of gpras/metrics.py accumulated on the fly
+        # against a resident truth block, the T x C prediction never written
+        from gpras_b200.metrics import MetricsAccumulator
+
+        acc = MetricsAccumulator(c, reps * int(xt.shape[0]) + 1)
+        acc.set_elevations(cm.elevations, cm.elevations)
+        gtr = torch.Generator(device="cuda").manual_seed(7 + rank)
+        truth = torch.rand(int(xt.shape[0]), c, dtype=torch.float64, device="cuda", generator=gtr) * 4 + 3
+        acc.reset(0.0)
+        acc.predict_update(gp, xt, truth)
+        barrier()
+        p0.record(stream)
+        acc.reset(0.0)
+        for _ in range(reps):
+            acc.predict_update(gp, xt, truth)
+        summary = acc.finalize(0.5)
+        p1.record(stream)
+        barrier()
+        fms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+        predict["fused_metrics"] = {
+            "value": t_events * c / (float(fms.item()) * 1e-3), "unit": "cell-depths/s",
+            "what": "predict -> cells -> depth -> all gpras/metrics.py reductions vs a resident truth block; nothing written per cell-depth",
+            "rmse_aoi_toi": summary["rmse_aoi_toi"],
+        }
+        acc.close()
+        del truth
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -11,6 +11,7 @@
 namespace {
 
 constexpr int PRE_MAX_MODES = 64;
+constexpr int PRE_GRAM_MAX_N = 2048;  // above this many (padded) samples the PCA runs Gram-free
 constexpr int PRE_REV_TB = 1024;  // rows per reverse-transform block
 
 // wet cells: Ef[p][c] = x_std[p] E[p][c] / w[c], Ef2 = Ef^2, bias[c] = sum_p x_mean[p] E[p][c] / w[c] + mean[c];
@@ -211,9 +212,13 @@ int build_map(gpras_pre* h) {
   return 0;
 }
 
-// Leading eigenpairs of the symmetric PSD matrix G (n_pad x n_pad, full storage) by blocked subspace iteration with a
-// Rayleigh-Ritz step per iteration.  On return U (n_pad x 128) holds the Ritz vectors, h->h_lambda / h_resid the values.
-int subspace_eig(gpras_pre* h, const double* G, int n, int n_pad, int kconv, double tol, int max_iter, double* U) {
+// Leading eigenpairs of the symmetric PSD matrix G = Xw Xw^T by blocked subspace iteration with a Rayleigh-Ritz step per
+// iteration.  G != NULL: explicit Gram matrix (n_pad x n_pad, full storage); G == NULL: operator form, Y = Xw (Xw^T Q) as
+// two skinny products per iteration -- 4 n c 128 flop instead of the n^2 c of forming G, which wins once n exceeds a few
+// thousand samples, and never squares the data in memory.  On return U (n_pad x 128) holds the Ritz vectors,
+// h->h_lambda / h_resid the values.
+int subspace_eig(gpras_pre* h, const double* G, const double* Xw, long c_pad, int n, int n_pad, int kconv, double tol,
+                 int max_iter, double* U) {
   cudaStream_t s = h->stream;
   const bool trace = getenv("GPRAS_B200_TRACE") != nullptr;
   auto t_start = std::chrono::steady_clock::now();
@@ -226,22 +231,30 @@ int subspace_eig(gpras_pre* h, const double* G, int n, int n_pad, int kconv, dou
   };
   stamp("enter");
   const size_t nb = (size_t)n_pad * EIG_B, bb = (size_t)EIG_B * EIG_B;
-  double *Q = nullptr, *Y = nullptr, *Z = nullptr, *small = nullptr, *skinny = nullptr, *logdet = nullptr;
+  double *Q = nullptr, *Y = nullptr, *Z = nullptr, *small = nullptr, *skinny = nullptr, *logdet = nullptr, *Tc = nullptr;
   int* info = nullptr;
   int r = 0;
+  const int mt = n_pad / 128;
+  // operator form: split of the long k = c_pad range of Y = Xw T into nz chunks (mt * nz CTAs ~ 3 waves)
+  int nz_op = (3 * 148 + mt - 1) / mt;
+  if (nz_op > (int)(c_pad / 512)) nz_op = (int)(c_pad / 512);
+  if (nz_op < 1) nz_op = 1;
+  const int ks_op = round_up((int)((c_pad + nz_op - 1) / nz_op), 128);
+  nz_op = (int)((c_pad + ks_op - 1) / ks_op);
+  const int n_slabs = G ? SKINNY_MAX_SLABS : (nz_op > SKINNY_MAX_SLABS ? nz_op : SKINNY_MAX_SLABS);
   auto cleanup = [&]() {
     cudaStreamSynchronize(s);
-    pfree(h, Q), pfree(h, Y), pfree(h, Z), pfree(h, small), pfree(h, skinny), pfree(h, logdet), pfree(h, info);
+    pfree(h, Q), pfree(h, Y), pfree(h, Z), pfree(h, small), pfree(h, skinny), pfree(h, logdet), pfree(h, info), pfree(h, Tc);
   };
   if ((r = palloc(h, &Q, nb)) || (r = palloc(h, &Y, nb)) || (r = palloc(h, &Z, nb)) || (r = palloc(h, &small, 6 * bb)) ||
-      (r = palloc(h, &skinny, (size_t)SKINNY_MAX_SLABS * nb)) || (r = palloc(h, &logdet, 1)) ||
+      (r = palloc(h, &skinny, (size_t)n_slabs * nb)) || (r = palloc(h, &logdet, 1)) ||
+      (!G && (r = palloc(h, &Tc, (size_t)c_pad * EIG_B))) ||
       (r = pool_take(h, (void**)&info, sizeof(int)))) {
     cleanup();
     return r;
   }
   stamp("alloc");
   double *H = small, *B = small + bb, *V = small + 2 * bb, *Vs = small + 3 * bb, *L = small + 4 * bb, *W = small + 5 * bb;
-  const int mt = n_pad / 128;
   cudaMemsetAsync(W, 0, sizeof(double) * bb, s);  // the leaf never writes above the diagonal
   auto orthonormalise = [&](const double* Zin, double* Qout) -> int {
     // B = Zin^T Zin (split-k), guarded, factored by the Cholesky leaf; Qout = Zin W^T with W = L^-1
@@ -267,9 +280,18 @@ int subspace_eig(gpras_pre* h, const double* G, int n, int n_pad, int kconv, dou
   h->iters = 0;
   for (int it = 0; it < max_iter && !converged; it++) {
     h->iters = it + 1;
-    // Y = G Q
-    GemmDesc gy = make_desc(G, n_pad, Q, EIG_B, Y, EIG_B, mt, EIG_B / 32, n_pad);
-    if ((r = launch_skinny(s, false, gy, skinny, n_pad, &h->launches))) break;
+    if (G) {  // Y = G Q
+      GemmDesc gy = make_desc(G, n_pad, Q, EIG_B, Y, EIG_B, mt, EIG_B / 32, n_pad);
+      if ((r = launch_skinny(s, false, gy, skinny, n_pad, &h->launches))) break;
+    } else {  // T = Xw^T Q (c_pad x 128), Y = Xw T (split over the cells, fixed-order reduction)
+      GemmDesc gt = make_desc(Xw, c_pad, Q, EIG_B, Tc, EIG_B, (int)(c_pad / 128), 1, n_pad);
+      if ((r = launch_gemm(s, true, true, gt, 1, &h->launches))) break;
+      GemmDesc gy = make_desc(Xw, c_pad, Tc, EIG_B, skinny, EIG_B, mt, 1, (int)c_pad);
+      gy.k_split = ks_op, gy.splitC = (long)nb;
+      if ((r = launch_gemm(s, false, true, gy, 1, &h->launches, SHAPE_L, nz_op))) break;
+      splitk_reduce_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(skinny, (long)nb, nz_op, (long)nb, Y);
+      h->launches++;
+    }
     // H = Q^T Y
     GemmDesc gh = make_desc(Q, EIG_B, Y, EIG_B, H, EIG_B, 1, EIG_B / 32, n_pad);
     if ((r = launch_skinny(s, true, gh, skinny, EIG_B, &h->launches))) break;
@@ -416,9 +438,11 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
   PRE_CU(cudaGetLastError());
   h->launches++;
   PRE_CU(cudaEventRecord(h->ev[2], s));
-  // ---- 3. Gram matrix G = Xw Xw^T on the DMMA engine (lower tiles), mirrored to full storage ----
-  PRE_TRY(palloc(h, &G, (size_t)n_pad * n_pad));
-  {
+  // ---- 3. Gram matrix G = Xw Xw^T on the DMMA engine (lower tiles), mirrored to full storage -- only while forming it
+  //         is cheaper than applying Xw and Xw^T once per subspace iteration (see subspace_eig) ----
+  const bool use_gram = n_pad <= PRE_GRAM_MAX_N;
+  if (use_gram) {
+    PRE_TRY(palloc(h, &G, (size_t)n_pad * n_pad));
     GemmDesc g = make_desc(Xw, c_pad, Xw, c_pad, G, n_pad, n_pad / 128, n_pad / 128, (int)c_pad);
     g.tri = 1;
     PRE_TRY(launch_gemm(s, false, false, g, 1, &h->launches));
@@ -432,7 +456,7 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
   const int keep = modes > 0 ? modes : PRE_MAX_MODES;
   int kconv = keep < n - 1 ? keep : n - 1;
   if (kconv > c) kconv = c;
-  r = subspace_eig(h, G, n, n_pad, kconv, tol, max_iter, U);
+  r = subspace_eig(h, use_gram ? G : nullptr, Xw, c_pad, n, n_pad, kconv, tol, max_iter, U);
   if (r < 0) {
     cleanup();
     return r;

@@ -3,7 +3,10 @@
 The path shards without any data-path collective: independent optimiser restarts /
 hyperparameter candidates go round-robin to ranks, test-event batches go to ranks in contiguous blocks, and
 the only exchanges are an all-gather of per-restart ``[loss, theta]`` rows and of mode-space prediction
-shards.  The reference itself is single-process (``gpras/gpr.py:273-274,336-339`` loop sequentially).
+shards.  Two more axes of BASELINE.json's north_star are covered here: target-column blocks (``shard_columns`` /
+``lml_grad_column_sharded``: with one theta shared by all columns the log marginal likelihood and its gradient are sums
+over columns, so ranks holding disjoint column blocks exchange ``3 + D`` doubles per evaluation) and events for the
+streaming metrics (``metrics_sharded``: whole events go round-robin to ranks, the per-event scalar rows are gathered).  The reference itself is single-process (``gpras/gpr.py:273-274,336-339`` loop sequentially).
 On CPU test runs the same code runs over ``gloo``.
 """
 
@@ -95,3 +98,50 @@ def predict_sharded(gpras, x: np.ndarray):
     p = mean.shape[1]
     both = all_gather_rows(np.concatenate([mean, var], axis=1), 2 * p)
     return both[:, :p], both[:, p:]
+
+
+def shard_columns(n_cols: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [start, stop) block of target columns for this rank (BASELINE config 4: targets column-sharded)."""
+    return shard_rows(n_cols, rank, world)
+
+
+def all_reduce_sum(vec: np.ndarray) -> np.ndarray:
+    """Sum a small float64 vector over ranks (identity when not distributed)."""
+    rank, world, dev = dist_info()
+    vec = np.asarray(vec, np.float64)
+    if world == 1:
+        return vec
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(vec.copy()).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def lml_grad_column_sharded(evaluate, theta, want_grad: bool = True):
+    """Log marginal likelihood and gradient of a shared-theta model whose target columns are sharded over ranks.
+
+    ``evaluate(theta, want_grad) -> (lml, grad)`` is this rank's evaluation on ITS column block (an ``ExactGP`` bound to
+    ``y[:, shard_columns(P, rank, world)]``).  With one theta for all columns
+    ``LML = sum_p [-1/2 y_p^T K^-1 y_p - 1/2 log|K| - N/2 log 2 pi]`` and its gradient are sums over columns, so the
+    exchange is one all-reduce of ``1 + (2 + D)`` doubles.  Every rank factorises K itself: at P << N that is redundant
+    work (replicas), at P >> N (raw-cell targets) the 3 N^2 P term that dominates is what gets divided."""
+    lml, grad = evaluate(np.asarray(theta, np.float64), want_grad)
+    packed = np.concatenate([[lml], grad if want_grad else []])
+    total = all_reduce_sum(packed)
+    return float(total[0]), (total[1:] if want_grad else None)
+
+
+def metrics_sharded(event_ids, summarise_event, keys) -> np.ndarray:
+    """Scalar metrics of many events, whole events sharded round-robin over ranks.
+
+    ``summarise_event(event_id) -> dict`` runs on this rank's GPU (``gpras_b200.metrics.summarise`` or a
+    ``MetricsAccumulator``); returns the gathered table with rows ``[event index, *keys]`` in event order on every rank."""
+    rank, world, _ = dist_info()
+    rows = []
+    for i in shard_indices(len(event_ids), rank, world):
+        s = summarise_event(event_ids[i])
+        rows.append([float(i)] + [float(s[k]) for k in keys])
+    table = all_gather_rows(np.array(rows).reshape(-1, 1 + len(keys)), 1 + len(keys))
+    return table[np.argsort(table[:, 0], kind="stable")]

@@ -41,6 +41,28 @@ def _worker(rank, world, port, out_dir):
     table = parallel.run_restarts(m, gpr.OPTIMIZERS["L-BFGS-B"], starts, dict(max_iter=30))
     np.save(os.path.join(out_dir, f"table{rank}.npy"), table)
     np.save(os.path.join(out_dir, f"theta{rank}.npy"), m.theta())
+
+    # target columns sharded over ranks: LML and gradient are sums over column blocks (oracle as the local evaluator)
+    from oracle import metrics as om
+    from oracle.exact_gp import Theta, lml_and_grad
+
+    d5 = make_gp_data(50, 3, 5, seed=8)
+    lo, hi = parallel.shard_columns(5, rank, world)
+    th = np.array([1.3, 0.07, 1.5, 2.0, 0.8])
+
+    def local_eval(theta, want_grad):
+        lml, gv, gn, gl = lml_and_grad("Matern52", d5.x, d5.y[:, lo:hi], Theta(theta[0], theta[1], theta[2:]), want_grad=want_grad)
+        return lml, np.concatenate([[gv, gn], gl])
+
+    lml, grad = parallel.lml_grad_column_sharded(local_eval, th)
+    np.save(os.path.join(out_dir, f"colshard{rank}.npy"), np.concatenate([[lml], grad]))
+
+    # events sharded over ranks for the metrics
+    rng = np.random.default_rng(3)
+    events = [(rng.random((6, 9)), rng.random((6, 9)), rng.random((6, 9))) for _ in range(5)]
+    keys = ["rmse_aoi_toi", "mae_aoi_toi", "conf_aoi_toi", "err_aoi_mts"]
+    tab = parallel.metrics_sharded(list(range(5)), lambda i: om.summarise(*events[i]), keys)
+    np.save(os.path.join(out_dir, f"metrics{rank}.npy"), tab)
     dist.destroy_process_group()
 
 
@@ -63,3 +85,24 @@ def test_restart_sharding_world2_matches_serial(tmp_path):
     np.testing.assert_allclose(ts, t0, rtol=1e-12)
     best = int(np.argmin(ts[:, 1]))
     np.testing.assert_allclose(m.theta()[:3], ts[best, 2:5], rtol=1e-12)
+
+
+def test_column_and_event_sharding_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    from gpras_b200.synth import make_gp_data
+    from oracle import metrics as om
+    from oracle.exact_gp import Theta, lml_and_grad
+
+    c0, c1 = np.load(tmp_path / "colshard0.npy"), np.load(tmp_path / "colshard1.npy")
+    np.testing.assert_array_equal(c0, c1)
+    d5 = make_gp_data(50, 3, 5, seed=8)
+    lml, gv, gn, gl = lml_and_grad("Matern52", d5.x, d5.y, Theta(1.3, 0.07, np.array([1.5, 2.0, 0.8])))
+    np.testing.assert_allclose(c0, np.concatenate([[lml, gv, gn], gl]), rtol=1e-11)
+    m0, m1 = np.load(tmp_path / "metrics0.npy"), np.load(tmp_path / "metrics1.npy")
+    np.testing.assert_array_equal(m0, m1)
+    rng = np.random.default_rng(3)
+    events = [(rng.random((6, 9)), rng.random((6, 9)), rng.random((6, 9))) for _ in range(5)]
+    for i, (x, y, cf) in enumerate(events):
+        s = om.summarise(x, y, cf)
+        np.testing.assert_allclose(m0[i], [i, s["rmse_aoi_toi"], s["mae_aoi_toi"], s["conf_aoi_toi"], s["err_aoi_mts"]], rtol=1e-13)

@@ -82,9 +82,10 @@ def test_fit_then_transform_device_tensor(cuda, pre_golden):
     pp.close()
 
 
-@pytest.mark.parametrize("n,cells,k,modes,hp", [(700, 3000, 6, 6, "wse"), (1500, 1100, 5, 5, "depth"), (300, 5000, 8, None, "wse")])
+@pytest.mark.parametrize("n,cells,k,modes,hp", [(700, 3000, 6, 6, "wse"), (1500, 1100, 5, 5, "depth"), (300, 5000, 8, None, "wse"), (2500, 1500, 6, 6, "wse")])
 def test_fit_subspace_iteration_against_oracle(cuda, n, cells, k, modes, hp):
-    """More samples than one 128-block: the subspace iteration has to converge (not just diagonalise the whole Gram)."""
+    """More samples than one 128-block: the subspace iteration has to converge (not just diagonalise the whole Gram).
+    The last case has more than 2048 samples and takes the Gram-free (operator) form of the iteration."""
     import sys
     from pathlib import Path
 
