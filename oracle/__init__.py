@@ -5,7 +5,11 @@ permitted users are ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``, and there only as
 the checker or the timed CPU baseline -- never as a compute fallback.
 
-PARITY UNPINNED BY THE REFERENCE: ``/root/reference`` ships no tests, golden
+PARITY PINNED TO THE REFERENCE for ``cells.py``, ``preprocess.py`` and ``metrics.py``: their subjects
+(``gpras.preprocess.PreProcessor`` and ``gpras/metrics.py``) are NumPy / scikit-learn code that runs offline, and
+``tests/golden/make_golden_reference.py`` committed the reference's own outputs as golden vectors.
+
+PARITY UNPINNED BY THE REFERENCE for the GP core: ``/root/reference`` ships no tests, golden
 vectors or expected outputs for ``gpras/gpr.py`` and its arithmetic lives in the
 un-vendored, un-pinned third-party packages ``gpflow`` / ``tensorflow`` /
 ``tensorflow_probability`` (``pyproject.toml:16-23``), none of which can be
