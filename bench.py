@@ -237,6 +237,12 @@ def run_ours(args) -> None:
     ms_total = float(ms.item())
     value = world * K / (ms_total * 1e-3)
 
+    # ---- the timed results must not depend on what else was in flight: recompute two of them alone ----
+    verified = True
+    for i in (0, K - 1):
+        lml1, g1 = gp.lml_grad(thetas[W + i])
+        verified = verified and lml1 == results[i, 0] and bool(np.array_equal(g1, results[i, 1:]))
+
     # ---- stage timing for the roofline (separate pass; event records perturb nothing measurable) --
     gp.set_stage_timing(True)
     stage = []
@@ -337,6 +343,7 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_eval * K,
+            "verified": {"concurrent_equals_serial_bitwise": verified},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_DGEMM_TFLOPS, "traffic": None, "kernel": "gemm_tile_kernel (DMMA engine) + leaf, dense stages of one eval",
                          "flops_per_eval": f_eval(n, p), "dense_ms_per_eval": dense_ms, "peak_source": FP64_PEAK_SOURCE,

@@ -126,6 +126,13 @@ __device__ __forceinline__ void leaf_factor_panel(double* S, double* dvec, int j
     for (int c = 0; c <= rr; c++) D[rr][c] = S[(j0 + rr) * LEAF_LD + j0 + c];
 #pragma unroll
   for (int c = 0; c < 8; c++) v[c] = live ? S[r * LEAF_LD + j0 + c] : 0.0;
+  // Rows j0 .. j0+7 are the diagonal tile every lane has just read AND the panel rows warp 0 writes back below: the
+  // participating warps meet on a named barrier first, or a warp that was held up (the SM is shared with other CTAs
+  // when several evaluations are in flight) would read an already factored tile.
+  {
+    const int nw = (LEAF_N - j0 + 31) / 32;  // warps that own rows of this panel (all of them reach this point)
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * nw) : "memory");
+  }
 #pragma unroll
   for (int c = 0; c < 8; c++) {
     double dpiv = D[c][c];

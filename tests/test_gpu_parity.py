@@ -409,3 +409,32 @@ def test_fit_n_jobs_matches_sequential(cuda):
         mean, var = g.predict(data.x_test)
         assert np.all(np.isfinite(mean)) and np.all(var > 0)
     np.testing.assert_array_equal(res[0], res[1])  # deterministic kernels: thread scheduling cannot change results
+
+
+@pytest.mark.parametrize("n,handles", [(1024, 32), (2048, 16)])
+def test_concurrent_handles_are_bitwise_identical(cuda, n, handles):
+    """Many evaluations in flight on one GPU (independent handles / streams, the way bench.py and fit(n_jobs) run them)
+    share SMs, which changes warp timing inside every CTA: results must not depend on it.  (Regression test: the
+    Cholesky leaf once let a delayed warp read a diagonal tile that warp 0 had already factored.)"""
+    from gpras_b200.engine import ExactGP
+    from gpras_b200.synth import fixed_theta, make_gp_data
+
+    d = p = 16
+    data = make_gp_data(n, d, p, 0, seed=0)
+    v, s, ls = fixed_theta(d, True)
+    gps = []
+    for _ in range(handles):
+        g = ExactGP("Matern52", n, d, p)
+        g.set_data(data.x, data.y)
+        gps.append(g)
+    th = gps[0].theta_vector(v, s, ls)
+    ref_lml, ref_grad = gps[0].lml_grad(th)  # alone on the device
+    for _ in range(6):
+        for g in gps:
+            g.enqueue(th)
+        for g in gps:
+            lml, grad = g.fetch()
+            assert lml == ref_lml
+            np.testing.assert_array_equal(grad, ref_grad)
+    for g in gps:
+        g.close()
