@@ -162,12 +162,32 @@ class _DeviceSlot:
             st["owner"] = model
         return st["gp"]
 
+    def pool(self, model: "ExactModel", count: int) -> list:
+        """``count`` handles bound to the model's data (the calling thread's own handle first): independent evaluations
+        enqueued on them run concurrently on the GPU, which is what fills the machine at small N (measured at N = 256:
+        3.7e3 evals/s with one evaluation in flight, 7.3e4 with 32)."""
+        first = self.acquire(model)
+        st = self._per_thread[threading.get_ident()]
+        extra = st.setdefault("extra", [])
+        if st.get("extra_key") != (st["key"], id(model)):
+            for g in extra:
+                g.close()
+            extra.clear()
+            st["extra_key"] = (st["key"], id(model))
+        while len(extra) < count - 1:
+            g = ExactGP(model.kernel.name, model.x.shape[0], model.x.shape[1], model.y.shape[1], device=model.device)
+            g.set_data(model.x, model.y)
+            extra.append(g)
+        return [first] + extra[: count - 1]
+
     def release_other_threads(self) -> None:
         me = threading.get_ident()
         for tid in [t for t in self._per_thread if t != me]:
             st = self._per_thread.pop(tid)
             if st["gp"] is not None:
                 st["gp"].close()
+            for g in st.get("extra", []):
+                g.close()
 
 
 class ExactModel:
@@ -251,6 +271,52 @@ class ExactModel:
                 parts.append(-(dv * p.dvalue_du()))
         grad = np.concatenate(parts) if parts else np.zeros(0)
         return -(lml + self._log_prior()), grad
+
+    def loss_and_grad_many(self, us, want_grad: bool = True):
+        """``loss_and_grad`` at several unconstrained vectors with the device evaluations in flight TOGETHER (independent
+        restarts / candidates are the batch axis of the path).  Returns (losses, grads); the
+        model is left at the last vector.  Each value is bitwise what the one-at-a-time call returns."""
+        us = [np.asarray(u, np.float64) for u in us]
+        if not hasattr(self._slot, "pool"):  # e.g. the oracle-backed test double: one at a time
+            outs = [self.loss_and_grad(u) if want_grad else (self._loss_at(u), None) for u in us]
+            return [o[0] for o in outs], [o[1] for o in outs]
+        n = self.x.shape[0]
+        width = 32 if n <= 512 else (16 if n <= 2048 else (4 if n <= 4096 else 2))
+        gps = self._slot.pool(self, min(width, len(us)))
+        losses, grads = [None] * len(us), [None] * len(us)
+        for lo in range(0, len(us), len(gps)):
+            chunk = list(range(lo, min(lo + len(gps), len(us))))
+            host = []
+            for k, i in enumerate(chunk):
+                self.set_u(us[i])
+                gps[k].enqueue(self.theta(), want_grad)
+                host.append((self._log_prior(), [(p, _softplus(p.unconstrained) + p.lower, p.dlog_prior_dvalue(), p.dvalue_du())
+                                                 for p in self.parameters]))
+            for k, i in enumerate(chunk):
+                try:
+                    lml, glog = gps[k].fetch()
+                except Exception:
+                    for k2 in range(k + 1, len(chunk)):  # leave no evaluation pending on the other handles
+                        try:
+                            gps[k2].fetch()
+                        except Exception:
+                            pass
+                    raise
+                self.n_evals += 1
+                log_prior, per_param = host[k]
+                losses[i] = -(lml + log_prior)
+                if want_grad:
+                    g_ls = glog[2:] if self.kernel.lengthscales.size > 1 else np.array([glog[2:].sum()])
+                    parts = []
+                    for (p, v, dlp, dvdu), gl in zip(per_param, (np.array([glog[0]]), np.array([glog[1]]), g_ls)):
+                        if p.trainable:
+                            parts.append(-((gl / v + dlp) * dvdu))
+                    grads[i] = np.concatenate(parts) if parts else np.zeros(0)
+        return losses, grads
+
+    def _loss_at(self, u) -> float:
+        self.set_u(u)
+        return self.training_loss()
 
     # -- prediction --
     def predict_y(self, xs):
@@ -362,19 +428,24 @@ def _optimize_three_stage(model, max_iter: int = 100) -> None:
 
 
 def _optimize_multi_start(model, n_starts: int = 40, iter_initial: int = 20, iter_final: int = 1000, seed=None,
-                          starts=None, pick_best: bool = False) -> None:
+                          starts=None, pick_best: bool = False, lockstep: bool | None = None) -> None:
     """Random restarts with a short Adam run each, then L-BFGS from the selected start (``gpr.py:73-109``).
 
     Faithful to the reference by default: its ``best_loss`` is never assigned (``gpr.py:86,96``), so the LAST
     start is the one that gets polished; ``pick_best=True`` selects the lowest coarse loss instead.  The
     reference's generator is unseeded (``gpr.py:76-77``); ``seed`` / ``starts`` ((R, 3) constrained
-    [variance, lengthscale, noise]) make runs reproducible.
+    [variance, lengthscale, noise]) make runs reproducible.  ``lockstep`` (default: on for models without trainable
+    inducing inputs) advances all starts together so that their device evaluations overlap; the result is identical.
     """
     rng = np.random.default_rng(seed)
     x = model.data[0]
     mins, maxs = x.min(axis=0), x.max(axis=0)
     best_loss, best = None, None
-    for r in range(int(n_starts)):
+    if lockstep is None:
+        lockstep = hasattr(model, "loss_and_grad_many") and not _has_z(model)
+    if lockstep:
+        best = _multi_start_lockstep(model, rng, int(n_starts), int(iter_initial), starts, pick_best)
+    for r in range(0 if lockstep else int(n_starts)):
         if starts is not None:
             var0, ls0, noise0 = starts[r]
         else:
@@ -396,6 +467,56 @@ def _optimize_multi_start(model, n_starts: int = 40, iter_initial: int = 20, ite
     if _has_z(model):
         model.inducing_variable.Z = best[3]
     _optimize_bfgs(model, iter_final)
+
+
+def _multi_start_lockstep(model, rng, n_starts: int, iter_initial: int, starts, pick_best: bool):
+    """The coarse stage of ``_optimize_multi_start`` with all starts advancing one Adam step per round, their objective
+    evaluations in flight together on the GPU.  Starts are independent (no inducing inputs to draw, Adam consumes no random
+    numbers), so every start follows exactly the trajectory of the one-after-the-other loop; only the order of the device
+    work changes.  Returns the selected (variance, lengthscales, noise, Z)."""
+    nls = model.kernel.lengthscales.size
+    u0 = []
+    for r in range(n_starts):
+        if starts is not None:
+            var0, ls0, noise0 = starts[r]
+        else:
+            var0, ls0, noise0 = 10 ** rng.uniform(-1, 1), 10 ** rng.uniform(-1, 1), 10 ** rng.uniform(-3, 0)
+        model.kernel.variance.assign(var0)
+        model.kernel.lengthscales.assign(np.full(nls, ls0) if nls > 1 else ls0)
+        model.likelihood.variance.assign(noise0)
+        u0.append(model.get_u())
+    u = [v.copy() for v in u0]
+    if u and u[0].size:
+        m = [np.zeros_like(v) for v in u]
+        vv = [np.zeros_like(v) for v in u]
+        best, count = [np.inf] * n_starts, [0] * n_starts
+        active = list(range(n_starts))
+        b1, b2, eps, lr, tol, patience = 0.9, 0.999, 1e-7, 0.001, 10e-6, 50
+        for t in range(1, iter_initial + 1):
+            if not active:
+                break
+            losses, grads = model.loss_and_grad_many([u[r] for r in active])
+            still = []
+            for loss, g, r in zip(losses, grads, active):
+                m[r] = b1 * m[r] + (1.0 - b1) * g
+                vv[r] = b2 * vv[r] + (1.0 - b2) * g * g
+                alpha = lr * np.sqrt(1.0 - b2**t) / (1.0 - b1**t)
+                u[r] = u[r] - alpha * m[r] / (np.sqrt(vv[r]) + eps)
+                if ((best[r] - loss) / abs(loss)) > tol:
+                    best[r], count[r] = loss, 0
+                    still.append(r)
+                else:
+                    count[r] += 1
+                    if count[r] <= patience:
+                        still.append(r)
+            active = still
+    final, _ = model.loss_and_grad_many(u, want_grad=False)
+    pick = n_starts - 1
+    if pick_best:  # first minimum, like the strict `<` of the sequential loop
+        pick = min(range(n_starts), key=lambda r: (final[r], r))
+    model.set_u(u[pick])
+    return (model.kernel.variance.numpy(), model.kernel.lengthscales.numpy(), model.likelihood.variance.numpy(),
+            np.array(model.inducing_variable.Z))
 
 
 def _optimize_differential_evolutions(model, popsize: int = 15, max_iter: int = 500, seed=None, verbose: bool = False) -> None:

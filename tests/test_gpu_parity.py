@@ -438,3 +438,23 @@ def test_concurrent_handles_are_bitwise_identical(cuda, n, handles):
             np.testing.assert_array_equal(grad, ref_grad)
     for g in gps:
         g.close()
+
+
+def test_multi_start_lockstep_on_device_equals_sequential(cuda):
+    """cfg1-sized exact model, "stochastic" recipe: batched (lock-stepped) starts == one start after the other, bitwise."""
+    import time
+
+    from gpras_b200 import gpr
+    from gpras_b200.synth import make_gp_data
+
+    d = make_gp_data(256, 8, 8, seed=1)
+    out, secs = [], []
+    for lock in (False, True):
+        g = gpr.GPRAS("RBF")
+        t0 = time.perf_counter()
+        g.fit(d.x, d.y, None, "kmeans", "stochastic", shared_kernel=True, n_starts=12, iter_initial=10, iter_final=5, seed=4,
+              lockstep=lock)
+        secs.append(time.perf_counter() - t0)
+        out.append(g.models[0].theta())
+    np.testing.assert_array_equal(out[0], out[1])
+    print(f"stochastic recipe, 12 starts x 10 Adam steps at N=256: sequential {secs[0]:.3f} s, lock-step {secs[1]:.3f} s")

@@ -176,3 +176,15 @@ def test_abi_argument_validation(lib):
     assert lib.gpras_gp_create(C.byref(h), 0, 0, 8, 65, 1) == -1
     assert lib.gpras_dgemm_tiles(None, 0, 0, 0, None, 0, None, 0, None, 0, 100, 128, 16, 1.0, 0.0) == -1
     assert lib.gpras_dpotrf(None, None, 0, None, 0, 100, None, None) == -1
+
+
+@pytest.mark.parametrize("pick_best", [False, True])
+def test_multi_start_lockstep_equals_sequential(pick_best):
+    """All starts advancing together (batched evaluations) must follow the one-after-the-other trajectories exactly."""
+    d = make_gp_data(40, 2, 2, seed=9)
+    res = []
+    for lock in (False, True):
+        m = OracleBackedModel("Matern32", d.x, d.y, 1.0)
+        gpr._optimize_multi_start(m, n_starts=5, iter_initial=6, iter_final=8, seed=3, pick_best=pick_best, lockstep=lock)
+        res.append(np.concatenate([m.theta(), [m.training_loss()]]))
+    np.testing.assert_array_equal(res[0], res[1])
