@@ -65,6 +65,7 @@ struct gpras_gp {
   int* info = nullptr;
   double *h_theta = nullptr, *h_result = nullptr;
   int* h_info = nullptr;
+  void *arena = nullptr, *h_arena = nullptr;  // single device / pinned allocations the training buffers are carved from
   // prediction state
   double *Xt = nullptr, *Xts = nullptr, *Ks = nullptr, *mean = nullptr, *vpart = nullptr, *var = nullptr,
          *varm = nullptr;
@@ -262,19 +263,39 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
   h->use_graphs = h->n_pad <= 4096 && !getenv("GPRAS_B200_NO_GRAPHS");
   const size_t nn = (size_t)h->n_pad * h->n_pad, np = (size_t)h->n_pad * h->p_pad;
   const int ntile = h->nt * (h->nt + 1) / 2;
-  if ((r = dalloc(&h->X, (size_t)h->n_pad * d)) || (r = dalloc(&h->Xs, (size_t)h->n_pad * d)) || (r = dalloc(&h->Y, np)) ||
-      (r = dalloc(&h->K, nn)) || (r = dalloc(&h->W, nn)) || (r = dalloc(&h->Kinv, nn)) || (r = dalloc(&h->U, np)) ||
-      (r = dalloc(&h->alpha, np)) || (r = dalloc(&h->theta, 2 + d)) || (r = dalloc(&h->logdet, h->nt)) ||
-      (r = dalloc(&h->gpart, (size_t)ntile * (2 + d))) || (r = dalloc(&h->gsum, 2 + d)) ||
-      (r = dalloc(&h->usq, USQ_PARTS)) || (r = dalloc(&h->result, 3 + d)) ||
-      (r = dalloc(&h->skinny, (size_t)SKINNY_MAX_SLABS * (h->n_pad > PRED_TB ? h->n_pad : PRED_TB) * h->p_pad))) {
-    gpras_gp_destroy(h);
-    return r;
+  // One device allocation and one pinned allocation per handle, carved below: a handle costs ~1 ms to create instead of
+  // ~4 ms (two dozen cudaMalloc / cudaMallocHost calls), which matters when a pool of them serves batched restarts.
+  struct Carve {
+    double** p;
+    size_t count;
+  };
+  const Carve parts[] = {
+      {&h->X, (size_t)h->n_pad * d}, {&h->Xs, (size_t)h->n_pad * d}, {&h->Y, np}, {&h->K, nn}, {&h->W, nn}, {&h->Kinv, nn},
+      {&h->U, np}, {&h->alpha, np}, {&h->theta, (size_t)2 + d}, {&h->logdet, (size_t)h->nt},
+      {&h->gpart, (size_t)ntile * (2 + d)}, {&h->gsum, (size_t)2 + d}, {&h->usq, (size_t)USQ_PARTS}, {&h->result, (size_t)3 + d},
+      {&h->skinny, (size_t)SKINNY_MAX_SLABS * (h->n_pad > PRED_TB ? h->n_pad : PRED_TB) * h->p_pad}};
+  size_t total = 64;  // the info word lives in the first 64 bytes
+  for (const Carve& c : parts) total += (c.count * sizeof(double) + 255) / 256 * 256;
+  {
+    cudaError_t e = cudaMalloc((void**)&h->arena, total);
+    if (e != cudaSuccess) {
+      gpras_gp_destroy(h);
+      return fail(GPRAS_E_NOMEM, "cudaMalloc", e);
+    }
   }
-  CU(cudaMalloc((void**)&h->info, sizeof(int)));
-  CU(cudaMallocHost((void**)&h->h_theta, sizeof(double) * (2 + d)));
-  CU(cudaMallocHost((void**)&h->h_result, sizeof(double) * (3 + d)));
-  CU(cudaMallocHost((void**)&h->h_info, sizeof(int)));
+  {
+    char* cur = (char*)h->arena;
+    h->info = (int*)cur;
+    cur += 64;
+    for (const Carve& c : parts) {
+      *c.p = (double*)cur;
+      cur += (c.count * sizeof(double) + 255) / 256 * 256;
+    }
+  }
+  CU(cudaMallocHost((void**)&h->h_arena, sizeof(double) * (2 + d) + sizeof(double) * (3 + d) + 64));
+  h->h_theta = (double*)h->h_arena;
+  h->h_result = h->h_theta + (2 + d);
+  h->h_info = (int*)(h->h_result + (3 + d));
   // stream-ordered: the handle's stream is non-blocking, so legacy-stream memsets would race with set_data
   CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->n_pad * d, h->stream));
   CU(cudaMemsetAsync(h->Y, 0, sizeof(double) * np, h->stream));
@@ -290,15 +311,12 @@ int gpras_gp_destroy(gpras_gp* h) {
   if (!h) return 0;
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  double* bufs[] = {h->X,    h->Xs,  h->Y,   h->K,  h->W,     h->Kinv, h->U,    h->alpha, h->theta, h->logdet, h->gpart,
-                    h->gsum, h->usq, h->result, h->skinny, h->Xt, h->Xts, h->Ks,   h->mean, h->vpart, h->var,   h->varm,   h->E1,
-                    h->E2,   h->bias, h->zbias, h->ring_m, h->ring_v, h->rootS};
+  double* bufs[] = {h->Xt, h->Xts, h->Ks, h->mean, h->vpart, h->var, h->varm, h->E1, h->E2, h->bias, h->zbias, h->ring_m, h->ring_v,
+                    h->rootS};
   for (double* b : bufs)
     if (b) cudaFree(b);
-  if (h->info) cudaFree(h->info);
-  if (h->h_theta) cudaFreeHost(h->h_theta);
-  if (h->h_result) cudaFreeHost(h->h_result);
-  if (h->h_info) cudaFreeHost(h->h_info);
+  if (h->arena) cudaFree(h->arena);
+  if (h->h_arena) cudaFreeHost(h->h_arena);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& g : h->graph)

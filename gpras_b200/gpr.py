@@ -141,6 +141,9 @@ class _Inducing:
         self.trainable = trainable
 
 
+_POOL_CACHE: dict = {}
+
+
 class _DeviceSlot:
     """Device handles of one GPRAS instance: one per calling thread and problem shape.  Per-column models take turns
     on their thread's handle; with ``fit(n_jobs > 1)`` several threads keep several evaluations in flight on one GPU
@@ -168,16 +171,21 @@ class _DeviceSlot:
         3.7e3 evals/s with one evaluation in flight, 7.3e4 with 32)."""
         first = self.acquire(model)
         st = self._per_thread[threading.get_ident()]
-        extra = st.setdefault("extra", [])
-        if st.get("extra_key") != (st["key"], id(model)):
-            for g in extra:
-                g.close()
-            extra.clear()
-            st["extra_key"] = (st["key"], id(model))
+        small = model.x.shape[0] <= 2048
+        # creating a handle costs ~10 ms (pinned + device allocations), so pools for small problems outlive this GPRAS
+        # instance in a process-wide cache (<= 100 MB per handle); large ones belong to the slot and are closed with it
+        cache = _POOL_CACHE if small else st.setdefault("own_pools", {})
+        ent = cache.setdefault((threading.get_ident(),) + st["key"], {"gps": [], "owner": None})
+        extra = ent["gps"]
+        if not small:
+            st["extra"] = extra
         while len(extra) < count - 1:
-            g = ExactGP(model.kernel.name, model.x.shape[0], model.x.shape[1], model.y.shape[1], device=model.device)
-            g.set_data(model.x, model.y)
-            extra.append(g)
+            extra.append(ExactGP(model.kernel.name, model.x.shape[0], model.x.shape[1], model.y.shape[1], device=model.device))
+            ent["owner"] = None
+        if ent["owner"] is not model:  # models take turns on the pool: rebinding data is a ~20 us copy per handle
+            for g in extra:
+                g.set_data(model.x, model.y)
+            ent["owner"] = model
         return [first] + extra[: count - 1]
 
     def release_other_threads(self) -> None:
@@ -281,7 +289,7 @@ class ExactModel:
             outs = [self.loss_and_grad(u) if want_grad else (self._loss_at(u), None) for u in us]
             return [o[0] for o in outs], [o[1] for o in outs]
         n = self.x.shape[0]
-        width = 32 if n <= 512 else (16 if n <= 2048 else (4 if n <= 4096 else 2))
+        width = 16 if n <= 2048 else (4 if n <= 4096 else 2)
         gps = self._slot.pool(self, min(width, len(us)))
         losses, grads = [None] * len(us), [None] * len(us)
         for lo in range(0, len(us), len(gps)):
