@@ -181,3 +181,38 @@ def test_export_metric_summary_tables(cuda, tmp_path):
     np.testing.assert_allclose(sc.rmse_aoi_toi[0], np.sqrt((e1 ** 2).mean()), rtol=1e-12)
     np.testing.assert_allclose(ts.err_aoi_ts[:12], e1.mean(axis=1), rtol=1e-11, atol=1e-14)
     np.testing.assert_allclose(ce.rmse_cell_toi[:37], np.sqrt((e1 ** 2).mean(axis=0)), rtol=1e-12)
+
+
+def test_full_size_properties_cfg5_block(cuda):
+    """BASELINE sizes (C = 200 000 cells, one 2 048-timestep block): properties that do not need an oracle pass.
+    y = x + delta  =>  rmse = mae = |delta|, err = -delta, every per-cell / per-timestep value equals the closed form;
+    swapping x and y flips the sign of the errors; results are bitwise repeatable."""
+    torch = cuda
+    from gpras_b200.metrics import MetricsAccumulator
+
+    t, c, delta = 2048, 200_000, 0.125
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(t, c, dtype=torch.float64, device="cuda", generator=g) * 4
+    y = x + delta
+    conf = torch.full((t, c), 0.25, dtype=torch.float64, device="cuda")
+    acc = MetricsAccumulator(c, t)
+    acc.reset(0.2)
+    acc.update(x, y, conf)
+    s = acc.finalize(0.5)
+    assert abs(s["rmse_aoi_toi"] - delta) < 1e-12 and abs(s["mae_aoi_toi"] - delta) < 1e-12 and abs(s["err_aoi_toi"] + delta) < 1e-12
+    np.testing.assert_allclose(s["rmse_cell_toi"], delta, rtol=1e-12)
+    np.testing.assert_allclose(s["err_aoi_ts"], -delta, rtol=1e-12)
+    np.testing.assert_allclose(s["err_cell_mts"], -delta, rtol=1e-12)
+    np.testing.assert_allclose(s["conf_aoi_ts"], 0.25, rtol=1e-13)
+    assert s["conf_aoi_toi"] == 0.25 and s["fi_aoi_toi"] == 1.0  # |e| = 0.125 <= v_tol everywhere
+    acc.reset(0.2)
+    acc.update(y, x, conf)
+    s2 = acc.finalize(0.5)
+    np.testing.assert_allclose(s2["err_cell_toi"], -s["err_cell_toi"], rtol=1e-13)
+    np.testing.assert_array_equal(s2["rmse_cell_toi"], s["rmse_cell_toi"])
+    acc.reset(0.2)
+    acc.update(x, y, conf)
+    s3 = acc.finalize(0.5)
+    for k in VEC + SCA:
+        np.testing.assert_array_equal(s3[k], s[k])
+    acc.close()

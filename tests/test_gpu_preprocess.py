@@ -132,3 +132,34 @@ def test_dsyev128_against_lapack(cuda, lib):
     v = V.cpu().numpy()[:, :40]
     np.testing.assert_allclose(v.T @ v, np.eye(40), atol=1e-9)
     np.testing.assert_allclose(h @ v, v * lam.cpu().numpy()[:40], atol=1e-12 * w[0])
+
+
+def test_full_size_properties_cfg3(cuda):
+    """BASELINE config 3 sizes (8 192 samples x 200 000 cells, 32 modes, generated on the device): EOF rows orthonormal,
+    eigenvalues descending and consistent with the score variances, retained residuals converged,
+    transform(reverse_transform(z)) == z, scores of the training samples standardised."""
+    import sys
+    from pathlib import Path
+
+    torch = cuda
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
+    from bench_pre_metrics import flood_tensor
+    from gpras_b200.preprocess import PreProcessor
+
+    n, c, p = 8192, 200_000, 32
+    x, elev, w = flood_tensor(torch, n, c, k=40)
+    pp = PreProcessor(hydraulic_parameter="wse")
+    pp.fit(x, elev, w, p)
+    e = pp.eofs
+    np.testing.assert_allclose(e @ e.T, np.eye(p), atol=1e-10)
+    ev = pp.eigenvalues
+    assert np.all(np.diff(ev[: p + 8]) <= 0)
+    assert np.max(pp.fit_info["residuals"][:p]) <= 1e-11
+    np.testing.assert_allclose(pp.x_std**2 * n / (n - 1), ev[:p], rtol=1e-9)   # population variance of the scores vs s^2 / (n - 1)
+    z = pp.transform(x[:256]).cpu().numpy()
+    z_all = pp.transform(x).cpu().numpy()
+    np.testing.assert_allclose(z_all.mean(axis=0), 0.0, atol=1e-9)
+    np.testing.assert_allclose(z_all.std(axis=0), 1.0, rtol=1e-9)
+    back = pp.reverse_transform(z)
+    np.testing.assert_allclose(pp.transform(back), z, rtol=1e-8, atol=1e-8)
+    pp.close()
