@@ -608,7 +608,8 @@ class GPRAS:
         start points, column order [variance, noise, lengthscale(s)]) runs the recipe from every start and keeps
         the lowest final loss (sharded across ranks when ``torch.distributed`` is initialised); ``n_jobs > 1``
         optimises that many per-column models concurrently on the GPU (host threads, one device handle each; the
-        reference loops sequentially, ``gpr.py:273-274``, and so does the default).
+        reference loops sequentially, ``gpr.py:273-274``, and so does the default).  Under ``torch.distributed`` (one
+        process per GPU) per-column models are sharded round-robin over ranks and their parameters all-gathered.
         """
         self.x = np.asarray(x).astype(np.float64)
         self.y = np.asarray(y).astype(np.float64)
@@ -629,7 +630,14 @@ class GPRAS:
 
                 run_restarts(model, opt, np.asarray(restarts, np.float64), opt_kwargs)
 
-        if n_jobs > 1 and len(unique) > 1:
+        from .parallel import dist_info
+
+        if dist_info()[1] > 1 and len(unique) > 1 and restarts is None:
+            # one process per GPU: per-column models go round-robin to ranks, parameters are all-gathered at the end
+            from .parallel import run_models_sharded
+
+            run_models_sharded(unique, run_one)
+        elif n_jobs > 1 and len(unique) > 1:
             from concurrent.futures import ThreadPoolExecutor
 
             with ThreadPoolExecutor(max_workers=int(n_jobs)) as ex:

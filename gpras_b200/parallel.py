@@ -145,3 +145,34 @@ def metrics_sharded(event_ids, summarise_event, keys) -> np.ndarray:
         rows.append([float(i)] + [float(s[k]) for k in keys])
     table = all_gather_rows(np.array(rows).reshape(-1, 1 + len(keys)), 1 + len(keys))
     return table[np.argsort(table[:, 0], kind="stable")]
+
+
+def run_models_sharded(models, run_one) -> None:
+    """Per-column models (the reference's default: one independent model per spatial mode, ``gpr.py:273-274``) sharded
+    round-robin over ranks: rank r optimises models r, r + world, ...; the optimised parameters (variance, likelihood
+    variance, lengthscales, inducing inputs) are all-gathered so that every rank ends with every model.  One exchange of
+    ``P x (2 + n_ls + M D)`` doubles at the end, nothing during optimisation."""
+    rank, world, _ = dist_info()
+    mine = shard_indices(len(models), rank, world)
+    for i in mine:
+        run_one(models[i])
+
+    def pack(i):
+        d = models[i].parameter_dict()
+        return np.concatenate([[float(i)], np.atleast_1d(d[".kernel.variance"]).ravel(), np.atleast_1d(d[".likelihood.variance"]).ravel(),
+                               np.atleast_1d(d[".kernel.lengthscales"]).ravel(), np.asarray(d[".inducing_variable.Z"], np.float64).ravel()])
+
+    if world == 1 or not models:
+        return
+    width = pack(0).size
+    table = all_gather_rows(np.array([pack(i) for i in mine]).reshape(-1, width), width)
+    nls = np.atleast_1d(models[0].parameter_dict()[".kernel.lengthscales"]).size
+    zshape = np.asarray(models[0].parameter_dict()[".inducing_variable.Z"]).shape
+    for row in table:
+        i = int(row[0])
+        if i % world == rank:
+            continue
+        ls = row[3 : 3 + nls]
+        models[i].assign_parameters({".kernel.variance": row[1], ".likelihood.variance": row[2],
+                                     ".kernel.lengthscales": ls if nls > 1 else ls[0],
+                                     ".inducing_variable.Z": row[3 + nls :].reshape(zshape)})

@@ -57,6 +57,12 @@ def _worker(rank, world, port, out_dir):
     lml, grad = parallel.lml_grad_column_sharded(local_eval, th)
     np.save(os.path.join(out_dir, f"colshard{rank}.npy"), np.concatenate([[lml], grad]))
 
+    # per-column models sharded over ranks, parameters gathered
+    d3 = make_gp_data(30, 2, 3, seed=11)
+    models = [OracleBackedModel("RBF", d3.x, d3.y[:, j : j + 1], 1.0) for j in range(3)]
+    parallel.run_models_sharded(models, lambda m_: gpr.OPTIMIZERS["L-BFGS-B"](m_, max_iter=15))
+    np.save(os.path.join(out_dir, f"models{rank}.npy"), np.array([m_.theta() for m_ in models]))
+
     # events sharded over ranks for the metrics
     rng = np.random.default_rng(3)
     events = [(rng.random((6, 9)), rng.random((6, 9)), rng.random((6, 9))) for _ in range(5)]
@@ -99,6 +105,16 @@ def test_column_and_event_sharding_world2(tmp_path):
     d5 = make_gp_data(50, 3, 5, seed=8)
     lml, gv, gn, gl = lml_and_grad("Matern52", d5.x, d5.y, Theta(1.3, 0.07, np.array([1.5, 2.0, 0.8])))
     np.testing.assert_allclose(c0, np.concatenate([[lml, gv, gn], gl]), rtol=1e-11)
+    a0, a1 = np.load(tmp_path / "models0.npy"), np.load(tmp_path / "models1.npy")
+    np.testing.assert_allclose(a0, a1, rtol=1e-14)  # gathered values pass through the inverse softplus once more
+    from gpras_b200 import gpr
+    from test_host_cpu import OracleBackedModel
+
+    d3 = make_gp_data(30, 2, 3, seed=11)
+    for j in range(3):
+        mj = OracleBackedModel("RBF", d3.x, d3.y[:, j : j + 1], 1.0)
+        gpr.OPTIMIZERS["L-BFGS-B"](mj, max_iter=15)
+        np.testing.assert_allclose(a0[j], mj.theta(), rtol=1e-12)
     m0, m1 = np.load(tmp_path / "metrics0.npy"), np.load(tmp_path / "metrics1.npy")
     np.testing.assert_array_equal(m0, m1)
     rng = np.random.default_rng(3)
