@@ -8,7 +8,7 @@
 namespace gpras {
 
 constexpr int EIG_B = 128;            // block size of the subspace iteration == engine tile
-constexpr int EIG_THREADS = 512;      // 64 column pairs x 8 threads
+constexpr int EIG_THREADS = 1024;     // 64 column pairs x 16 threads: a half-warp reads 16 consecutive rows of one column
 constexpr int EIG_LD = EIG_B + 2;     // column pitch (doubles)
 constexpr int EIG_SMEM_BYTES = (EIG_B * EIG_LD + 2 * EIG_B) * (int)sizeof(double);
 
@@ -31,7 +31,7 @@ jacobi_eig128_kernel(const double* __restrict__ H, long ldh, double cut, double*
     M[c * EIG_LD + r] = 0.5 * (H[(long)r * ldh + c] + H[(long)c * ldh + r]);
   }
   __syncthreads();
-  const int pair = tid >> 3, sub = tid & 7;
+  const int pair = tid >> 4, sub = tid & 15;
   int sweeps = 0;
   for (; sweeps < 40; sweeps++) {
     int rotated = 0;
@@ -45,15 +45,15 @@ jacobi_eig128_kernel(const double* __restrict__ H, long ldh, double cut, double*
       }
       double* pa = M + ca * EIG_LD + sub;
       double* pb = M + cb * EIG_LD + sub;
-      double xa[16], xb[16];
+      double xa[8], xb[8];
       double al = 0.0, be = 0.0, ga = 0.0;
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        xa[k] = pa[8 * k], xb[k] = pb[8 * k];
+      for (int k = 0; k < 8; k++) {
+        xa[k] = pa[16 * k], xb[k] = pb[16 * k];
         al += xa[k] * xa[k], be += xb[k] * xb[k], ga += xa[k] * xb[k];
       }
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
+      for (int o = 1; o < 16; o <<= 1) {
         al += __shfl_xor_sync(0xffffffffu, al, o);
         be += __shfl_xor_sync(0xffffffffu, be, o);
         ga += __shfl_xor_sync(0xffffffffu, ga, o);
@@ -64,9 +64,9 @@ jacobi_eig128_kernel(const double* __restrict__ H, long ldh, double cut, double*
         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
         const double cs = rsqrt(1.0 + t * t), sn = cs * t;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          pa[8 * k] = cs * xa[k] - sn * xb[k];
-          pb[8 * k] = sn * xa[k] + cs * xb[k];
+        for (int k = 0; k < 8; k++) {
+          pa[16 * k] = cs * xa[k] - sn * xb[k];
+          pb[16 * k] = sn * xa[k] + cs * xb[k];
         }
       }
       __syncthreads();

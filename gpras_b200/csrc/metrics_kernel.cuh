@@ -22,6 +22,7 @@ constexpr int MET_ROWS = 32;   // timesteps per row tile
 constexpr int MET_CELLQ = 5;   // per cell: sum e, sum e^2, sum conf, max x, max y
 constexpr int MET_ROWQ = 3;    // per row : sum e, sum e^2, sum conf
 constexpr int MET_CTAQ = 2;    // per CTA : sum |e|, count(|e| <= v_tol)
+constexpr int MET_RED_LD = MET_ROWS + 4;  // row-sum scratch [quantity][32 slots][36]: conflict-free writes (8q + 2g banks) and reads
 
 struct MetricsArgs {
   // FUSED prediction source
@@ -59,11 +60,11 @@ struct MetCfg {
   static constexpr int LDE = 128 + 4;
   static constexpr int LDA = P16 + 4;
   // E tile, two row tiles of modes, two variance vectors, reduction scratch
-  static constexpr int RED_DOUBLES = 2 * MET_ROWS * 33 + 16;
+  static constexpr int RED_DOUBLES = 2 * 32 * MET_RED_LD + 16;
   static constexpr int SMEM_DOUBLES = P16 * LDE + 2 * MET_ROWS * LDA + 2 * MET_ROWS + RED_DOUBLES;
   static constexpr int SMEM_BYTES = SMEM_DOUBLES * (int)sizeof(double);
 };
-constexpr int MET_PLAIN_SMEM_BYTES = (3 * MET_ROWS * 33 + 16) * (int)sizeof(double);
+constexpr int MET_PLAIN_SMEM_BYTES = (3 * 32 * MET_RED_LD + 16) * (int)sizeof(double);
 
 // Thread layout: warp w owns the 16 columns [16w, 16w+16) of the CTA's 128-cell tile for all 32 rows of a row tile
 // (4 x 2 DMMA accumulator tiles); a thread holds rows 8f+g (f < 4) and columns 16w + 8h + 2q + {0,1} (h < 2).
@@ -79,8 +80,8 @@ __global__ void __launch_bounds__(MET_THREADS, FUSED ? 2 : 1) metrics_stream_ker
   double* sE = smem;
   double* sA = sE + (FUSED ? P16 * Cfg::LDE : 0);
   double* sV = sA + (FUSED ? 2 * MET_ROWS * Cfg::LDA : 0);
-  double* sRed = sV + (FUSED ? 2 * MET_ROWS : 0);  // [NQ][MET_ROWS][33]
-  double* sMisc = sRed + NQ * MET_ROWS * 33;       // [16]
+  double* sRed = sV + (FUSED ? 2 * MET_ROWS : 0);  // [NQ][32 slots][MET_RED_LD]
+  double* sMisc = sRed + NQ * 32 * MET_RED_LD;     // [16]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int wn = warp * 16;
@@ -261,17 +262,17 @@ __global__ void __launch_bounds__(MET_THREADS, FUSED ? 2 : 1) metrics_stream_ker
           }
         }
       const int slot = warp * 4 + q;
-      sRed[(0 * MET_ROWS + rl) * 33 + slot] = r_e;
-      sRed[(1 * MET_ROWS + rl) * 33 + slot] = r_e2;
-      if (!FUSED) sRed[(2 * MET_ROWS + rl) * 33 + slot] = r_cf;
+      sRed[(0 * 32 + slot) * MET_RED_LD + rl] = r_e;
+      sRed[(1 * 32 + slot) * MET_RED_LD + rl] = r_e2;
+      if (!FUSED) sRed[(2 * 32 + slot) * MET_RED_LD + rl] = r_cf;
     }
     __syncthreads();
     if (tid < NQ * MET_ROWS) {
-      const double* r = sRed + tid * 33;  // tid = quantity * MET_ROWS + row
+      const int qq = tid / MET_ROWS, row = tid - qq * MET_ROWS;
+      const double* r = sRed + (long)qq * 32 * MET_RED_LD + row;
       double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < 32; k++) s += r[k];
-      const int qq = tid / MET_ROWS, row = tid - qq * MET_ROWS;
+      for (int k = 0; k < 32; k++) s += r[k * MET_RED_LD];
       a.row_part[((long)qq * a.t_tiles * MET_ROWS + row_base + row) * a.n_ctile + tj] = s;
     }
     __syncthreads();
