@@ -36,8 +36,9 @@ UNIT = "evals/s"
 # measured on this pool's B200 (profiles/r01/lib_bars_cublas_cusolver.json): cuBLAS DGEMM 8192^3, sustained
 FP64_DGEMM_TFLOPS = 35.4
 # one `ncu --set full` capture per kernel (cold cache, one launch each), summarised in profiles/
-NCU = {"source": "profiles/r01/ncu_full_final.json (one launch each, cold cache)", "lauum_dram_bytes": 1.631e9, "lauum_dmma_pct": 88.4,
-       "syrk_dram_bytes": 4.668e8, "syrk_dmma_pct": 75.8}
+NCU = {"source": "profiles/r01/ncu_full_final_r01b.json, ncu_eval_traffic_final_summary.json (one launch each, cold cache)",
+       "lauum_dram_bytes": 1.634e9, "lauum_dmma_pct": 96.7, "syrk_dram_bytes": 4.668e8, "syrk_dmma_pct": 75.8,
+       "eval_dram_bytes": 14.95e9, "eval_launches": 275}
 FP64_PEAK_SOURCE = "measured cuBLAS Dgemm 8192^3 on this pool (profiles/r01/lib_bars_cublas_cusolver.json); MEASURED_PEAKS.json has no FP64 entry"
 
 
@@ -359,7 +360,8 @@ def run_ours(args) -> None:
                                        "achieved": achieved, "frac": achieved / FP64_DGEMM_TFLOPS, "flops_per_eval": f_eval(n, p),
                                        "dense_ms_per_eval": dense_ms},
                          "stage_tflops": per_stage,
-                         "ncu": {"source": NCU["source"],
+                         "ncu": {"source": NCU["source"], "whole_eval_dram_bytes": NCU["eval_dram_bytes"],
+                                 "whole_eval_algorithmic_bytes": 16.0 * n * n + 16.0 * n * d + 8.0 * n * p,
                                  "lauum_launch": {"dram_bytes": NCU["lauum_dram_bytes"], "algorithmic_bytes": 8.0 * n * n,
                                                   "dmma_pipe_active_pct": NCU["lauum_dmma_pct"]},
                                  "syrk_launch": {"dram_bytes": NCU["syrk_dram_bytes"], "algorithmic_bytes": 2 * 1953 * 128 * 128 * 8.0,

@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round-end evidence run on the GPU box (one gpurun call): bench line, ncu launch list of the same command, per-launch
+# traffic of one whole evaluation, and `--set full` captures of the main kernels.  Outputs -> gpurun_out/final/.
+set -u
+O=gpurun_out/final; mkdir -p $O
+python bench.py --steps 10 --warmup 3 > $O/bench_1gpu.json 2> $O/bench_1gpu.err || echo "bench failed"
+python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2>> $O/bench_1gpu.err || echo "ref failed"
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/bench_short_plain.json 2>> $O/bench_1gpu.err || echo "short bench failed"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/ncu_launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_bench.log 2>&1
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed
+python tools/profile_eval.py 2 > $O/eval_plain.log 2>&1
+ncu --metrics $M --clock-control none --launch-skip 277 -c 290 --csv --log-file $O/ncu_eval_traffic.csv python tools/profile_eval.py 2 > $O/ncu_eval.log 2>&1
+full() { # name regex skip count
+  ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k "regex:$2" --launch-skip $3 -c $4 -o $O/full_$1 -f \
+      python tools/profile_eval.py 2 > $O/ncu_full_$1.log 2>&1
+}
+full lauum 'Li3ELi1EEELb1ELb1' 1 1
+full rest0 'Li16ELi3ELi2EEELb0ELb0' 63 1
+full trtri_top 'Li3ELi1EEELb0ELb1' 22 2
+full leaf 'leaf_potrf' 64 1
+full cov 'cov_kernel' 1 1
+full grad 'grad_kernel' 1 1
+ls -la $O
