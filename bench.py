@@ -306,7 +306,7 @@ def run_ours(args) -> None:
         # against a resident truth block, the T x C prediction never written
         from gpras_b200.metrics import MetricsAccumulator
 
-        acc = MetricsAccumulator(c, reps * int(xt.shape[0]) + 1)
+        acc = MetricsAccumulator(c, reps * int(xt.shape[0]) + 1, device=local)
         acc.set_elevations(cm.elevations, cm.elevations)
         gtr = torch.Generator(device="cuda").manual_seed(7 + rank)
         truth = torch.rand(int(xt.shape[0]), c, dtype=torch.float64, device="cuda", generator=gtr) * 4 + 3
