@@ -5,6 +5,7 @@
 #include "../../include/gpras_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -146,6 +147,7 @@ int launch_skinny(cudaStream_t s, bool akm, GemmDesc d, double* part, int rows, 
   return 0;
 }
 constexpr int SKINNY_MAX_SLABS = 16;
+constexpr int PAIR_MIN_REM = 36;  // Cholesky: pair the trailing updates while more than this many block rows remain
 
 // ---- dense building blocks -------------------------------------------------------------------
 // Side stream + events for the one-panel look-ahead of the Cholesky.
@@ -221,16 +223,33 @@ int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, lo
     if ((r = launch_gemm(s, false, false, p, 1, launches, SHAPE_P))) return r;
   }
   CU(cudaEventRecord(evPanel[0], s));
+  int j_single = nt - 1 - PAIR_MIN_REM;  // first step whose trailing matrix is short enough for single panels ...
+  if (j_single < 0) j_single = 0;
+  j_single += j_single & 1;                // ... rounded up to an even step
+  if (const char* e = getenv("GPRAS_B200_PAIR_MIN_REM")) {
+    j_single = nt - 1 - atoi(e);
+    if (j_single < 0) j_single = 0;
+    j_single += j_single & 1;
+  }
   for (int j = 0; j + 1 < nt; j++) {
     const int rem = nt - j - 1;  // tiles below / right of block j
-    double* pn = A + (long)(j + 1) * 128 * lda + (long)j * 128;  // panel j, rows from tile j+1
+    // Trailing updates are applied in PAIRS of panels (rank 256): the bulk update runs at odd j with panels j-1 and j, which
+    // halves the read-modify-write traffic on the trailing matrix and doubles the k extent per tile of the short-k kernel.
+    // The chain's column update brings block column j+1 fully up to date itself: one pending panel at even j, two at odd j.
+    // Pairing pays while the bulk update dominates the step; once the leaf -> panel chain does (short trailing matrix), single
+    // panels keep the pipeline fine-grained.  The switch happens at an even j, where no panel is pending.
+    const bool paired = j < j_single;
+    const bool odd = paired && (j & 1) != 0;
+    const int kp = odd ? 256 : 128;                 // k extent of the chain's column update
+    const long pcol = (long)(odd ? j - 1 : j) * 128;  // first column of the pending panel(s)
+    double* pn = A + (long)(j + 1) * 128 * lda + pcol;  // pending panel(s), rows from tile j+1
     // ---- side stream: block column j+1 -> S, then the next diagonal block and panel ----
     CU(cudaStreamWaitEvent(s2, evPanel[j], 0));
-    if (j > 0) CU(cudaStreamWaitEvent(s2, evRest[j - 1], 0));
+    if (!odd && j > 0) CU(cudaStreamWaitEvent(s2, evRest[j - 1], 0));  // (an odd paired step waited two steps ago)
     double* Sj = S + (long)(j + 1) * 128 * 128;  // rows from tile j+1
     {
       const double* col = A + (long)(j + 1) * 128 * (lda + 1);
-      GemmDesc c = make_desc(pn, lda, pn, lda, Sj, 128, 2 * rem, 4, 128);
+      GemmDesc c = make_desc(pn, lda, pn, lda, Sj, 128, 2 * rem, 4, kp);
       c.alpha = -1.0, c.beta = 1.0;
       c.Cin = col, c.ldcin = lda;
       if ((r = launch_gemm(s2, false, false, c, 1, launches, SHAPE_T))) return r;
@@ -244,14 +263,16 @@ int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, lo
         if ((r = launch_gemm(s2, false, false, p, 1, launches, SHAPE_T))) return r;
       }
       CU(cudaEventRecord(evPanel[j + 1], s2));
-      // ---- main stream: the rest of the trailing triangle ----
-      if (j > 0) CU(cudaStreamWaitEvent(s, evPanel[j], 0));
-      double* pn2 = pn + (long)128 * lda;  // panel j, rows from tile j+2
-      double* trail = A + (long)(j + 2) * 128 * (lda + 1);
-      GemmDesc u = make_desc(pn2, lda, pn2, lda, trail, lda, rem - 1, 2 * (rem - 1), 128);
-      u.tri = 1, u.alpha = -1.0, u.beta = 1.0;
-      if ((r = launch_gemm(s, false, false, u, 1, launches, SHAPE_S))) return r;
-      CU(cudaEventRecord(evRest[j], s));
+      // ---- main stream: the rest of the trailing triangle, panels j-1 and j together ----
+      if (odd || !paired) {
+        CU(cudaStreamWaitEvent(s, evPanel[j], 0));
+        double* pn2 = pn + (long)128 * lda;  // pending panel(s): rows from tile j+2
+        double* trail = A + (long)(j + 2) * 128 * (lda + 1);
+        GemmDesc u = make_desc(pn2, lda, pn2, lda, trail, lda, rem - 1, 2 * (rem - 1), kp);
+        u.tri = 1, u.alpha = -1.0, u.beta = 1.0;
+        if ((r = launch_gemm(s, false, false, u, 1, launches, SHAPE_S))) return r;
+        CU(cudaEventRecord(evRest[j], s));
+      }
     }
   }
   CU(cudaEventRecord(evJoin, s2));
