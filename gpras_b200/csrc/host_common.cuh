@@ -147,7 +147,8 @@ int launch_skinny(cudaStream_t s, bool akm, GemmDesc d, double* part, int rows, 
   return 0;
 }
 constexpr int SKINNY_MAX_SLABS = 16;
-constexpr int PAIR_MIN_REM = 36;  // Cholesky: pair the trailing updates while more than this many block rows remain
+constexpr int PANEL_GROUP = 2;    // Cholesky: trailing updates for groups of this many panels ...
+constexpr int PAIR_MIN_REM = 36;  // ... while more than this many block rows remain
 
 // ---- dense building blocks -------------------------------------------------------------------
 // Side stream + events for the one-panel look-ahead of the Cholesky.
@@ -223,29 +224,28 @@ int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, lo
     if ((r = launch_gemm(s, false, false, p, 1, launches, SHAPE_P))) return r;
   }
   CU(cudaEventRecord(evPanel[0], s));
-  int j_single = nt - 1 - PAIR_MIN_REM;  // first step whose trailing matrix is short enough for single panels ...
+  // Trailing updates are applied for GROUPS of G panels (rank 128 G) while the trailing matrix is large: that divides the
+  // read-modify-write traffic on the trailing matrix by G and multiplies the k extent per tile of the short-k kernel.  The
+  // chain's column update brings block column j+1 fully up to date itself (1 .. G pending panels).  Grouping pays while the
+  // bulk update dominates the step; once the leaf -> panel chain does (short trailing matrix), single panels keep the pipeline
+  // fine-grained.  The switch happens at a multiple of G, where no panel is pending.
+  int G = PANEL_GROUP, min_rem = PAIR_MIN_REM;
+  if (const char* e = getenv("GPRAS_B200_PANEL_GROUP")) G = atoi(e) > 0 ? atoi(e) : 1;
+  if (const char* e = getenv("GPRAS_B200_PAIR_MIN_REM")) min_rem = atoi(e);
+  int j_single = nt - 1 - min_rem;  // first step whose trailing matrix is short enough for single panels ...
   if (j_single < 0) j_single = 0;
-  j_single += j_single & 1;                // ... rounded up to an even step
-  if (const char* e = getenv("GPRAS_B200_PAIR_MIN_REM")) {
-    j_single = nt - 1 - atoi(e);
-    if (j_single < 0) j_single = 0;
-    j_single += j_single & 1;
-  }
+  j_single = (j_single + G - 1) / G * G;  // ... rounded up to a group boundary
   for (int j = 0; j + 1 < nt; j++) {
     const int rem = nt - j - 1;  // tiles below / right of block j
-    // Trailing updates are applied in PAIRS of panels (rank 256): the bulk update runs at odd j with panels j-1 and j, which
-    // halves the read-modify-write traffic on the trailing matrix and doubles the k extent per tile of the short-k kernel.
-    // The chain's column update brings block column j+1 fully up to date itself: one pending panel at even j, two at odd j.
-    // Pairing pays while the bulk update dominates the step; once the leaf -> panel chain does (short trailing matrix), single
-    // panels keep the pipeline fine-grained.  The switch happens at an even j, where no panel is pending.
-    const bool paired = j < j_single;
-    const bool odd = paired && (j & 1) != 0;
-    const int kp = odd ? 256 : 128;                 // k extent of the chain's column update
-    const long pcol = (long)(odd ? j - 1 : j) * 128;  // first column of the pending panel(s)
+    const bool grouped = j < j_single;
+    const int pc = grouped ? (j % G) + 1 : 1;         // pending panels at this step
+    const bool bulk = pc == (grouped ? G : 1);        // the group is complete: apply it to the rest of the trailing matrix
+    const int kp = 128 * pc;                          // k extent of the chain's column update
+    const long pcol = (long)(j - (pc - 1)) * 128;     // first column of the pending panel(s)
     double* pn = A + (long)(j + 1) * 128 * lda + pcol;  // pending panel(s), rows from tile j+1
     // ---- side stream: block column j+1 -> S, then the next diagonal block and panel ----
     CU(cudaStreamWaitEvent(s2, evPanel[j], 0));
-    if (!odd && j > 0) CU(cudaStreamWaitEvent(s2, evRest[j - 1], 0));  // (an odd paired step waited two steps ago)
+    if (pc == 1 && j > 0) CU(cudaStreamWaitEvent(s2, evRest[j - 1], 0));  // (later steps of a group: waited at its first step)
     double* Sj = S + (long)(j + 1) * 128 * 128;  // rows from tile j+1
     {
       const double* col = A + (long)(j + 1) * 128 * (lda + 1);
@@ -263,8 +263,8 @@ int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, lo
         if ((r = launch_gemm(s2, false, false, p, 1, launches, SHAPE_T))) return r;
       }
       CU(cudaEventRecord(evPanel[j + 1], s2));
-      // ---- main stream: the rest of the trailing triangle, panels j-1 and j together ----
-      if (odd || !paired) {
+      // ---- main stream: the rest of the trailing triangle, the whole group of panels together ----
+      if (bulk) {
         CU(cudaStreamWaitEvent(s, evPanel[j], 0));
         double* pn2 = pn + (long)128 * lda;  // pending panel(s): rows from tile j+2
         double* trail = A + (long)(j + 2) * 128 * (lda + 1);
