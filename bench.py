@@ -359,6 +359,8 @@ def run_ours(args) -> None:
                          "aggregate": {"what": "all dense stages of one evaluation: potrf + inverse + W^T W + alpha (F_eval = N^3 + 3 N^2 P)",
                                        "achieved": achieved, "frac": achieved / FP64_DGEMM_TFLOPS, "flops_per_eval": f_eval(n, p),
                                        "dense_ms_per_eval": dense_ms},
+                         "job": {"what": "F_eval x measured evals/s of the timed region (two evaluations in flight per GPU)",
+                                 "achieved": value / world * f_eval(n, p) * 1e-12, "frac": value / world * f_eval(n, p) * 1e-12 / FP64_DGEMM_TFLOPS},
                          "stage_tflops": per_stage,
                          "ncu": {"source": NCU["source"], "whole_eval_dram_bytes": NCU["eval_dram_bytes"],
                                  "whole_eval_algorithmic_bytes": 16.0 * n * n + 16.0 * n * d + 8.0 * n * p,

@@ -63,6 +63,21 @@ def run_cfg5_sweep():
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(json.dumps({"config": "cfg5", "events": t, "cells": cells, "wall_s": dt, "events_per_s": t / dt, "cell_depths_per_s": t * cells / dt,
                       "mode_mean_shape": list(mm.shape), "mode_var_min": float(mv.min())}), flush=True)
+    # the same sweep with the consumer fused: per-cell mean / max depth, mean confidence, exceedance counts -- nothing written per cell-depth
+    from gpras_b200.metrics import MetricsAccumulator
+    acc = MetricsAccumulator(cells, t)
+    acc.set_elevations(None, cm.elevations)
+    acc.reset(0.0)
+    acc.predict_update(gp, xt[:4096], None)
+    acc.reset(0.0)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    acc.predict_update(gp, xt, None)
+    summ = acc.finalize(0.5)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(json.dumps({"config": "cfg5 fused per-cell reductions", "events": t, "cells": cells, "wall_s": dt, "events_per_s": t / dt,
+                      "cell_depths_per_s": t * cells / dt, "max_depth_over_all_events_p99": float(np.percentile(summ["cell_max_y"], 99)),
+                      "mean_depth_mean": float((-summ["err_cell_toi"]).mean()), "mean_conf": summ["conf_aoi_toi"]}), flush=True)
+    acc.close()
     gp.close()
 
 
