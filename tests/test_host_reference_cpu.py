@@ -1,0 +1,77 @@
+"""CPU: host-side logic of the PreProcessor / metrics mirrors that needs no device -- the closed forms that turn the kernel's
+raw reductions into the metrics of ``gpras/metrics.py``, North's rule, persistence keys -- against the reference-generated
+golden vectors."""
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import MET_CASES, PRE_CASES, sub
+from gpras_b200 import metrics as gm
+from gpras_b200.preprocess import PreProcessor, compute_norths_rule
+
+
+def _raw_reductions(x, y, conf, thr, v_tol):
+    """What metrics_stream_kernel + metrics_finalize_kernel hand to the host (restated with NumPy)."""
+    e = x - y
+    xm, ym = x.max(axis=0), y.max(axis=0)
+    d = xm - ym
+    cells = np.stack([e.sum(axis=0), (e * e).sum(axis=0), conf.sum(axis=0), xm, ym])
+    rows = np.stack([e.sum(axis=1), (e * e).sum(axis=1), conf.sum(axis=1)])
+    hx, hy, zx, zy = xm >= thr, ym >= thr, xm >= 0, ym >= 0
+    scal = np.array([cells[0].sum(), cells[1].sum(), cells[2].sum(), np.abs(e).sum(), (np.abs(e) <= v_tol).sum(), d.sum(), (d * d).sum(),
+                     xm.sum(), ((xm - xm.mean()) ** 2).sum(), (hx & hy).sum(), (hx & ~hy).sum(), (~hx & hy).sum(),
+                     (zx & zy).sum(), (zx & ~zy).sum(), (~zx & zy).sum()], float)
+    return scal, cells, rows
+
+
+@pytest.mark.parametrize("name", MET_CASES)
+def test_summary_closed_forms_match_reference(met_golden, name):
+    c = sub(met_golden, name)
+    x, y, conf = c["x"], c["y"], c["conf"]
+    scal, cells, rows = _raw_reductions(x, y, conf, float(c["depth_threshold"]), 0.0)
+    s = gm._summary(scal, cells, rows, x.shape[0], x.shape[1])
+    for k in ("rmse_cell_toi", "err_cell_toi", "conf_cell_toi", "err_cell_mts", "rmse_aoi_ts", "err_aoi_ts", "conf_aoi_ts"):
+        np.testing.assert_allclose(s[k], c[k], rtol=1e-12, atol=1e-14, err_msg=k)
+    for k in ("rmse_aoi_toi", "mae_aoi_toi", "conf_aoi_toi", "err_aoi_toi", "rmse_aoi_mts", "err_aoi_mts", "nse_aoi_mts", "pod_mts",
+              "rfa_mts", "csi_mts", "f2_mts", "f3_mts"):
+        np.testing.assert_allclose(s[k], float(c[k]), rtol=1e-12, atol=1e-14, err_msg=k)
+    assert s["fi_aoi_toi"] == float(c["fi_aoi_toi_0"])
+
+
+def test_metrics_module_surface_matches_reference():
+    # gpras/metrics.py:11-324
+    names = ["export_metric_summary", "rmse_aoi_toi", "mae_aoi_toi", "conf_aoi_toi", "rmse_aoi_ts", "rmse_cell_toi", "rmse_aoi_mts",
+             "err_cell_mts", "nse_aoi_mts", "err_aoi_toi", "err_aoi_mts", "err_aoi_ts", "conf_aoi_ts", "err_cell_toi", "conf_cell_toi",
+             "fi_aoi_toi", "pod_mts", "rfa_mts", "csi_mts", "f2_mts", "f3_mts"]
+    for n in names:
+        assert callable(getattr(gm, n)), n
+
+
+@pytest.mark.parametrize("name", PRE_CASES)
+def test_norths_rule_and_persistence_keys(pre_golden, name, tmp_path):
+    c = sub(pre_golden, name)
+    if int(c["modes_requested"]) < 0:
+        assert compute_norths_rule(c["eigenvalues"], int(c["n_samples_fit"])) == int(c["spatial_mode_count"])
+    pp = PreProcessor(spatial_mode_count=int(c["spatial_mode_count"]), input_mean=c["input_mean"], elevations=c["elevations"],
+                      hydraulic_parameter=str(c["hydraulic_parameter"]), wetness_classes=c["wetness_classes"], weights=c["fit_weights"],
+                      eofs=c["eofs"], eigenvalues=c["eigenvalues"], n_samples_fit=int(c["n_samples_fit"]), x_mean=c["x_mean"], x_std=c["x_std"])
+    np.testing.assert_array_equal(pp.dry_indices, c["dry_indices"])
+    pp.to_file(tmp_path / "pp.pkl")
+    with open(tmp_path / "pp.pkl", "rb") as f:
+        d = pickle.load(f)
+    # the reference's to_dict keys (gpras/preprocess.py:1134-1148)
+    assert set(d) == {"spatial_mode_count", "wet_threshold", "hydraulic_parameter", "elevations", "wetness_classes", "input_mean",
+                      "weights", "eofs", "eigenvalues", "n_samples_fit", "x_mean", "x_std"}
+    q = PreProcessor.from_file(tmp_path / "pp.pkl")
+    np.testing.assert_array_equal(q.eofs, c["eofs"])
+    np.testing.assert_array_equal(q.wse_2_depth(c["reverse_mean"].copy()), c["reverse_depth"])
+
+
+def test_norths_rule_object_form():
+    class Fitted:
+        explained_variance_ = np.array([9.0, 4.0, 3.9, 1.2, 0.5])
+        n_samples_seen_ = 50
+
+    assert compute_norths_rule(Fitted()) == 1
+    assert compute_norths_rule(np.array([0.5, 0.2]), 10) == 0
