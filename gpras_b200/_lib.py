@@ -45,6 +45,8 @@ SYMBOLS = {
     "gpras_sgpr_destroy": (C.c_int, [vp]),
     "gpras_sgpr_set_data": (C.c_int, [vp, vp, vp, C.c_int]),
     "gpras_sgpr_elbo_grad": (C.c_int, [vp, vp, vp, C.c_double, vp, vp, vp]),
+    "gpras_sgpr_elbo_grad_enqueue": (C.c_int, [vp, vp, vp, C.c_double, C.c_int]),
+    "gpras_sgpr_elbo_grad_fetch": (C.c_int, [vp, vp, vp, vp]),
     "gpras_sgpr_condition": (C.c_int, [vp, vp, vp, C.c_double]),
     "gpras_sgpr_predict": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "gpras_sgpr_last_launches": (C.c_int, [vp]),

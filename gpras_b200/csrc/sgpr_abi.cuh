@@ -24,6 +24,12 @@ struct gpras_sgpr {
   int* info = nullptr;
   double *h_theta = nullptr, *h_z = nullptr, *h_result = nullptr;
   int* h_info = nullptr;
+  void *arena = nullptr, *h_arena = nullptr;  // one device / one pinned allocation carved into the training buffers
+  // asynchronous objective + CUDA-graph replay (index: want_grad); the jitter is baked into the captured kernel arguments
+  bool pending = false, pending_grad = false, use_graphs = true, graph_failed = false, eager_done[2] = {false, false};
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  double graph_jitter = -1.0;
+  int graph_launches[2] = {0, 0};
   // prediction
   double *Xt = nullptr, *Xts = nullptr, *Kus = nullptr, *tmp1 = nullptr, *p2 = nullptr, *q1 = nullptr, *mean = nullptr,
          *var = nullptr, *varm = nullptr;
@@ -92,8 +98,10 @@ int sgpr_forward(gpras_sgpr* h, const double* theta, const double* z) {
   cudaStream_t s = h->stream;
   const int n = h->n, D = h->d, m = h->m, n_pad = h->n_pad, m_pad = h->m_pad, ntm = h->ntm, ntn = h->ntn, rp = h->r_pad;
   int r;
-  memcpy(h->h_theta, theta, sizeof(double) * (2 + D));
-  memcpy(h->h_z, z, sizeof(double) * (size_t)m * D);
+  if (theta) {  // NULL: the pinned staging buffers were filled by the caller (graph capture / replay)
+    memcpy(h->h_theta, theta, sizeof(double) * (2 + D));
+    memcpy(h->h_z, z, sizeof(double) * (size_t)m * D);
+  }
   CU(cudaMemcpyAsync(h->theta, h->h_theta, sizeof(double) * (2 + D), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(h->Z, h->h_z, sizeof(double) * (size_t)m * D, cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(h->info, 0, sizeof(int), s));
@@ -175,30 +183,42 @@ int gpras_sgpr_create(gpras_sgpr** out, int device, int kernel_id, int n, int d,
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const size_t mm = (size_t)h->m_pad * h->m_pad, mn = (size_t)h->m_pad * h->n_pad, mr = (size_t)h->m_pad * h->r_pad;
   const size_t sk = (size_t)SKINNY_MAX_SLABS * (h->m_pad > SGPR_TB ? h->m_pad : SGPR_TB) * h->r_pad;
-  if ((rc = sgpr_alloc(h, &h->X, (size_t)h->n_pad * d)) || (rc = sgpr_alloc(h, &h->Xs, (size_t)h->n_pad * d)) ||
-      (rc = sgpr_alloc(h, &h->Z, (size_t)h->m_pad * d)) || (rc = sgpr_alloc(h, &h->Zs, (size_t)h->m_pad * d)) ||
-      (rc = sgpr_alloc(h, &h->Y, (size_t)h->n_pad * h->r_pad)) || (rc = sgpr_alloc(h, &h->Kuf, mn)) ||
-      (rc = sgpr_alloc(h, &h->Kuu, mm)) || (rc = sgpr_alloc(h, &h->WL, mm)) || (rc = sgpr_alloc(h, &h->Ap, mn)) ||
-      (rc = sgpr_alloc(h, &h->slabs, mm * h->nz_aat)) || (rc = sgpr_alloc(h, &h->AATs, mm)) ||
-      (rc = sgpr_alloc(h, &h->B, mm)) || (rc = sgpr_alloc(h, &h->WB, mm)) || (rc = sgpr_alloc(h, &h->Binv, mm)) ||
-      (rc = sgpr_alloc(h, &h->T, mm)) || (rc = sgpr_alloc(h, &h->Rm, mm)) || (rc = sgpr_alloc(h, &h->RA, mm)) ||
-      (rc = sgpr_alloc(h, &h->RW, mm)) || (rc = sgpr_alloc(h, &h->T1, mm)) || (rc = sgpr_alloc(h, &h->Guu, mm)) ||
-      (rc = sgpr_alloc(h, &h->Guf1, mn)) || (rc = sgpr_alloc(h, &h->ae, mr)) || (rc = sgpr_alloc(h, &h->c, mr)) ||
-      (rc = sgpr_alloc(h, &h->chat, mr)) || (rc = sgpr_alloc(h, &h->u, mr)) || (rc = sgpr_alloc(h, &h->skinny, sk)) ||
-      (rc = sgpr_alloc(h, &h->theta, 2 + d)) || (rc = sgpr_alloc(h, &h->logdetL, h->ntm)) ||
-      (rc = sgpr_alloc(h, &h->logdetB, h->ntm)) || (rc = sgpr_alloc(h, &h->scal, 8)) ||
-      (rc = sgpr_alloc(h, &h->partA, (size_t)h->ntm * h->ntn * (1 + d))) ||
-      (rc = sgpr_alloc(h, &h->partB, (size_t)h->ntm * h->ntm * (1 + d))) ||
-      (rc = sgpr_alloc(h, &h->zpA, (size_t)h->ntn * h->m_pad * d)) || (rc = sgpr_alloc(h, &h->zpB, (size_t)h->ntm * h->m_pad * d)) ||
-      (rc = sgpr_alloc(h, &h->result, 3 + d + (size_t)m * d))) {
-    gpras_sgpr_destroy(h);
-    return rc;
+  // one device allocation and one pinned allocation, carved (a handle per model is created when models train in lock-step)
+  struct Carve {
+    double** p;
+    size_t count;
+  };
+  const Carve parts[] = {
+      {&h->X, (size_t)h->n_pad * d}, {&h->Xs, (size_t)h->n_pad * d}, {&h->Z, (size_t)h->m_pad * d}, {&h->Zs, (size_t)h->m_pad * d},
+      {&h->Y, (size_t)h->n_pad * h->r_pad}, {&h->Kuf, mn}, {&h->Kuu, mm}, {&h->WL, mm}, {&h->Ap, mn}, {&h->slabs, mm * h->nz_aat},
+      {&h->AATs, mm}, {&h->B, mm}, {&h->WB, mm}, {&h->Binv, mm}, {&h->T, mm}, {&h->Rm, mm}, {&h->RA, mm}, {&h->RW, mm}, {&h->T1, mm},
+      {&h->Guu, mm}, {&h->Guf1, mn}, {&h->ae, mr}, {&h->c, mr}, {&h->chat, mr}, {&h->u, mr}, {&h->skinny, sk},
+      {&h->theta, (size_t)2 + d}, {&h->logdetL, (size_t)h->ntm}, {&h->logdetB, (size_t)h->ntm}, {&h->scal, 8},
+      {&h->partA, (size_t)h->ntm * h->ntn * (1 + d)}, {&h->partB, (size_t)h->ntm * h->ntm * (1 + d)},
+      {&h->zpA, (size_t)h->ntn * h->m_pad * d}, {&h->zpB, (size_t)h->ntm * h->m_pad * d}, {&h->result, 3 + d + (size_t)m * d}};
+  size_t total = 64;
+  for (const Carve& c : parts) total += (c.count * sizeof(double) + 255) / 256 * 256;
+  {
+    cudaError_t e = cudaMalloc(&h->arena, total);
+    if (e != cudaSuccess) {
+      gpras_sgpr_destroy(h);
+      return fail(GPRAS_E_NOMEM, "cudaMalloc", e);
+    }
+    char* cur = (char*)h->arena;
+    h->info = (int*)cur;
+    cur += 64;
+    for (const Carve& c : parts) {
+      *c.p = (double*)cur;
+      cur += (c.count * sizeof(double) + 255) / 256 * 256;
+    }
   }
-  CU(cudaMalloc((void**)&h->info, sizeof(int)));
-  CU(cudaMallocHost((void**)&h->h_theta, sizeof(double) * (2 + d)));
-  CU(cudaMallocHost((void**)&h->h_z, sizeof(double) * (size_t)m * d));
-  CU(cudaMallocHost((void**)&h->h_result, sizeof(double) * (3 + d + (size_t)m * d)));
-  CU(cudaMallocHost((void**)&h->h_info, sizeof(int)));
+  const size_t nres = 3 + d + (size_t)m * d;
+  CU(cudaMallocHost(&h->h_arena, sizeof(double) * ((2 + d) + (size_t)m * d + nres) + 64));
+  h->h_theta = (double*)h->h_arena;
+  h->h_z = h->h_theta + (2 + d);
+  h->h_result = h->h_z + (size_t)m * d;
+  h->h_info = (int*)(h->h_result + nres);
+  h->use_graphs = !getenv("GPRAS_B200_NO_GRAPHS");
   CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->n_pad * d, h->stream));
   CU(cudaMemsetAsync(h->Z, 0, sizeof(double) * h->m_pad * d, h->stream));
   CU(cudaMemsetAsync(h->Y, 0, sizeof(double) * h->n_pad * h->r_pad, h->stream));
@@ -214,11 +234,10 @@ int gpras_sgpr_destroy(gpras_sgpr* h) {
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (double* b : h->owned) cudaFree(b);
-  if (h->info) cudaFree(h->info);
-  if (h->h_theta) cudaFreeHost(h->h_theta);
-  if (h->h_z) cudaFreeHost(h->h_z);
-  if (h->h_result) cudaFreeHost(h->h_result);
-  if (h->h_info) cudaFreeHost(h->h_info);
+  if (h->arena) cudaFree(h->arena);
+  if (h->h_arena) cudaFreeHost(h->h_arena);
+  for (auto& g : h->graph)
+    if (g) cudaGraphExecDestroy(g);
   h->la.destroy();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -238,19 +257,12 @@ int gpras_sgpr_set_data(gpras_sgpr* h, const double* x, const double* y, int on_
   return 0;
 }
 
-int gpras_sgpr_elbo_grad(gpras_sgpr* h, const double* theta, const double* z, double jitter, double* elbo,
-                         double* grad_theta, double* grad_z) {
-  if (!h || !theta || !z) return fail(GPRAS_E_ARG, "null argument");
-  if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
-  DeviceGuard guard(h->device);
+// Enqueue every operation of one objective evaluation on h->stream (theta and z are already in the pinned staging buffers).
+static int sgpr_record_eval(gpras_sgpr* h, bool want_grad) {
   cudaStream_t s = h->stream;
   const int n = h->n, D = h->d, m = h->m, n_pad = h->n_pad, m_pad = h->m_pad, ntm = h->ntm, ntn = h->ntn, rp = h->r_pad, R = h->r;
-  const bool want_grad = grad_theta != nullptr || grad_z != nullptr;
   int r;
-  h->launches = 0;
-  h->conditioned = false;
-  h->jitter = jitter;
-  if ((r = sgpr_forward(h, theta, z))) return r;
+  if ((r = sgpr_forward(h, nullptr, nullptr))) return r;
   // Binv = WB^T WB (needed for the bound's gradient and its noise derivative)
   if ((r = lauum_impl(s, h->WB, m_pad, h->Binv, m_pad, m_pad, &h->launches))) return r;
   mirror_lower_kernel<<<(unsigned)(((long)m_pad * m_pad + 255) / 256), 256, 0, s>>>(h->Binv, m_pad, m_pad);
@@ -293,12 +305,79 @@ int gpras_sgpr_elbo_grad(gpras_sgpr* h, const double* theta, const double* z, do
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h->h_result, h->result, sizeof(double) * (3 + D + (size_t)m * D), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(h->h_info, h->info, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  if ((r = sgpr_check_info(h))) return r;
-  if (elbo) *elbo = h->h_result[0];
-  if (grad_theta) memcpy(grad_theta, h->h_result + 1, sizeof(double) * (2 + D));
-  if (grad_z) memcpy(grad_z, h->h_result + 3 + D, sizeof(double) * (size_t)m * D);
   return 0;
+}
+
+// One evaluation is ~40 launches of microsecond kernels at reference scale (M = 50): it is captured once per
+// (handle, want_grad, jitter) into a CUDA graph and replayed (the first evaluation runs eagerly: it creates events and sets
+// kernel attributes).  Works like the exact model's enqueue / fetch pair (gpras_abi.cu).
+int gpras_sgpr_elbo_grad_enqueue(gpras_sgpr* h, const double* theta, const double* z, double jitter, int want_grad) {
+  if (!h || !theta || !z) return fail(GPRAS_E_ARG, "null argument");
+  if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = h->stream;
+  h->conditioned = false;
+  if (jitter != h->graph_jitter) {  // the jitter is a captured kernel argument: new value, new graphs
+    for (auto& g : h->graph)
+      if (g) cudaGraphExecDestroy(g), g = nullptr;
+    h->graph_jitter = jitter;
+  }
+  h->jitter = jitter;
+  memcpy(h->h_theta, theta, sizeof(double) * (2 + h->d));
+  memcpy(h->h_z, z, sizeof(double) * (size_t)h->m * h->d);
+  const int g = want_grad ? 1 : 0;
+  int r;
+  if (h->use_graphs && h->graph[g]) {
+    h->launches = h->graph_launches[g];
+    CU(cudaGraphLaunch(h->graph[g], s));
+  } else if (h->use_graphs && h->eager_done[g] && !h->graph_failed) {
+    h->launches = 0;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    r = sgpr_record_eval(h, want_grad != 0);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (r == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&h->graph[g], graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (r != 0 || e != cudaSuccess || !h->graph[g]) {
+      cudaGetLastError();
+      h->graph[g] = nullptr;
+      h->graph_failed = true;  // eager launches from now on (still the CUDA path, never a CPU one)
+      h->launches = 0;
+      if ((r = sgpr_record_eval(h, want_grad != 0))) return r;
+    } else {
+      h->graph_launches[g] = h->launches;
+      CU(cudaGraphLaunch(h->graph[g], s));
+    }
+  } else {
+    h->launches = 0;
+    if ((r = sgpr_record_eval(h, want_grad != 0))) return r;
+    h->eager_done[g] = true;
+  }
+  h->pending = true;
+  h->pending_grad = want_grad != 0;
+  return 0;
+}
+
+int gpras_sgpr_elbo_grad_fetch(gpras_sgpr* h, double* elbo, double* grad_theta, double* grad_z) {
+  if (!h) return fail(GPRAS_E_ARG, "null handle");
+  if (!h->pending) return fail(GPRAS_E_STATE, "no evaluation enqueued");
+  DeviceGuard guard(h->device);
+  CU(cudaStreamSynchronize(h->stream));
+  h->pending = false;
+  int r;
+  if ((r = sgpr_check_info(h))) return r;
+  const int D = h->d;
+  if (elbo) *elbo = h->h_result[0];
+  if (grad_theta && h->pending_grad) memcpy(grad_theta, h->h_result + 1, sizeof(double) * (2 + D));
+  if (grad_z && h->pending_grad) memcpy(grad_z, h->h_result + 3 + D, sizeof(double) * (size_t)h->m * D);
+  return 0;
+}
+
+int gpras_sgpr_elbo_grad(gpras_sgpr* h, const double* theta, const double* z, double jitter, double* elbo,
+                         double* grad_theta, double* grad_z) {
+  int r = gpras_sgpr_elbo_grad_enqueue(h, theta, z, jitter, grad_theta != nullptr || grad_z != nullptr);
+  if (r) return r;
+  return gpras_sgpr_elbo_grad_fetch(h, elbo, grad_theta, grad_z);
 }
 
 int gpras_sgpr_condition(gpras_sgpr* h, const double* theta, const double* z, double jitter) {

@@ -200,6 +200,22 @@ class SparseGP:
                                             ptr(gt) if want_grad else None, ptr(gz) if want_grad else None))
         return elbo.value, gt, gz
 
+    def enqueue(self, theta, z, jitter: float = 1e-6, want_grad: bool = True) -> None:
+        """Start one evaluation on the handle's stream (replayed from a CUDA graph after the first two calls)."""
+        theta, z = _f64(theta), _f64(z)
+        if z.shape != (self.m, self.d):
+            raise ValueError(f"expected inducing inputs {(self.m, self.d)}, got {z.shape}")
+        check(self.lib.gpras_sgpr_elbo_grad_enqueue(self._h, ptr(theta), ptr(z), float(jitter), int(want_grad)))
+        self._want_grad = bool(want_grad)
+
+    def fetch(self):
+        elbo = C.c_double()
+        gt = np.empty(2 + self.d) if self._want_grad else None
+        gz = np.empty((self.m, self.d)) if self._want_grad else None
+        check(self.lib.gpras_sgpr_elbo_grad_fetch(self._h, C.byref(elbo), ptr(gt) if self._want_grad else None,
+                                                  ptr(gz) if self._want_grad else None))
+        return elbo.value, gt, gz
+
     def condition(self, theta, z, jitter: float = 1e-6) -> None:
         theta, z = _f64(theta), _f64(z)
         check(self.lib.gpras_sgpr_condition(self._h, ptr(theta), ptr(z), float(jitter)))

@@ -597,6 +597,7 @@ class GPRAS:
         initial_theta: NDArray[Any] | None = None,
         restarts: NDArray[Any] | None = None,
         n_jobs: int = 1,
+        lockstep_models: bool = True,
         **opt_kwargs: Any,
     ) -> None:
         """Fit the surrogate (``gpr.py:237-275``).  Positional arguments and ``**opt_kwargs`` are the reference's.
@@ -610,6 +611,8 @@ class GPRAS:
         optimises that many per-column models concurrently on the GPU (host threads, one device handle each; the
         reference loops sequentially, ``gpr.py:273-274``, and so does the default).  Under ``torch.distributed`` (one
         process per GPU) per-column models are sharded round-robin over ranks and their parameters all-gathered.
+        ``lockstep_models`` (default on) trains the per-column sparse models of the Adam-based recipes together, one round of
+        evaluations in flight at a time; the result is the one of the sequential loop.
         """
         self.x = np.asarray(x).astype(np.float64)
         self.y = np.asarray(y).astype(np.float64)
@@ -632,7 +635,14 @@ class GPRAS:
 
         from .parallel import dist_info
 
-        if dist_info()[1] > 1 and len(unique) > 1 and restarts is None:
+        if (not exact and lockstep_models and n_jobs == 1 and restarts is None and initial_theta is None and dist_info()[1] == 1
+                and len(unique) > 1 and optimization_method in ("adam", "two-stage") and set(opt_kwargs) <= {"max_iter"}):
+            # the reference's default path: independent per-column sparse models trained by Adam -- all of them advance
+            # together, their evaluations overlapping on the GPU (same trajectories as the sequential loop)
+            from .sparse import fit_lockstep
+
+            fit_lockstep(unique, optimization_method, **opt_kwargs)
+        elif dist_info()[1] > 1 and len(unique) > 1 and restarts is None:
             # one process per GPU: per-column models go round-robin to ranks, parameters are all-gathered at the end
             from .parallel import run_models_sharded
 

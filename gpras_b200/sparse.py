@@ -113,6 +113,23 @@ class SparseModel:
         if u is not None:
             self.set_u(u)
         elbo, gt, gz = self._gp().elbo_grad(self.theta(), np.asarray(self.inducing_variable.Z, np.float64), JITTER)
+        return self._assemble(elbo, gt, gz)
+
+    # -- asynchronous form on a handle of the model's own (lock-stepped training of the per-column models) --
+    def bind(self, gp: SparseGP) -> None:
+        gp.set_data(self.x, self.y)
+        self._own = gp
+
+    def enqueue_loss_and_grad(self, u) -> None:
+        self.set_u(u)
+        self._own.enqueue(self.theta(), np.asarray(self.inducing_variable.Z, np.float64), JITTER, True)
+
+    def fetch_loss_and_grad(self):
+        return self._assemble(*self._own.fetch())
+
+    def _assemble(self, elbo, gt, gz):
+        """Loss and gradient w.r.t. the trainable unconstrained variables from the device's ELBO and its gradients
+        (log-prior terms and the softplus chain rule are host logic)."""
         self.n_evals += 1
         g_ls = gt[2:] if self.kernel.lengthscales.size > 1 else np.array([gt[2:].sum()])
         parts = []
@@ -144,3 +161,77 @@ class SparseModel:
         self.kernel.lengthscales.assign(d[".kernel.lengthscales"])
         self.likelihood.variance.assign(d[".likelihood.variance"])
         self.inducing_variable.Z = np.asarray(d[".inducing_variable.Z"], np.float64)
+
+
+# ------------------------------------------------------------------------------------------------
+# lock-stepped training of the per-column models
+# ------------------------------------------------------------------------------------------------
+_MODEL_POOLS: dict = {}
+
+
+def _model_pool(kernel: str, n: int, d: int, m: int, r: int, device: int, count: int) -> list:
+    """``count`` sparse handles of one problem shape, kept for the life of the process (creating one costs several ms)."""
+    pool = _MODEL_POOLS.setdefault((threading.get_ident(), kernel, n, d, m, r, device), [])
+    while len(pool) < count:
+        pool.append(SparseGP(kernel, n, d, m, r, device=device))
+    return pool[:count]
+
+
+def adam_lockstep(models, max_iter: int, learning_rate: float = 0.001) -> None:
+    """``_optimize_adam`` (Keras Adam + the reference's early-stopping rule, ``gpr.py:147-173``) for SEVERAL independent models
+    at once: every round enqueues one loss+gradient evaluation per still-active model on that model's own handle, then
+    fetches them, so the evaluations of the P per-column models overlap on the GPU instead of running one after the
+    other (``gpr.py:273-274``).  Each model follows exactly the trajectory of the one-model loop."""
+    u = [mdl.get_u() for mdl in models]
+    active = [i for i, v in enumerate(u) if v.size]
+    mom = [np.zeros_like(v) for v in u]
+    vel = [np.zeros_like(v) for v in u]
+    best, count = [np.inf] * len(models), [0] * len(models)
+    b1, b2, eps, tol, patience = 0.9, 0.999, 1e-7, 10e-6, 50
+    for t in range(1, int(max_iter) + 1):
+        if not active:
+            break
+        for i in active:
+            models[i].enqueue_loss_and_grad(u[i])
+        still = []
+        for i in active:
+            loss, g = models[i].fetch_loss_and_grad()
+            mom[i] = b1 * mom[i] + (1.0 - b1) * g
+            vel[i] = b2 * vel[i] + (1.0 - b2) * g * g
+            alpha = learning_rate * np.sqrt(1.0 - b2**t) / (1.0 - b1**t)
+            u[i] = u[i] - alpha * mom[i] / (np.sqrt(vel[i]) + eps)
+            models[i].set_u(u[i])
+            if ((best[i] - loss) / abs(loss)) > tol:
+                best[i], count[i] = loss, 0
+                still.append(i)
+            else:
+                count[i] += 1
+                if count[i] <= patience:
+                    still.append(i)
+        active = still
+
+
+def fit_lockstep(models, method: str, max_iter: int = 100) -> bool:
+    """Train all per-column sparse models together with the Adam-based recipes (``"adam"``, ``"two-stage"``).  Returns False
+    (nothing done) for other recipes."""
+    from .gpr import _set_stage
+
+    if method not in ("adam", "two-stage") or not models:
+        return False
+    m0 = models[0]
+    n, d = m0.x.shape
+    pool = _model_pool(m0.kernel.name, n, d, m0.inducing_variable.Z.shape[0], m0.y.shape[1], m0.device, len(models))
+    for mdl, gp in zip(models, pool):
+        mdl.bind(gp)
+    if method == "adam":
+        adam_lockstep(models, max_iter)
+        return True
+    for mdl in models:
+        _set_stage(mdl, hypers=False, z=True)
+    adam_lockstep(models, max_iter)
+    for mdl in models:
+        _set_stage(mdl, hypers=True, z=False)
+    adam_lockstep(models, max_iter)
+    for mdl in models:
+        _set_stage(mdl, hypers=True, z=True)
+    return True

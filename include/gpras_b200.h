@@ -99,6 +99,10 @@ int gpras_sgpr_set_data(gpras_sgpr* h, const double* x, const double* y, int on_
  * Either gradient pointer may be NULL; both NULL skips the backward pass (differential evolution, gpr.py:62). */
 int gpras_sgpr_elbo_grad(gpras_sgpr* h, const double* theta, const double* z, double jitter, double* elbo,
                          double* grad_theta, double* grad_z);
+/* Asynchronous pair (the evaluation is replayed from a CUDA graph): enqueue on the handle's stream, then fetch (synchronises).
+ * Several handles -- one per per-column model -- keep their evaluations in flight together. */
+int gpras_sgpr_elbo_grad_enqueue(gpras_sgpr* h, const double* theta, const double* z, double jitter, int want_grad);
+int gpras_sgpr_elbo_grad_fetch(gpras_sgpr* h, double* elbo, double* grad_theta, double* grad_z);
 /* predict_y (gpr.py:337): condition at (theta, z), then mean (t x r) and variance (t x r, noise included). */
 int gpras_sgpr_condition(gpras_sgpr* h, const double* theta, const double* z, double jitter);
 int gpras_sgpr_predict(gpras_sgpr* h, const double* xs, int t, double* mean, double* var);
