@@ -266,6 +266,21 @@ class ExactModel:
             self.set_u(u)
         gp = self._slot.acquire(self)
         lml, glog = gp.lml_grad(self.theta(), want_grad=True)
+        return self._assemble(lml, glog)
+
+    # -- asynchronous form on a handle of the model's own (lock-stepped training of per-column models) --
+    def bind(self, gp: ExactGP) -> None:
+        gp.set_data(self.x, self.y)
+        self._own = gp
+
+    def enqueue_loss_and_grad(self, u) -> None:
+        self.set_u(u)
+        self._own.enqueue(self.theta(), True)
+
+    def fetch_loss_and_grad(self):
+        return self._assemble(*self._own.fetch())
+
+    def _assemble(self, lml, glog):
         self.n_evals += 1
         g_var, g_noise, g_ls = glog[0], glog[1], glog[2:]
         if self.kernel.lengthscales.size == 1:
@@ -635,12 +650,16 @@ class GPRAS:
 
         from .parallel import dist_info
 
-        if (not exact and lockstep_models and n_jobs == 1 and restarts is None and initial_theta is None and dist_info()[1] == 1
-                and len(unique) > 1 and optimization_method in ("adam", "two-stage") and set(opt_kwargs) <= {"max_iter"}):
-            # the reference's default path: independent per-column sparse models trained by Adam -- all of them advance
-            # together, their evaluations overlapping on the GPU (same trajectories as the sequential loop)
+        if (lockstep_models and n_jobs == 1 and restarts is None and dist_info()[1] == 1 and len(unique) > 1
+                and optimization_method in ("adam", "two-stage") and set(opt_kwargs) <= {"max_iter"}
+                and (not exact or self.x.shape[0] <= 4096)):
+            # the reference's default path: independent per-column models trained by Adam -- all of them advance together,
+            # their evaluations overlapping on the GPU (same trajectories as the sequential loop)
             from .sparse import fit_lockstep
 
+            if initial_theta is not None:
+                for model in unique:
+                    _assign_theta(model, initial_theta)
             fit_lockstep(unique, optimization_method, **opt_kwargs)
         elif dist_info()[1] > 1 and len(unique) > 1 and restarts is None:
             # one process per GPU: per-column models go round-robin to ranks, parameters are all-gathered at the end

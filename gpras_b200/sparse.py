@@ -177,6 +177,15 @@ def _model_pool(kernel: str, n: int, d: int, m: int, r: int, device: int, count:
     return pool[:count]
 
 
+def _exact_pool(kernel: str, n: int, d: int, p: int, device: int, count: int) -> list:
+    from .engine import ExactGP
+
+    pool = _MODEL_POOLS.setdefault((threading.get_ident(), "exact", kernel, n, d, p, device), [])
+    while len(pool) < count:
+        pool.append(ExactGP(kernel, n, d, p, device=device))
+    return pool[:count]
+
+
 def adam_lockstep(models, max_iter: int, learning_rate: float = 0.001) -> None:
     """``_optimize_adam`` (Keras Adam + the reference's early-stopping rule, ``gpr.py:147-173``) for SEVERAL independent models
     at once: every round enqueues one loss+gradient evaluation per still-active model on that model's own handle, then
@@ -220,7 +229,10 @@ def fit_lockstep(models, method: str, max_iter: int = 100) -> bool:
         return False
     m0 = models[0]
     n, d = m0.x.shape
-    pool = _model_pool(m0.kernel.name, n, d, m0.inducing_variable.Z.shape[0], m0.y.shape[1], m0.device, len(models))
+    if isinstance(m0, SparseModel):
+        pool = _model_pool(m0.kernel.name, n, d, m0.inducing_variable.Z.shape[0], m0.y.shape[1], m0.device, len(models))
+    else:  # per-column exact models: one exact-GP handle each
+        pool = _exact_pool(m0.kernel.name, n, d, m0.y.shape[1], m0.device, len(models))
     for mdl, gp in zip(models, pool):
         mdl.bind(gp)
     if method == "adam":

@@ -483,3 +483,19 @@ def test_sparse_models_lockstep_equals_sequential(cuda, method):
             assert mean.shape == (50, 6) and np.all(var > 0)
     np.testing.assert_array_equal(out[0], out[1])
     print(f"{method}, 6 models x 25(+25) Adam steps: sequential {secs[0]:.3f} s, lock-step {secs[1]:.3f} s")
+
+
+def test_exact_per_column_models_lockstep_equals_sequential(cuda):
+    """Per-column EXACT models (n_inducing=None, not shared_kernel) under the Adam recipe: lock-step == sequential, bitwise."""
+    from gpras_b200 import GPRAS
+    from gpras_b200.synth import make_gp_data
+
+    data = make_gp_data(300, 4, 5, 20, seed=21)
+    out = []
+    for lock in (False, True):
+        g = GPRAS("RBF")
+        g.fit(data.x, data.y, None, "kmeans", "adam", max_iter=30, lockstep_models=lock)
+        out.append(np.concatenate([m.theta() for m in g.models]))
+    np.testing.assert_array_equal(out[0], out[1])
+    mean, var = g.predict(data.x_test)
+    assert mean.shape == (20, 5) and np.all(var > 0)
