@@ -67,9 +67,9 @@ int metrics_block(gpras_metrics* m, cudaStream_t s, MetricsArgs a, int t, int p1
   return 0;
 }
 
-int metrics_stage(gpras_metrics* m, int which, size_t rows) {
+// Staging buffer `which` (0 truth, 1 prediction, 2 confidence) for host inputs: MET_TB rows, allocated on first use, kept.
+int metrics_stage(gpras_metrics* m, int which) {
   if (m->stage[which]) return 0;
-  (void)rows;
   return dalloc(&m->stage[which], (size_t)MET_TB * m->c_pad);
 }
 
@@ -158,7 +158,7 @@ int gpras_metrics_update(gpras_metrics* m, const double* x, long ldx, const doub
       if (on_device) {
         dev[k] = src[k] + (size_t)t0 * lds[k], ldd[k] = lds[k];
       } else {
-        if ((r = metrics_stage(m, k, tb))) return r;
+        if ((r = metrics_stage(m, k))) return r;
         CU(cudaMemcpy2DAsync(m->stage[k], sizeof(double) * m->c_pad, src[k] + (size_t)t0 * lds[k], sizeof(double) * lds[k],
                              sizeof(double) * m->c, tb, cudaMemcpyHostToDevice, s));
         dev[k] = m->stage[k], ldd[k] = m->c_pad;
@@ -209,7 +209,7 @@ int gpras_gp_predict_metrics(gpras_gp* h, gpras_metrics* m, const double* xs, in
       if (truth_on_device) {
         a.X = truth + (size_t)t0 * ldx, a.ldx = ldx;
       } else {
-        if ((r = metrics_stage(m, 0, tb))) return r;
+        if ((r = metrics_stage(m, 0))) return r;
         CU(cudaMemcpy2DAsync(m->stage[0], sizeof(double) * m->c_pad, truth + (size_t)t0 * ldx, sizeof(double) * ldx,
                              sizeof(double) * m->c, tb, cudaMemcpyHostToDevice, s));
         a.X = m->stage[0], a.ldx = m->c_pad;

@@ -169,8 +169,13 @@ int stage_matrix(gpras_pre* h, const double* x, long ldx, int n, int on_device, 
   }
   int r;
   if ((r = palloc(h, owned, (size_t)n * h->c_pad))) return r;
-  CU(cudaMemcpy2DAsync(*owned, sizeof(double) * h->c_pad, x, sizeof(double) * ldx, sizeof(double) * h->c, n,
-                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  cudaError_t e = cudaMemcpy2DAsync(*owned, sizeof(double) * h->c_pad, x, sizeof(double) * ldx, sizeof(double) * h->c, n,
+                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) {
+    pfree(h, *owned);
+    *owned = nullptr;
+    return fail(GPRAS_E_CUDA, "staging copy of the input matrix", e);
+  }
   *xd = *owned, *ldd = h->c_pad;
   return 0;
 }
