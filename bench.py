@@ -38,7 +38,7 @@ FP64_DGEMM_TFLOPS = 35.4
 # one `ncu --set full` capture per kernel (cold cache, one launch each), summarised in profiles/
 NCU = {"source": "profiles/r01/ncu_full_final_r01b.json, ncu_eval_traffic_final_summary.json (one launch each, cold cache)",
        "lauum_dram_bytes": 1.634e9, "lauum_dmma_pct": 96.7, "syrk_dram_bytes": 4.668e8, "syrk_dmma_pct": 75.8,
-       "eval_dram_bytes": 14.95e9, "eval_launches": 275}
+       "eval_dram_bytes": 11.2e9, "eval_launches": 262}
 FP64_PEAK_SOURCE = "measured cuBLAS Dgemm 8192^3 on this pool (profiles/r01/lib_bars_cublas_cusolver.json); MEASURED_PEAKS.json has no FP64 entry"
 
 

@@ -10,11 +10,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-fi
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_bench.log 2>&1
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed
 python tools/profile_eval.py 2 > $O/eval_plain.log 2>&1
-ncu --metrics $M --clock-control none --launch-skip 277 -c 290 --csv --log-file $O/ncu_eval_traffic.csv python tools/profile_eval.py 2 > $O/ncu_eval.log 2>&1
+# launches of ONE evaluation = gpu_launches / steps of the bench line; skip the first (eager) evaluation, capture the second
+L=$(python -c "import json; d=json.load(open('$O/bench_short_plain.json')); print(d['gpu_launches'] // d['steps'])")
+ncu --metrics $M --clock-control none --launch-skip $L -c $L --csv --log-file $O/ncu_eval_traffic.csv python tools/profile_eval.py 2 > $O/ncu_eval.log 2>&1
 full() { # name regex skip count
   ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k "regex:$2" --launch-skip $3 -c $4 -o $O/full_$1 -f \
       python tools/profile_eval.py 2 > $O/ncu_full_$1.log 2>&1
 }
+[ -n "${SKIP_FULL:-}" ] && { ls -la $O; exit 0; }
 full lauum 'Li3ELi1EEELb1ELb1' 1 1
 full rest0 'Li16ELi3ELi2EEELb0ELb0' 63 1
 full trtri_top 'Li3ELi1EEELb0ELb1' 22 2

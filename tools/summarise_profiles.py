@@ -88,5 +88,6 @@ for rep in sorted(SRC.glob("full_*.ncu-rep")):
     hdr, units = rr[0], rr[1]
     idx = {h: i for i, h in enumerate(hdr)}
     full[rep.stem.replace("full_", "")] = [{w: (d[idx[w]] + (" " + units[idx[w]] if units[idx[w]] else "")) for w in WANT if w in idx} for d in rr[2:]]
-json.dump(full, open(DST / "ncu_full_final_r01b.json", "w"), indent=1)
+if full:
+    json.dump(full, open(DST / "ncu_full_final_r01b.json", "w"), indent=1)
 print("full captures:", {k: len(v) for k, v in full.items()})
