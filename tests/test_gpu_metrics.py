@@ -216,3 +216,21 @@ def test_full_size_properties_cfg5_block(cuda):
     for k in VEC + SCA:
         np.testing.assert_array_equal(s3[k], s[k])
     acc.close()
+
+
+def test_metrics_misuse_raises(cuda):
+    from gpras_b200 import _lib
+    from gpras_b200.metrics import MetricsAccumulator
+
+    acc = MetricsAccumulator(40, 10)
+    acc.reset(0.0)
+    with pytest.raises(ValueError):
+        acc.update(np.zeros((3, 41)), np.zeros((3, 41)))  # wrong cell count
+    with pytest.raises(_lib.GprasError):
+        acc.finalize()  # nothing accumulated
+    acc.update(np.zeros((6, 40)), np.ones((6, 40)))
+    with pytest.raises(_lib.GprasError):
+        acc.update(np.zeros((6, 40)), np.ones((6, 40)))  # beyond the accumulator's capacity of 10 timesteps
+    s = acc.finalize(0.5)
+    assert s["rmse_aoi_toi"] == 1.0 and s["err_aoi_toi"] == -1.0 and acc.timesteps() == 6
+    acc.close()

@@ -163,3 +163,36 @@ def test_full_size_properties_cfg3(cuda):
     back = pp.reverse_transform(z)
     np.testing.assert_allclose(pp.transform(back), z, rtol=1e-8, atol=1e-8)
     pp.close()
+
+
+def test_edge_shapes_and_errors(cuda):
+    """One mode, one sample to transform, one event to expand, fewer cells than one tile; misuse raises."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    from make_golden_reference import flood_samples
+    from gpras_b200.preprocess import PreProcessor
+    from oracle import preprocess as opre
+    from oracle.cells import reverse_transform
+
+    wse, elev, w = flood_samples(37, 50, 3, seed=77)
+    f = opre.fit(wse, elev, w, 1, 0.03, "wse")
+    pp = PreProcessor(hydraulic_parameter="wse")
+    with pytest.raises(ValueError):
+        pp.transform(wse[:1].copy())  # not fitted
+    pp.fit(wse.copy(), elev, w, 1)
+    assert pp.eofs.shape == f.eofs.shape == (1, int((~f.dry).sum()))
+    np.testing.assert_allclose(pp.eofs, f.eofs, atol=1e-9)
+    z = pp.transform(wse[:1].copy())
+    assert z.shape == (1, 1)
+    np.testing.assert_allclose(z, opre.transform(f, wse[:1]), rtol=1e-9, atol=1e-9)
+    m, v = pp.reverse_transform(z, np.abs(z))
+    rm, rv = reverse_transform(z, np.abs(z), pp.eofs, pp.x_mean, pp.x_std, pp.weights, pp.input_mean, pp.dry_indices, elev)
+    np.testing.assert_allclose(m, rm, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(v, rv, rtol=1e-12, atol=1e-14)
+    with pytest.raises(ValueError):
+        pp.transform(np.zeros((3, 49)))  # wrong number of cells
+    with pytest.raises(ValueError):
+        pp.reverse_transform(np.zeros((2, 3)))  # wrong number of modes
+    pp.close()
