@@ -12,8 +12,10 @@ Same constructor, attributes and methods as the reference class (``gpras/preproc
 * ``reverse_transform``: the folded modes -> cells map as two GEMMs with the offset fused into the epilogue.
 
 Differences from the reference, all documented limits rather than approximations: at most 64 spatial modes; ``eigenvalues``
-holds the leading ``min(128, samples, cells)`` explained variances (the reference keeps all ``min(samples, cells)``);
-North's rule is evaluated on those.  There is no CPU fallback.
+holds the leading ``min(128, samples, cells)`` explained variances (the reference keeps all ``min(samples, cells)``), of which
+the retained ones (all 64 candidates when North's rule chooses) are converged to the residual tolerance and the rest are the
+Ritz values of the last subspace iteration (lower bounds, typically within a percent); North's rule is evaluated on the
+converged ones.  There is no CPU fallback.
 """
 
 from __future__ import annotations
