@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(PT_THREADS) cov_kernel(const double* __restric
 // never materialised (8 N^2 n_theta bytes otherwise).  DC = lengthscale accumulators per thread (D <= DC).
 // ---------------------------------------------------------------------------------------------
 template <int KID, int DC>
-__global__ void __launch_bounds__(PT_THREADS) grad_kernel(const double* __restrict__ Xs, int n, int D,
+__global__ void __launch_bounds__(PT_THREADS, DC <= 32 ? 2 : 1) grad_kernel(const double* __restrict__ Xs, int n, int D,
                                                           const double* __restrict__ Wt, long ldw,
                                                           double* __restrict__ part, int npart_cols) {
   extern __shared__ __align__(16) double smem[];
