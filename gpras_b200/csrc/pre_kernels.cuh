@@ -98,23 +98,24 @@ static __global__ void center_weight_kernel(const double* __restrict__ X, long l
 // (the host stages the input into a padded buffer when that does not hold).
 constexpr int PROJ_THREADS = 256;
 constexpr int PROJ_BK = 16;
-constexpr int PROJ_STAGES = 4;
+constexpr int PROJ_STAGES_MAX = 4;
 
 template <int PN>
 struct ProjCfg {
   static constexpr int LD = PROJ_BK + 4;
   static constexpr int A_DOUBLES = 128 * LD, B_DOUBLES = PN * LD, V_DOUBLES = 3 * PROJ_BK;
   static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES + V_DOUBLES;
-  static constexpr int SMEM_BYTES = PROJ_STAGES * STAGE_DOUBLES * (int)sizeof(double);
+  static constexpr int STAGES = PN <= 32 ? PROJ_STAGES_MAX : 3;  // 64 modes: three 31 KB stages, so that two CTAs still share an SM
+  static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);
 };
 
 template <int PN>
-__global__ void __launch_bounds__(PROJ_THREADS, PN <= 32 ? 2 : 1)
+__global__ void __launch_bounds__(PROJ_THREADS, 2)
 project_kernel(const double* __restrict__ X, long ldx, int n, int c, const double* __restrict__ elev, int clamp,
                const double* __restrict__ mean, const double* __restrict__ wfull, const double* __restrict__ E, long lde,
                int k_stages_total, int stages_per_split, double* __restrict__ part, long n_pad) {
   using Cfg = ProjCfg<PN>;
-  constexpr int NF = PN / 8, LD = Cfg::LD;
+  constexpr int NF = PN / 8, LD = Cfg::LD, PROJ_STAGES = Cfg::STAGES;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
