@@ -235,15 +235,24 @@ def fit_lockstep(models, method: str, max_iter: int = 100) -> bool:
         pool = _exact_pool(m0.kernel.name, n, d, m0.y.shape[1], m0.device, len(models))
     for mdl, gp in zip(models, pool):
         mdl.bind(gp)
-    if method == "adam":
+    try:
+        if method == "adam":
+            adam_lockstep(models, max_iter)
+            return True
+        for mdl in models:
+            _set_stage(mdl, hypers=False, z=True)
         adam_lockstep(models, max_iter)
+        for mdl in models:
+            _set_stage(mdl, hypers=True, z=False)
+        adam_lockstep(models, max_iter)
+        for mdl in models:
+            _set_stage(mdl, hypers=True, z=True)
         return True
-    for mdl in models:
-        _set_stage(mdl, hypers=False, z=True)
-    adam_lockstep(models, max_iter)
-    for mdl in models:
-        _set_stage(mdl, hypers=True, z=False)
-    adam_lockstep(models, max_iter)
-    for mdl in models:
-        _set_stage(mdl, hypers=True, z=True)
-    return True
+    finally:
+        for mdl in models:
+            mdl._own = None
+        if not isinstance(m0, SparseModel) and n > 2048:
+            # large exact handles (3 n^2 doubles each) are not worth keeping around: give them back
+            for key in [k for k in _MODEL_POOLS if k[0] == threading.get_ident() and k[1] == "exact" and k[3] == n]:
+                for gp in _MODEL_POOLS.pop(key):
+                    gp.close()
