@@ -14,7 +14,7 @@ int launch_grad(cudaStream_t s, const double* Xs, int n, int n_pad, int D, const
   const int nt = n_pad / CT;
   const int tiles = nt * (nt + 1) / 2;
   const int smem = 2 * D * CT_LD * (int)sizeof(double);
-  static bool attr_done[64] = {};
+  static std::atomic<bool> attr_done[64] = {};  // benign if two threads both set the (idempotent) attributes
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev]) {
@@ -507,7 +507,7 @@ int gpras_gp_set_cell_map(gpras_gp* h, const double* e_mean, const double* bias,
   CU(cudaMemcpyAsync(h->E2, sq.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->bias, b.data(), sizeof(double) * h->c_pad, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  static bool attr_done[64] = {};
+  static std::atomic<bool> attr_done[64] = {};  // benign if two threads both set the (idempotent) attributes
   if (h->device < 64 && !attr_done[h->device]) {
     if ((r = opt_in_smem(cells_kernel<32>, CellsCfg<32>::SMEM_BYTES)) || (r = opt_in_smem(cells_kernel<64>, CellsCfg<64>::SMEM_BYTES)))
       return r;

@@ -4,6 +4,7 @@
 #pragma once
 #include "../../include/gpras_b200.h"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,7 +48,7 @@ int opt_in_smem(K kernel, int bytes) {
 }
 
 // cudaFuncSetAttribute is per device; remember which devices were prepared.
-bool g_prepared[64] = {};
+std::atomic<bool> g_prepared[64] = {};
 
 template <int KID>
 int prepare_kid() {

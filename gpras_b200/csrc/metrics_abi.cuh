@@ -83,7 +83,7 @@ int gpras_metrics_create(gpras_metrics** out, int device, int c, long t_capacity
   DeviceGuard guard(device);
   int r;
   if ((r = prepare_device())) return r;
-  static bool attr_done[64] = {};
+  static std::atomic<bool> attr_done[64] = {};  // benign if two threads both set the (idempotent) attributes
   if (device < 64 && !attr_done[device]) {
     if ((r = prepare_metrics_kernels<32>()) || (r = prepare_metrics_kernels<64>())) return r;
     attr_done[device] = true;

@@ -337,7 +337,7 @@ int gpras_pre_create(gpras_pre** out, int device, int c, int hydraulic, double w
   DeviceGuard guard(device);
   int r;
   if ((r = prepare_device())) return r;
-  static bool attr_done[64] = {};
+  static std::atomic<bool> attr_done[64] = {};  // benign if two threads both set the (idempotent) attributes
   if (device < 64 && !attr_done[device]) {
     if ((r = opt_in_smem(project_kernel<8>, ProjCfg<8>::SMEM_BYTES)) || (r = opt_in_smem(project_kernel<16>, ProjCfg<16>::SMEM_BYTES)) ||
         (r = opt_in_smem(project_kernel<32>, ProjCfg<32>::SMEM_BYTES)) || (r = opt_in_smem(project_kernel<64>, ProjCfg<64>::SMEM_BYTES)) ||

@@ -59,7 +59,7 @@ int launch_chain(cudaStream_t s, bool uu, const double* Zs, int m, const double*
                  double* part, int ncols, double* zpart, int m_pad) {
   const int smem = (2 * D * CT_LD + CT * D + 2 * R * CT_LD) * (int)sizeof(double);
   const int grid = tiles_y * tiles_x;
-  static bool attr_done[64] = {};
+  static std::atomic<bool> attr_done[64] = {};  // benign if two threads both set the (idempotent) attributes
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev]) {
