@@ -138,6 +138,56 @@ def make_metrics():
     print("wrote metrics_reference.npz")
 
 
+def make_edge_cases():
+    """CPU-only extras: North's rule on many spectra, and metrics on degenerate events (all dry, ties, a single cell)."""
+    pre, _ = import_reference("gpras.preprocess")
+    met, _ = import_reference("gpras.metrics")
+    from sklearn.decomposition import PCA
+
+    rng = np.random.default_rng(99)
+    out = {}
+    evs, ns, expect = [], [], []
+    for i in range(120):
+        k = int(rng.integers(1, 40))
+        ev = np.sort(rng.gamma(0.7, 6.0, k) + (rng.random() < 0.3) * 1.0)[::-1]
+        n = int(rng.integers(5, 400))
+        fake = PCA()
+        fake.n_samples_, fake.explained_variance_ = n, ev
+        pad = np.full(40, np.nan)
+        pad[:k] = ev
+        try:
+            r = pre.compute_norths_rule(fake)
+        except ValueError:  # the reference takes argmax of an empty array when exactly one eigenvalue exceeds 1
+            r = -1
+        evs.append(pad), ns.append(n), expect.append(r)
+    out["north.eigenvalues"], out["north.n"], out["north.expected"] = np.array(evs), np.array(ns), np.array(expect)
+    cases = {
+        "all_dry": (np.zeros((7, 9)), np.zeros((7, 9)), np.zeros((7, 9))),
+        "ties": (np.tile(np.array([[0.0, 1.0, 1.0, 2.0]]), (5, 1)), np.tile(np.array([[0.5, 1.0, 0.0, 2.0]]), (5, 1)), np.full((5, 4), 0.1)),
+        "one_cell": (rng.random((11, 1)) * 2, rng.random((11, 1)) * 2, rng.random((11, 1))),
+        "never_detected": (np.full((4, 6), 0.1), np.full((4, 6), 0.2), np.full((4, 6), 0.05)),
+    }
+    for name, (x, y, conf) in cases.items():
+        x_mts, y_mts = np.argmax(x, axis=0), np.argmax(y, axis=0)
+        with np.errstate(all="ignore"):
+            vals = dict(
+                x=x, y=y, conf=conf, rmse_aoi_toi=met.rmse_aoi_toi(x, y), mae_aoi_toi=met.mae_aoi_toi(x, y),
+                conf_aoi_toi=met.conf_aoi_toi(conf), rmse_aoi_mts=met.rmse_aoi_mts(x, y, x_mts, y_mts),
+                nse_aoi_mts=met.nse_aoi_mts(x, y, x_mts, y_mts), err_aoi_toi=met.err_aoi_toi(x, y),
+                err_aoi_mts=met.err_aoi_mts(x, y, x_mts, y_mts), fi_aoi_toi_0=met.fi_aoi_toi(x, y, 0, 0),
+                pod_mts=met.pod_mts(x, y, 0.5, x_mts, y_mts), rfa_mts=met.rfa_mts(x, y, 0.5, x_mts, y_mts),
+                csi_mts=met.csi_mts(x, y, 0.5, x_mts, y_mts), f2_mts=met.f2_mts(x, y, 0, x_mts, y_mts),
+                f3_mts=met.f3_mts(x, y, 0, x_mts, y_mts), rmse_aoi_ts=met.rmse_aoi_ts(x, y), err_aoi_ts=met.err_aoi_ts(x, y),
+                conf_aoi_ts=met.conf_aoi_ts(conf), rmse_cell_toi=met.rmse_cell_toi(x, y), err_cell_mts=met.err_cell_mts(x, y, x_mts, y_mts),
+                err_cell_toi=met.err_cell_toi(x, y), conf_cell_toi=met.conf_cell_toi(conf),
+            )
+        for key, val in vals.items():
+            out[f"{name}.{key}"] = np.asarray(val, dtype=np.float64)
+    np.savez_compressed(HERE / "edge_cases_reference.npz", **out)
+    print("wrote edge_cases_reference.npz")
+
+
 if __name__ == "__main__":
     make_preprocess()
     make_metrics()
+    make_edge_cases()

@@ -75,3 +75,47 @@ def test_norths_rule_object_form():
 
     assert compute_norths_rule(Fitted()) == 1
     assert compute_norths_rule(np.array([0.5, 0.2]), 10) == 0
+
+
+# ---- edge cases generated from the reference itself (tests/golden/edge_cases_reference.npz) -----------------------------
+from pathlib import Path
+
+EDGE = np.load(Path(__file__).resolve().parent / "golden" / "edge_cases_reference.npz")
+EDGE_EVENTS = ["all_dry", "ties", "one_cell", "never_detected"]
+
+
+def test_norths_rule_matches_reference_on_random_spectra():
+    evs, ns, expected = EDGE["north.eigenvalues"], EDGE["north.n"], EDGE["north.expected"]
+    from oracle import preprocess as opre
+
+    checked = 0
+    for ev, n, want in zip(evs, ns, expected):
+        ev = ev[~np.isnan(ev)]
+        if want < 0:
+            # the reference raises here (argmax of an empty array when exactly one eigenvalue exceeds 1); the mirror keeps that mode
+            assert compute_norths_rule(ev, int(n)) == 1 and opre.norths_rule(ev, int(n)) == 1
+            continue
+        assert compute_norths_rule(ev, int(n)) == int(want)
+        assert opre.norths_rule(ev, int(n)) == int(want)
+        checked += 1
+    assert checked > 100
+
+
+@pytest.mark.parametrize("name", EDGE_EVENTS)
+def test_degenerate_events_match_reference(name):
+    """All-dry events, ties in the arg-max, a single cell, never-detected peaks: NaNs and the `== 1` branches of f2 / f3 come out
+    exactly as the reference produces them -- for the oracle and for the host closed forms of the device summary."""
+    from oracle import metrics as ometrics
+
+    c = {k[len(name) + 1:]: EDGE[k] for k in EDGE.files if k.startswith(name + ".")}
+    x, y, conf = c["x"], c["y"], c["conf"]
+    with np.errstate(all="ignore"):
+        so = ometrics.summarise(x, y, conf, 0.5, 0.0)
+        sh = gm._summary(*_raw_reductions(x, y, conf, 0.5, 0.0), x.shape[0], x.shape[1])
+    for s in (so, sh):
+        for k in ("rmse_cell_toi", "err_cell_toi", "conf_cell_toi", "err_cell_mts", "rmse_aoi_ts", "err_aoi_ts", "conf_aoi_ts"):
+            np.testing.assert_allclose(s[k], c[k], rtol=1e-12, atol=1e-14, err_msg=k)
+        for k in ("rmse_aoi_toi", "mae_aoi_toi", "conf_aoi_toi", "err_aoi_toi", "rmse_aoi_mts", "err_aoi_mts", "nse_aoi_mts", "pod_mts",
+                  "rfa_mts", "csi_mts", "f2_mts", "f3_mts"):
+            np.testing.assert_allclose(s[k], float(c[k]), rtol=1e-12, atol=1e-14, equal_nan=True, err_msg=k)
+        assert s["fi_aoi_toi"] == float(c["fi_aoi_toi_0"])
