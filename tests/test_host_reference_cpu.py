@@ -119,3 +119,22 @@ def test_degenerate_events_match_reference(name):
                   "rfa_mts", "csi_mts", "f2_mts", "f3_mts"):
             np.testing.assert_allclose(s[k], float(c[k]), rtol=1e-12, atol=1e-14, equal_nan=True, err_msg=k)
         assert s["fi_aoi_toi"] == float(c["fi_aoi_toi_0"])
+
+
+def test_new_mirrors_fail_loudly_without_a_gpu(lib):
+    """No CPU fallback: on a box without a CUDA device every compute entry of the PreProcessor / metrics mirrors raises."""
+    if lib.gpras_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from gpras_b200 import _lib
+
+    with pytest.raises(_lib.GprasError):
+        gm.MetricsAccumulator(10, 5)
+    with pytest.raises(_lib.GprasError):
+        gm.summarise(np.zeros((2, 3)), np.ones((2, 3)))
+    with pytest.raises(_lib.GprasError):
+        PreProcessor().fit(np.random.default_rng(0).random((5, 7)), np.zeros(7), np.ones(7), 2)
+    import ctypes as C
+
+    h = C.c_void_p()
+    assert lib.gpras_pre_create(C.byref(h), 0, 16, 0, 0.03) == -2 and b"no CPU fallback" in lib.gpras_last_error()
+    assert lib.gpras_metrics_create(C.byref(h), 0, 16, 4) == -2 and b"no CPU fallback" in lib.gpras_last_error()
