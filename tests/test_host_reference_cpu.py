@@ -138,3 +138,27 @@ def test_new_mirrors_fail_loudly_without_a_gpu(lib):
     h = C.c_void_p()
     assert lib.gpras_pre_create(C.byref(h), 0, 16, 0, 0.03) == -2 and b"no CPU fallback" in lib.gpras_last_error()
     assert lib.gpras_metrics_create(C.byref(h), 0, 16, 4) == -2 and b"no CPU fallback" in lib.gpras_last_error()
+
+
+def test_host_closed_forms_agree_with_oracle_on_random_events():
+    """Property test (hypothesis): for random event shapes, thresholds and tolerances the host closed forms applied to the raw
+    reductions equal the oracle's whole-array evaluation -- two independent restatements of gpras/metrics.py."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from oracle import metrics as ometrics
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 23), st.integers(1, 37), st.integers(0, 2**31 - 1), st.floats(0.0, 1.5), st.floats(0.0, 0.5))
+    def check(t, c, seed, thr, v_tol):
+        rng = np.random.default_rng(seed)
+        x = np.maximum(rng.standard_normal((t, c)) + 0.3, 0.0)
+        y = np.maximum(x + 0.4 * rng.standard_normal((t, c)), 0.0)
+        conf = rng.random((t, c))
+        with np.errstate(all="ignore"):
+            so = ometrics.summarise(x, y, conf, thr, v_tol)
+            sh = gm._summary(*_raw_reductions(x, y, conf, thr, v_tol), t, c)
+        for k, vo in so.items():
+            np.testing.assert_allclose(sh[k], vo, rtol=1e-11, atol=1e-13, equal_nan=True, err_msg=k)
+
+    check()
