@@ -245,6 +245,7 @@ int gpras_metrics_finalize(gpras_metrics* m, double depth_threshold, double* sca
 int gpras_metrics_fidelity(const double* x, long ldx, const double* y, long ldy, int t, int c, int t_tol, double v_tol, int device,
                            double* matching) {
   if (!x || !y || !matching || t <= 0 || c <= 0 || t_tol < 0) return fail(GPRAS_E_ARG, "bad argument");
+  if (t > 65535) return fail(GPRAS_E_ARG, "more than 65 535 timesteps per call are not supported (one grid row per timestep)");
   if (gpras_device_count() <= device || device < 0) return fail(GPRAS_E_CUDA, "no such CUDA device (no CPU fallback)");
   DeviceGuard guard(device);
   const int bx = (c + 255) / 256;

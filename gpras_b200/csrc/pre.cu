@@ -386,6 +386,7 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
                   int modes, double tol, int max_iter) {
   if (!h || !x || !elevations || !weights || n < 2 || ldx < h->c) return fail(GPRAS_E_ARG, "bad argument");
   if (modes > PRE_MAX_MODES) return fail(GPRAS_E_ARG, "more than 64 spatial modes are not supported");
+  if (n > 65535 - 127) return fail(GPRAS_E_ARG, "more than 65 408 samples are not supported (one grid row per sample)");
   DeviceGuard guard(h->device);
   cudaStream_t s = h->stream;
   const int c = h->c, n_pad = round_up(n, 128);
