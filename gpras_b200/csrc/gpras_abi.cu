@@ -162,6 +162,8 @@ int record_eval(gpras_gp* h, int want_grad) {
 // hundreds (the first evaluation runs eagerly: it creates streams / events and sets kernel attributes).
 int enqueue_eval(gpras_gp* h, const double* theta, int want_grad) {
   if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
+  // the pinned theta staging buffer belongs to the evaluation in flight until it has been fetched
+  if (h->pending) return fail(GPRAS_E_STATE, "an evaluation is already enqueued on this handle: fetch it first");
   cudaStream_t s = h->stream;
   h->conditioned = false;
   memcpy(h->h_theta, theta, sizeof(double) * (2 + h->d));
@@ -386,6 +388,7 @@ int gpras_gp_lml_grad_host(gpras_gp* h, const double* x, const double* y, const 
 int gpras_gp_condition(gpras_gp* h, const double* theta) {
   if (!h || !theta) return fail(GPRAS_E_ARG, "null argument");
   if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
+  if (h->pending) return fail(GPRAS_E_STATE, "an evaluation is already enqueued on this handle: fetch it first");
   DeviceGuard guard(h->device);
   h->launches = 0;
   memcpy(h->h_theta, theta, sizeof(double) * (2 + h->d));

@@ -314,6 +314,8 @@ static int sgpr_record_eval(gpras_sgpr* h, bool want_grad) {
 int gpras_sgpr_elbo_grad_enqueue(gpras_sgpr* h, const double* theta, const double* z, double jitter, int want_grad) {
   if (!h || !theta || !z) return fail(GPRAS_E_ARG, "null argument");
   if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
+  // the pinned staging buffers below belong to the evaluation in flight until it has been fetched
+  if (h->pending) return fail(GPRAS_E_STATE, "an evaluation is already enqueued on this handle: fetch it first");
   DeviceGuard guard(h->device);
   cudaStream_t s = h->stream;
   h->conditioned = false;

@@ -30,6 +30,7 @@ class ExactGP:
         check(self.lib.gpras_gp_create(C.byref(h), device, KERNEL_IDS[kernel], self.n, self.d, self.p))
         self._h = h
         self._keep = []
+        self._cond_theta = None  # theta the handle is conditioned at (factor + alpha resident), or None
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -54,6 +55,7 @@ class ExactGP:
         if tuple(x.shape) != (self.n, self.d) or tuple(y.shape) != (self.n, self.p):
             raise ValueError(f"expected x {(self.n, self.d)} and y {(self.n, self.p)}, got {tuple(x.shape)}, {tuple(y.shape)}")
         self._keep = [x, y]
+        self._cond_theta = None
         check(self.lib.gpras_gp_set_data(self._h, ptr(x), ptr(y), int(on_device)))
 
     def theta_vector(self, variance: float, noise: float, lengthscales) -> np.ndarray:
@@ -70,6 +72,7 @@ class ExactGP:
         theta = _f64(theta)
         lml = C.c_double()
         grad = np.empty(2 + self.d) if want_grad else None
+        self._cond_theta = None
         check(self.lib.gpras_gp_lml_grad(self._h, ptr(theta), C.byref(lml), ptr(grad) if want_grad else None))
         return lml.value, grad
 
@@ -78,11 +81,13 @@ class ExactGP:
         x, y, theta = _f64(x), _f64(y), _f64(theta)
         lml = C.c_double()
         grad = np.empty(2 + self.d)
+        self._cond_theta = None
         check(self.lib.gpras_gp_lml_grad_host(self._h, ptr(x), ptr(y), ptr(theta), C.byref(lml), ptr(grad)))
         return lml.value, grad
 
     def enqueue(self, theta, want_grad: bool = True) -> None:
         theta = _f64(theta)
+        self._cond_theta = None
         check(self.lib.gpras_gp_lml_grad_enqueue(self._h, ptr(theta), int(want_grad)))
 
     def fetch(self):
@@ -92,9 +97,19 @@ class ExactGP:
         return lml.value, grad
 
     # ---- prediction -------------------------------------------------------------------------
-    def condition(self, theta) -> None:
+    def condition(self, theta, force: bool = False) -> None:
+        """Factorise at ``theta`` and keep the factor and alpha resident for ``predict``.  Conditioning again at the theta
+        the handle already holds is free (the reference's second caller predicts once per plan with an unchanged model,
+        ``gpras/preprocess.py:601-606``: that must not cost N^3 per call)."""
         theta = _f64(theta)
+        if not force and self._cond_theta is not None and np.array_equal(theta, self._cond_theta):
+            return
+        self._cond_theta = None
         check(self.lib.gpras_gp_condition(self._h, ptr(theta)))
+        self._cond_theta = theta.copy()
+
+    def conditioned_at(self, theta) -> bool:
+        return self._cond_theta is not None and np.array_equal(_f64(theta), self._cond_theta)
 
     def predict(self, xs):
         """(mean (T, P), var (T, P)) with likelihood noise included (``predict_y``)."""
@@ -164,6 +179,7 @@ class SparseGP:
         h = C.c_void_p()
         check(self.lib.gpras_sgpr_create(C.byref(h), device, KERNEL_IDS[kernel], self.n, self.d, self.m, self.r))
         self._h = h
+        self._cond = None  # (theta, z, jitter) the handle is conditioned at
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -180,6 +196,7 @@ class SparseGP:
         x, y = _f64(x), _f64(y)
         if x.shape != (self.n, self.d) or y.shape != (self.n, self.r):
             raise ValueError(f"expected x {(self.n, self.d)} and y {(self.n, self.r)}, got {x.shape}, {y.shape}")
+        self._cond = None
         check(self.lib.gpras_sgpr_set_data(self._h, ptr(x), ptr(y), 0))
 
     def theta_vector(self, variance: float, noise: float, lengthscales) -> np.ndarray:
@@ -196,6 +213,7 @@ class SparseGP:
         elbo = C.c_double()
         gt = np.empty(2 + self.d) if want_grad else None
         gz = np.empty((self.m, self.d)) if want_grad else None
+        self._cond = None
         check(self.lib.gpras_sgpr_elbo_grad(self._h, ptr(theta), ptr(z), float(jitter), C.byref(elbo),
                                             ptr(gt) if want_grad else None, ptr(gz) if want_grad else None))
         return elbo.value, gt, gz
@@ -205,6 +223,7 @@ class SparseGP:
         theta, z = _f64(theta), _f64(z)
         if z.shape != (self.m, self.d):
             raise ValueError(f"expected inducing inputs {(self.m, self.d)}, got {z.shape}")
+        self._cond = None
         check(self.lib.gpras_sgpr_elbo_grad_enqueue(self._h, ptr(theta), ptr(z), float(jitter), int(want_grad)))
         self._want_grad = bool(want_grad)
 
@@ -216,12 +235,23 @@ class SparseGP:
                                                   ptr(gz) if self._want_grad else None))
         return elbo.value, gt, gz
 
-    def condition(self, theta, z, jitter: float = 1e-6) -> None:
+    def condition(self, theta, z, jitter: float = 1e-6, force: bool = False) -> None:
         theta, z = _f64(theta), _f64(z)
+        if theta.shape != (2 + self.d,):
+            raise ValueError(f"expected theta of length {2 + self.d}, got {theta.shape}")
+        if z.shape != (self.m, self.d):
+            raise ValueError(f"expected inducing inputs {(self.m, self.d)}, got {z.shape}")
+        c = self._cond
+        if not force and c is not None and c[2] == float(jitter) and np.array_equal(c[0], theta) and np.array_equal(c[1], z):
+            return
+        self._cond = None
         check(self.lib.gpras_sgpr_condition(self._h, ptr(theta), ptr(z), float(jitter)))
+        self._cond = (theta.copy(), z.copy(), float(jitter))
 
     def predict(self, xs):
         xs = _f64(xs)
+        if xs.ndim != 2 or xs.shape[1] != self.d:
+            raise ValueError(f"expected (T, {self.d}) test inputs, got {xs.shape}")
         t = xs.shape[0]
         mean, var = np.empty((t, self.r)), np.empty((t, self.r))
         check(self.lib.gpras_sgpr_predict(self._h, ptr(xs), t, ptr(mean), ptr(var)))

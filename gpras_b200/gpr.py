@@ -23,6 +23,7 @@ constrained hyperparameters (``gpr.py:303-305``) counted only while the paramete
 
 from __future__ import annotations
 
+import collections
 import pickle
 import threading
 from pathlib import Path
@@ -80,41 +81,61 @@ def _sigmoid(u):
 
 
 class Parameter:
-    """Positive parameter stored unconstrained: value = softplus(u) + lower."""
+    """Positive parameter stored unconstrained.  ``transform="softplus"`` (GPflow ``positive()``, the reference's
+    parameterisation): value = softplus(u) + lower; ``transform="log"`` (scikit-learn's): value = exp(u) + lower."""
 
-    def __init__(self, value, lower: float = 0.0, prior: str | None = None, trainable: bool = True):
+    def __init__(self, value, lower: float = 0.0, prior: str | None = None, trainable: bool = True, transform: str = "softplus"):
+        if transform not in ("softplus", "log"):
+            raise ValueError(f"unknown transform {transform!r}")
         self.lower = float(lower)
         self.prior = prior  # "LogNormal(0,1)" or None
         self.trainable = trainable
-        self.unconstrained = np.atleast_1d(_softplus_inv(np.asarray(value, np.float64) - self.lower)).astype(np.float64)
+        self.transform = transform
+        self.unconstrained = np.atleast_1d(self._inverse(np.asarray(value, np.float64) - self.lower)).astype(np.float64)
         self._scalar = np.ndim(value) == 0
 
+    def _forward(self, u):
+        return np.exp(u) if self.transform == "log" else _softplus(u)
+
+    def _inverse(self, v):
+        return np.log(v) if self.transform == "log" else _softplus_inv(v)
+
+    def value(self):
+        """Constrained value as an array (always 1-D)."""
+        return self._forward(self.unconstrained) + self.lower
+
     def numpy(self):
-        v = _softplus(self.unconstrained) + self.lower
+        v = self.value()
         return float(v[0]) if self._scalar else v
 
     def assign(self, value) -> None:
         value = np.asarray(value, np.float64)
         self._scalar = value.ndim == 0
-        self.unconstrained = np.atleast_1d(_softplus_inv(value - self.lower)).astype(np.float64)
+        self.unconstrained = np.atleast_1d(self._inverse(value - self.lower)).astype(np.float64)
+
+    def set_transform(self, transform: str) -> None:
+        """Switch the parameterisation, keeping the constrained value."""
+        v = self.value()
+        self.transform = transform
+        self.unconstrained = np.atleast_1d(self._inverse(v - self.lower)).astype(np.float64)
 
     @property
     def size(self) -> int:
         return self.unconstrained.size
 
     def dvalue_du(self):
-        return _sigmoid(self.unconstrained)
+        return np.exp(self.unconstrained) if self.transform == "log" else _sigmoid(self.unconstrained)
 
     def log_prior(self) -> float:
         if self.prior is None:
             return 0.0
-        lv = np.log(_softplus(self.unconstrained) + self.lower)
+        lv = np.log(self.value())
         return float(np.sum(-lv - 0.5 * LOG_2PI - 0.5 * lv * lv))
 
     def dlog_prior_dvalue(self):
         if self.prior is None:
             return np.zeros_like(self.unconstrained)
-        v = _softplus(self.unconstrained) + self.lower
+        v = self.value()
         return -(1.0 + np.log(v)) / v
 
     def __repr__(self) -> str:
@@ -122,15 +143,17 @@ class Parameter:
 
 
 class _Kernel:
-    def __init__(self, name: str, variance, lengthscales):
+    def __init__(self, name: str, variance, lengthscales, transform: str = "softplus"):
         self.name = name
-        self.variance = Parameter(variance, prior="LogNormal(0,1)")
-        self.lengthscales = Parameter(lengthscales, prior="LogNormal(0,1)")
+        self.variance = Parameter(variance, prior="LogNormal(0,1)", transform=transform)
+        self.lengthscales = Parameter(lengthscales, prior="LogNormal(0,1)", transform=transform)
 
 
 class _Likelihood:
-    def __init__(self, variance=1.0):
-        self.variance = Parameter(variance, lower=NOISE_FLOOR, prior="LogNormal(0,1)")
+    def __init__(self, variance=1.0, transform: str = "softplus"):
+        # the 1e-6 floor belongs to GPflow's Gaussian likelihood; scikit-learn's log-space WhiteKernel has none
+        self.variance = Parameter(variance, lower=NOISE_FLOOR if transform == "softplus" else 0.0, prior="LogNormal(0,1)",
+                                  transform=transform)
 
 
 class _Inducing:
@@ -141,7 +164,18 @@ class _Inducing:
         self.trainable = trainable
 
 
-_POOL_CACHE: dict = {}
+# Pools of small-problem handles outlive a GPRAS instance (creating a handle costs ~1 ms and a pool of 16 serves the batched
+# restarts), but not without bound: the cache keeps the most recently used shapes and closes the handles of the rest.
+_POOL_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+_POOL_CACHE_MAX_SHAPES = 4
+
+
+def release_pools() -> None:
+    """Close every pooled device handle of this process (device memory goes back to the driver)."""
+    while _POOL_CACHE:
+        _, ent = _POOL_CACHE.popitem(last=False)
+        for g in ent["gps"]:
+            g.close()
 
 
 class _DeviceSlot:
@@ -175,7 +209,14 @@ class _DeviceSlot:
         # creating a handle costs ~10 ms (pinned + device allocations), so pools for small problems outlive this GPRAS
         # instance in a process-wide cache (<= 100 MB per handle); large ones belong to the slot and are closed with it
         cache = _POOL_CACHE if small else st.setdefault("own_pools", {})
-        ent = cache.setdefault((threading.get_ident(),) + st["key"], {"gps": [], "owner": None})
+        ckey = (threading.get_ident(),) + st["key"]
+        ent = cache.setdefault(ckey, {"gps": [], "owner": None})
+        if small:
+            _POOL_CACHE.move_to_end(ckey)
+            while len(_POOL_CACHE) > _POOL_CACHE_MAX_SHAPES:
+                _, old = _POOL_CACHE.popitem(last=False)
+                for g in old["gps"]:
+                    g.close()
         extra = ent["gps"]
         if not small:
             st["extra"] = extra
@@ -204,12 +245,13 @@ class ExactModel:
     ``kernel.variance / kernel.lengthscales / likelihood.variance / inducing_variable.Z / data /
     trainable_variables / training_loss()`` (``gpr.py:57-62,80-81,88-91,155``)."""
 
-    def __init__(self, kernel_name, x, y, lengthscales, slot: _DeviceSlot, device: int = 0, priors: bool = True):
+    def __init__(self, kernel_name, x, y, lengthscales, slot: _DeviceSlot, device: int = 0, priors: bool = True,
+                 parameterisation: str = "softplus"):
         self.x, self.y = x, y
         self.data = (x, y)
         self.device = device
-        self.kernel = _Kernel(kernel_name, 1.0, lengthscales)
-        self.likelihood = _Likelihood(1.0)
+        self.kernel = _Kernel(kernel_name, 1.0, lengthscales, parameterisation)
+        self.likelihood = _Likelihood(1.0, parameterisation)
         self.inducing_variable = _Inducing(x, trainable=False)
         if not priors:
             self.kernel.variance.prior = self.kernel.lengthscales.prior = self.likelihood.variance.prior = None
@@ -289,7 +331,7 @@ class ExactModel:
         for p, gl in ((self.kernel.variance, np.array([g_var])), (self.likelihood.variance, np.array([g_noise])),
                       (self.kernel.lengthscales, g_ls)):
             if p.trainable:
-                v = _softplus(p.unconstrained) + p.lower
+                v = p.value()
                 dv = gl / v + p.dlog_prior_dvalue()
                 parts.append(-(dv * p.dvalue_du()))
         grad = np.concatenate(parts) if parts else np.zeros(0)
@@ -313,7 +355,7 @@ class ExactModel:
             for k, i in enumerate(chunk):
                 self.set_u(us[i])
                 gps[k].enqueue(self.theta(), want_grad)
-                host.append((self._log_prior(), [(p, _softplus(p.unconstrained) + p.lower, p.dlog_prior_dvalue(), p.dvalue_du())
+                host.append((self._log_prior(), [(p, p.value(), p.dlog_prior_dvalue(), p.dvalue_du())
                                                  for p in self.parameters]))
             for k, i in enumerate(chunk):
                 try:
@@ -344,7 +386,7 @@ class ExactModel:
     # -- prediction --
     def predict_y(self, xs):
         gp = self._slot.acquire(self)
-        gp.condition(self.theta())
+        gp.condition(self.theta())  # free when the handle already holds this model's factor at this theta
         return gp.predict(np.asarray(xs, np.float64))
 
     def parameter_dict(self) -> dict:
@@ -418,14 +460,42 @@ def _optimize_adadelta(model, max_iter: int, learning_rate: float = 0.001) -> fl
     return loss
 
 
-def _optimize_bfgs(model, max_iter: int) -> Any:
-    """SciPy L-BFGS-B over the trainable unconstrained variables, as ``gpflow.optimizers.Scipy`` (``gpr.py:195-203``)."""
+def _optimize_bfgs(model, max_iter: int, *, bounds=None, **scipy_options: Any) -> Any:
+    """SciPy L-BFGS-B over the trainable unconstrained variables, as ``gpflow.optimizers.Scipy`` (``gpr.py:195-203``):
+    ``maxiter`` is the only option the reference sets, so SciPy's defaults (``ftol`` 2.2e-9, ``gtol`` 1e-5) decide when it
+    stops.  Extras: ``bounds`` (on the unconstrained variables, e.g. scikit-learn's log-space box) and any further SciPy
+    option (``ftol``, ``gtol``, ``maxfun`` ...).  A line-search trial point whose covariance matrix is not positive
+    definite makes the search back off instead of aborting the fit (the reference would die in TensorFlow's Cholesky)."""
     from scipy.optimize import minimize
+
+    from ._lib import NotPositiveDefiniteError
 
     u0 = model.get_u()
     if u0.size == 0:
         return None
-    res = minimize(model.loss_and_grad, u0, jac=True, method="L-BFGS-B", options={"maxiter": int(max_iter)})
+
+    good = {}
+
+    def fun(u):
+        try:
+            f, g = model.loss_and_grad(u)
+        except np.linalg.LinAlgError:  # NotPositiveDefiniteError is one
+            if not good:
+                raise  # the start itself is not positive definite: nothing to back off to
+            # A line-search trial point stepped outside the positive-definite region.  Answer with the mirror image of the
+            # last good point's descent (value above it by half the predicted decrease, slope reversed): the line search's
+            # quadratic interpolation then retries at a third of the step instead of aborting the fit.
+            d = u - good["u"]
+            slope = float(good["g"] @ d)
+            nd = float(d @ d)
+            if nd == 0.0 or not slope < 0.0:
+                raise
+            return good["f"] - 0.5 * slope, (-slope / nd) * d
+        if not good or f <= good["f"]:
+            good.update(u=np.array(u, np.float64), f=float(f), g=np.array(g, np.float64))
+        return f, g
+
+    res = minimize(fun, u0, jac=True, method="L-BFGS-B", bounds=bounds, options={"maxiter": int(max_iter), **scipy_options})
     model.set_u(res.x)
     return res
 
@@ -451,7 +521,7 @@ def _optimize_three_stage(model, max_iter: int = 100) -> None:
 
 
 def _optimize_multi_start(model, n_starts: int = 40, iter_initial: int = 20, iter_final: int = 1000, seed=None,
-                          starts=None, pick_best: bool = False, lockstep: bool | None = None) -> None:
+                          starts=None, pick_best: bool = False, lockstep: bool | None = None, train_z: bool = False) -> None:
     """Random restarts with a short Adam run each, then L-BFGS from the selected start (``gpr.py:73-109``).
 
     Faithful to the reference by default: its ``best_loss`` is never assigned (``gpr.py:86,96``), so the LAST
@@ -459,6 +529,9 @@ def _optimize_multi_start(model, n_starts: int = 40, iter_initial: int = 20, ite
     reference's generator is unseeded (``gpr.py:76-77``); ``seed`` / ``starts`` ((R, 3) constrained
     [variance, lengthscale, noise]) make runs reproducible.  ``lockstep`` (default: on for models without trainable
     inducing inputs) advances all starts together so that their device evaluations overlap; the result is identical.
+    The reference overwrites ``model.inducing_variable.Z`` with a raw ndarray (``gpr.py:91,108``), which replaces the GPflow
+    ``Parameter``: from the first redraw on Z is no longer a trainable variable, so Adam and the final L-BFGS move only the
+    three hyperparameters.  That is the default here too; ``train_z=True`` keeps the redrawn Z trainable instead.
     """
     rng = np.random.default_rng(seed)
     x = model.data[0]
@@ -478,6 +551,7 @@ def _optimize_multi_start(model, n_starts: int = 40, iter_initial: int = 20, ite
         model.likelihood.variance.assign(noise0)
         if _has_z(model):
             model.inducing_variable.Z = rng.uniform(mins, maxs, size=model.inducing_variable.Z.shape)
+            model.inducing_variable.trainable = bool(train_z)
         _optimize_adam(model, iter_initial)
         loss = model.training_loss()
         if not pick_best or best_loss is None or loss < best_loss:
@@ -542,10 +616,12 @@ def _multi_start_lockstep(model, rng, n_starts: int, iter_initial: int, starts, 
             np.array(model.inducing_variable.Z))
 
 
-def _optimize_differential_evolutions(model, popsize: int = 15, max_iter: int = 500, seed=None, verbose: bool = False) -> None:
+def _optimize_differential_evolutions(model, popsize: int = 15, max_iter: int = 500, seed=None, verbose: bool = False,
+                                      **de_options: Any) -> None:
     """Adam on Z (3000 its), then SciPy differential evolution over (log10 variance, log10 lengthscale,
     log10 noise) in [-1, 1]^2 x [-3, 0] with the loss as objective (``gpr.py:44-70``).  The reference prints
-    every evaluation (``gpr.py:61``); pass ``verbose=True`` for that."""
+    every evaluation (``gpr.py:61``); pass ``verbose=True`` for that.  Further SciPy options (``polish``, ``tol`` ...) pass
+    through; the defaults are the reference's (it sets none)."""
     from scipy.optimize import differential_evolution
 
     _set_stage(model, hypers=False, z=True)
@@ -565,7 +641,7 @@ def _optimize_differential_evolutions(model, popsize: int = 15, max_iter: int = 
             print(loss)
         return loss
 
-    res = differential_evolution(objective, bounds, popsize=popsize, maxiter=max_iter, seed=seed)
+    res = differential_evolution(objective, bounds, popsize=popsize, maxiter=max_iter, seed=seed, **de_options)
     assign(res.x)
 
 
@@ -608,7 +684,8 @@ class GPRAS:
         ard: bool = False,
         shared_kernel: bool = False,
         priors: bool = True,
-        device: int = 0,
+        parameterisation: Literal["softplus", "log"] = "softplus",
+        device: int | None = None,
         initial_theta: NDArray[Any] | None = None,
         restarts: NDArray[Any] | None = None,
         n_jobs: int = 1,
@@ -619,7 +696,10 @@ class GPRAS:
 
         Keyword-only extensions (defaults reproduce the reference): ``exact`` / ``n_inducing=None`` selects the
         exact GP; ``ard`` one lengthscale per feature; ``shared_kernel`` one hyperparameter set for all columns;
-        ``priors=False`` drops the LogNormal priors (scikit-learn's objective); ``initial_theta``
+        ``priors=False`` drops the LogNormal priors (scikit-learn's objective); ``parameterisation="log"`` optimises
+        log(theta) like scikit-learn instead of GPflow's softplus-unconstrained variables (same optimum, different path and
+        stopping point under SciPy's default tolerances); ``device`` defaults to the current CUDA device (``LOCAL_RANK``
+        under ``torch.distributed``); ``initial_theta``
         ([variance, noise, lengthscale(s)]) overrides the initial values; ``restarts`` ((R, 2 + n_ls) constrained
         start points, column order [variance, noise, lengthscale(s)]) runs the recipe from every start and keeps
         the lowest final loss (sharded across ranks when ``torch.distributed`` is initialised); ``n_jobs > 1``
@@ -633,7 +713,10 @@ class GPRAS:
         self.y = np.asarray(y).astype(np.float64)
         if exact is None:
             exact = n_inducing is None
-        self._opts = dict(exact=exact, ard=ard, shared_kernel=shared_kernel, priors=priors, device=device)
+        if device is None:
+            device = _default_device()
+        self._opts = dict(exact=exact, ard=ard, shared_kernel=shared_kernel, priors=priors, device=device,
+                          parameterisation=parameterisation)
         self._init_models(self.x, self.y, n_inducing, inducing_initializer)
         opt = OPTIMIZERS[optimization_method]  # KeyError on an unknown method, as the reference (gpr.py:272)
         unique = self.models[:1] if (shared_kernel and exact) else self.models
@@ -682,7 +765,8 @@ class GPRAS:
 
     def _init_models(self, x, y, n_inducing, inducing_initializer: InductionInitializerType = "kmeans") -> None:
         """One model per spatial mode with the reference's initial values (``gpr.py:277-308``)."""
-        o = self._opts or dict(exact=n_inducing is None, ard=False, shared_kernel=False, priors=True, device=0)
+        o = dict(exact=n_inducing is None, ard=False, shared_kernel=False, priors=True, device=0, parameterisation="softplus")
+        o.update(self._opts or {})
         if not self.kernel.supported:
             raise NotImplementedError(
                 f"kernel {self.kernel_str!r} cannot be constructed with lengthscales= in the reference either (gpr.py:26-28,298)"
@@ -692,19 +776,19 @@ class GPRAS:
         self.models = []
         if o["exact"]:
             if o["shared_kernel"]:
-                m = ExactModel(self.kernel_str, x, y, ls0, self._slot, o["device"], o["priors"])
+                m = ExactModel(self.kernel_str, x, y, ls0, self._slot, o["device"], o["priors"], o["parameterisation"])
                 self.models = [m] * y.shape[1]
             else:
                 for i in range(y.shape[1]):
                     self.models.append(ExactModel(self.kernel_str, x, np.ascontiguousarray(y[:, i : i + 1]), ls0, self._slot,
-                                                  o["device"], o["priors"]))
+                                                  o["device"], o["priors"], o["parameterisation"]))
             return
         from .sparse import SparseModel
 
         inducing = self._create_inducing(x, int(n_inducing), inducing_initializer)
         for i in range(y.shape[1]):
             self.models.append(SparseModel(self.kernel_str, x, np.ascontiguousarray(y[:, i : i + 1]), inducing.copy(), ls0,
-                                           o["device"], o["priors"]))
+                                           o["device"], o["priors"], o["parameterisation"]))
 
     def _create_inducing(self, x, n_inducing: int, method: InductionInitializerType) -> NDArray[Any]:
         """Inducing-input initialisation (``gpr.py:310-320``): KMeans centres or a per-feature linspace diagonal."""
@@ -759,7 +843,8 @@ class GPRAS:
             d = pickle.load(f)
         inst = cls(d["kernel"])
         inst.x, inst.y = d["data"]["x"], d["data"]["y"]
-        inst._opts = d.get("gpras_b200", dict(exact=False, ard=False, shared_kernel=False, priors=True, device=0))
+        inst._opts = dict(d.get("gpras_b200", dict(exact=False, ard=False, shared_kernel=False, priors=True)))
+        inst._opts["device"] = _default_device()  # the saving process's device index means nothing here
         inst._init_models(inst.x, inst.y, d["n_inducing"], "grid")
         seen = set()
         for ind, params in enumerate(d["models"]):
@@ -769,6 +854,18 @@ class GPRAS:
             seen.add(id(m))
             m.assign_parameters(params)
         return inst
+
+
+def _default_device() -> int:
+    """The CUDA device a fit lands on when the caller names none: torch's current device when torch is loaded and
+    initialised for CUDA (``torch.cuda.set_device(local_rank)`` under torchrun), else ``LOCAL_RANK``, else 0."""
+    import os
+    import sys
+
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+        return int(torch.cuda.current_device())
+    return int(os.environ.get("LOCAL_RANK", "0"))
 
 
 def _assign_theta(model, theta) -> None:

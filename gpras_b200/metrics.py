@@ -170,9 +170,50 @@ def summarise(x, y, conf=None, depth_threshold: float = 0.5, v_tol: float = 0.0,
         acc.close()
 
 
-def _peaks(x, y, x_mts, y_mts, depth_threshold=0.5) -> Summary:
-    # x_mts / y_mts (cached arg-max rows, metrics.py:35-36) are accepted for signature parity; x[argmax x] == max x.
-    return summarise(x, y, None, depth_threshold)
+def _gather_rows(a, rows) -> np.ndarray:
+    """``a[rows, arange(cells)]`` on the host (``a``: NumPy array or CUDA tensor) -- O(cells) work."""
+    rows = np.asarray(rows).astype(np.int64)
+    if _is_device(a):
+        import torch
+
+        r = torch.as_tensor(rows, device=a.device)
+        return a[r, torch.arange(a.shape[1], device=a.device)].double().cpu().numpy()
+    a = np.asarray(a)
+    return np.asarray(a[rows, np.arange(a.shape[1])], np.float64)
+
+
+def _peak_metrics(xp, yp, depth_threshold) -> dict:
+    """Every ``*_mts`` metric of ``gpras/metrics.py:111-318`` as a closed form of the two per-cell peak vectors
+    ``xp = x[x_mts, cells]`` and ``yp = y[y_mts, cells]``; ``depth_threshold`` is a scalar or, in the reference's own
+    call of f2 / f3 (``metrics.py:53-54``), a per-cell vector."""
+    xp, yp = np.asarray(xp, np.float64), np.asarray(yp, np.float64)
+    thr = np.asarray(depth_threshold, np.float64)
+    diff = xp - yp
+    out = {"err_cell_mts": diff, "rmse_aoi_mts": float(np.sqrt(np.mean(diff**2))), "err_aoi_mts": float(np.mean(diff))}
+    a = np.float64(np.sum((xp >= thr) & (yp >= thr)))
+    b = np.float64(np.sum((xp < thr) & (yp >= thr)))   # false alarms
+    c = np.float64(np.sum((xp >= thr) & (yp < thr)))   # misses
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out["nse_aoi_mts"] = float(1.0 - np.float64(np.sum(diff**2)) / np.float64(np.sum((xp - xp.mean()) ** 2)))
+        pod, rfa = a / (a + c), b / (a + b)
+        out["pod_mts"], out["rfa_mts"] = float(pod), float(rfa)
+        out["csi_mts"] = float(1.0 / ((1.0 / pod) + (1.0 / (1.0 - rfa)) - 1.0))
+    den = a + b + c
+    out["f2_mts"] = 1 if den == 0 else float((a - c) / den)
+    out["f3_mts"] = 1 if den == 0 else float((a - b) / den)
+    return out
+
+
+def _peaks(x, y, x_mts, y_mts, depth_threshold=0.5) -> dict:
+    """Peak metrics.  With no rows supplied the peaks are the per-cell maxima of the device pass (``x[argmax x] == max x``);
+    caller-supplied ``x_mts`` / ``y_mts`` (``metrics.py:35-36`` caches the arg-max rows, but any rows are legal) are honoured
+    by gathering those rows."""
+    if x_mts is None and y_mts is None and np.ndim(depth_threshold) == 0:
+        return summarise(x, y, None, float(depth_threshold))
+    s = summarise(x, y) if (x_mts is None or y_mts is None) else None
+    xp = s["cell_max_x"] if x_mts is None else _gather_rows(x, x_mts)
+    yp = s["cell_max_y"] if y_mts is None else _gather_rows(y, y_mts)
+    return _peak_metrics(xp, yp, depth_threshold)
 
 
 # ---- the reference's function set (gpras/metrics.py:85-324) -----------------------------------------------------------
@@ -259,26 +300,12 @@ def csi_mts(x, y, depth_threshold: float = 0, x_mts=None, y_mts=None) -> float:
     return _peaks(x, y, x_mts, y_mts, depth_threshold)["csi_mts"]
 
 
-def _f_counts(x, y, depth_threshold):
-    """hits / false alarms / misses of the per-cell peaks at a scalar or per-cell threshold (``metrics.py:265-324``;
-    ``export_metric_summary`` passes ``x_mts`` positionally as the threshold, ``metrics.py:53-54``)."""
-    s = summarise(x, y)
-    xm, ym = s["cell_max_x"], s["cell_max_y"]
-    thr = np.asarray(depth_threshold, np.float64)
-    a = float(np.sum((xm >= thr) & (ym >= thr)))
-    b = float(np.sum((xm < thr) & (ym >= thr)))
-    c = float(np.sum((xm >= thr) & (ym < thr)))
-    return a, b, c
-
-
 def f2_mts(x, y, depth_threshold=0, x_mts=None, y_mts=None) -> float:
-    a, b, c = _f_counts(x, y, depth_threshold)
-    return 1 if a + b + c == 0 else float((a - c) / (a + b + c))
+    return _peaks(x, y, x_mts, y_mts, depth_threshold)["f2_mts"]
 
 
 def f3_mts(x, y, depth_threshold=0, x_mts=None, y_mts=None) -> float:
-    a, b, c = _f_counts(x, y, depth_threshold)
-    return 1 if a + b + c == 0 else float((a - b) / (a + b + c))
+    return _peaks(x, y, x_mts, y_mts, depth_threshold)["f3_mts"]
 
 
 def export_metric_summary(x_all, y_all, conf_all, out_path, depth_threshold: float = 0.5, t_tol: int = 0, v_tol: float = 0,
@@ -295,18 +322,18 @@ def export_metric_summary(x_all, y_all, conf_all, out_path, depth_threshold: flo
         s = summarise(x, y, conf, depth_threshold, v_tol)
         fi = s["fi_aoi_toi"] if t_tol == 0 else fi_aoi_toi(x, y, t_tol, v_tol)
         vel = hydraulic_parameter == "velocity"
-        x_mts = np.argmax(x, axis=0)  # the reference hands the arg-max rows to f2 / f3 as their threshold (metrics.py:53-54)
-        a, b, c = (float(np.sum(m)) for m in (
-            (s["cell_max_x"] >= x_mts) & (s["cell_max_y"] >= x_mts), (s["cell_max_x"] < x_mts) & (s["cell_max_y"] >= x_mts),
-            (s["cell_max_x"] >= x_mts) & (s["cell_max_y"] < x_mts)))
-        den = a + b + c
+        # The reference calls f2_mts(x, y, x_mts, y_mts) POSITIONALLY (metrics.py:53-54): the arg-max rows of x land in
+        # `depth_threshold` and those of y in the `x_mts` parameter, so the "truth peak" is x at the row of y's maximum and the
+        # threshold is the row index of x's maximum.  Reproduced as is (two O(T C) host arg-max passes, like the reference).
+        x_rows, y_rows = np.argmax(x, axis=0), np.argmax(y, axis=0)
+        f23 = _peak_metrics(_gather_rows(x, y_rows), s["cell_max_y"], x_rows)
         all_scalar.append(pd.DataFrame.from_dict({
             "event": event, "rmse_aoi_toi": [s["rmse_aoi_toi"]], "mae_aoi_toi": [s["mae_aoi_toi"]],
             "conf_aoi_toi": [s["conf_aoi_toi"]], "rmse_aoi_mts": [s["rmse_aoi_mts"]], "nse_aoi_mts": [s["nse_aoi_mts"]],
             "err_aoi_toi": [s["err_aoi_toi"]], "err_aoi_mts": [s["err_aoi_mts"]], "fi_aoi_toi": [fi],
             "pod_mts": [np.nan if vel else s["pod_mts"]], "rfa_mts": [np.nan if vel else s["rfa_mts"]],
             "csi_mts": [np.nan if vel else s["csi_mts"]],
-            "f2_mts": [1 if den == 0 else (a - c) / den], "f3_mts": [1 if den == 0 else (a - b) / den],
+            "f2_mts": [f23["f2_mts"]], "f3_mts": [f23["f3_mts"]],
         }))
         all_timeseries.append(pd.DataFrame.from_dict({
             "event": np.repeat(event, x.shape[0]), "timestep": tsteps, "rmse_aoi_ts": s["rmse_aoi_ts"],

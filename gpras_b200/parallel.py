@@ -66,26 +66,53 @@ def all_gather_rows(local: np.ndarray, n_cols: int) -> np.ndarray:
 def run_restarts(model, opt, starts: np.ndarray, opt_kwargs: dict) -> np.ndarray:
     """Run recipe ``opt`` from every start (rows of constrained [variance, noise, lengthscale(s)]), sharded
     round-robin over ranks; every rank ends with the parameters of the lowest final loss (ties -> lowest
-    restart index).  Returns the gathered table with rows [restart, loss, theta...] sorted by restart."""
+    restart index).  Returns the gathered table with rows [restart, loss, theta...] sorted by restart.
+
+    Every restart begins from the same state: the start's hyperparameters, the model's INITIAL inducing inputs and
+    trainable flags (the Z-training recipes move Z, and "diffential_evolution" leaves the hyperparameters frozen), and the
+    winner's inducing inputs travel with its hyperparameters, so the model every rank ends with is the one whose loss is
+    reported.  A start whose covariance matrix is not positive definite (the reference's ranges reach noise 1e-3 with
+    lengthscales of 10, ``gpr.py:88-90``) scores ``+inf`` instead of aborting the whole fit."""
+    from ._lib import NotPositiveDefiniteError
     from .gpr import _assign_theta
 
     rank, world, _ = dist_info()
     n_theta = starts.shape[1]
+    nls = n_theta - 2
+    has_z = bool(getattr(model, "supports_z_training", False))
+    z0 = np.array(model.inducing_variable.Z, np.float64) if has_z else np.zeros((0, 0))
+    z_trainable0 = bool(model.inducing_variable.trainable) if has_z else False
+    flags0 = [p.trainable for p in model.parameters]
+    width = 2 + n_theta + z0.size
     rows = []
     for r in shard_indices(starts.shape[0], rank, world):
         _assign_theta(model, starts[r])
-        opt(model, **opt_kwargs)
-        loss = model.training_loss()
-        th = model.theta()
-        nls = n_theta - 2
-        rows.append(np.concatenate([[float(r), float(loss)], th[: 2 + nls]]))
-    table = all_gather_rows(np.array(rows).reshape(-1, 2 + n_theta), 2 + n_theta)
+        for p, f in zip(model.parameters, flags0):
+            p.trainable = f
+        if has_z:
+            model.inducing_variable.Z = z0.copy()
+            model.inducing_variable.trainable = z_trainable0
+        try:
+            opt(model, **opt_kwargs)
+            loss = float(model.training_loss())
+        except np.linalg.LinAlgError:  # NotPositiveDefiniteError is one
+            loss = float("inf")
+        z = np.asarray(model.inducing_variable.Z, np.float64).ravel() if has_z else np.zeros(0)
+        rows.append(np.concatenate([[float(r), loss], model.theta()[: 2 + nls], z]))
+    table = all_gather_rows(np.array(rows).reshape(-1, width), width)
     table = table[np.argsort(table[:, 0], kind="stable")]
     finite = np.where(np.isfinite(table[:, 1]), table[:, 1], np.inf)
     best = int(np.argmin(finite))
-    _assign_theta(model, table[best, 2:])
-    model.restart_table = table
-    return table
+    for p, f in zip(model.parameters, flags0):
+        p.trainable = f
+    _assign_theta(model, table[best, 2 : 2 + n_theta])
+    if has_z:
+        model.inducing_variable.Z = table[best, 2 + n_theta :].reshape(z0.shape).copy()
+        model.inducing_variable.trainable = z_trainable0
+    model.restart_table = table[:, : 2 + n_theta]
+    if not np.isfinite(finite[best]):
+        raise NotPositiveDefiniteError("every restart ended at a hyperparameter vector whose covariance matrix is not positive definite")
+    return model.restart_table
 
 
 def predict_sharded(gpras, x: np.ndarray):

@@ -14,7 +14,7 @@ import threading
 import numpy as np
 
 from .engine import SparseGP
-from .gpr import _Inducing, _Kernel, _Likelihood, _softplus
+from .gpr import _Inducing, _Kernel, _Likelihood
 
 JITTER = 1e-6  # gpflow.config.default_jitter()
 
@@ -39,12 +39,13 @@ def release_other_threads() -> None:
 class SparseModel:
     supports_z_training = True
 
-    def __init__(self, kernel_name, x, y, z, lengthscales, device: int = 0, priors: bool = True):
+    def __init__(self, kernel_name, x, y, z, lengthscales, device: int = 0, priors: bool = True,
+                 parameterisation: str = "softplus"):
         self.x, self.y = x, y
         self.data = (x, y)
         self.device = device
-        self.kernel = _Kernel(kernel_name, 1.0, lengthscales)
-        self.likelihood = _Likelihood(1.0)
+        self.kernel = _Kernel(kernel_name, 1.0, lengthscales, parameterisation)
+        self.likelihood = _Likelihood(1.0, parameterisation)
         self.inducing_variable = _Inducing(z, trainable=True)
         if not priors:
             self.kernel.variance.prior = self.kernel.lengthscales.prior = self.likelihood.variance.prior = None
@@ -136,7 +137,7 @@ class SparseModel:
         for p, gl in ((self.kernel.variance, np.array([gt[0]])), (self.likelihood.variance, np.array([gt[1]])),
                       (self.kernel.lengthscales, g_ls)):
             if p.trainable:
-                v = _softplus(p.unconstrained) + p.lower
+                v = p.value()
                 parts.append(-((gl / v + p.dlog_prior_dvalue()) * p.dvalue_du()))
         if self.inducing_variable.trainable:
             parts.append(-gz.ravel())
@@ -203,8 +204,16 @@ def adam_lockstep(models, max_iter: int, learning_rate: float = 0.001) -> None:
         for i in active:
             models[i].enqueue_loss_and_grad(u[i])
         still = []
-        for i in active:
-            loss, g = models[i].fetch_loss_and_grad()
+        for k, i in enumerate(active):
+            try:
+                loss, g = models[i].fetch_loss_and_grad()
+            except Exception:
+                for j in active[k + 1:]:  # leave no evaluation pending on the other handles
+                    try:
+                        models[j].fetch_loss_and_grad()
+                    except Exception:
+                        pass
+                raise
             mom[i] = b1 * mom[i] + (1.0 - b1) * g
             vel[i] = b2 * vel[i] + (1.0 - b2) * g * g
             alpha = learning_rate * np.sqrt(1.0 - b2**t) / (1.0 - b1**t)

@@ -31,7 +31,7 @@ def met_golden():
 
 
 PRE_CASES = ["wse_fixed", "depth_fixed", "wse_north", "velocity"]
-MET_CASES = ["small", "ragged", "one_step"]
+MET_CASES = ["small", "ragged", "one_step", "peaks_differ"]
 
 
 def sub(npz, name):

@@ -104,7 +104,7 @@ def make_preprocess():
     print("wrote preprocess_reference.npz; stubbed:", stubbed)
 
 
-METRIC_CASES = [("small", 30, 50, 31), ("ragged", 17, 131, 32), ("one_step", 1, 40, 33)]
+METRIC_CASES = [("small", 30, 50, 31), ("ragged", 17, 131, 32), ("one_step", 1, 40, 33), ("peaks_differ", 9, 23, 34)]
 
 
 def make_metrics():
@@ -114,6 +114,11 @@ def make_metrics():
         rng = np.random.default_rng(seed)
         x = np.maximum(rng.standard_normal((t, c)) + 0.4, 0.0)               # "truth" depths, many exact zeros
         y = np.maximum(x + 0.3 * rng.standard_normal((t, c)), 0.0)           # predicted depths
+        if name == "peaks_differ":
+            # prediction lags the truth by a few timesteps, so the arg-max rows of x and y differ in most cells, and depths of
+            # 0..8 straddle the per-cell thresholds argmax(x) in 0..8 that export_metric_summary hands to f2 / f3
+            x = np.maximum(4.0 * rng.random((t, c)) ** 2 + 4.0 * (np.arange(t)[:, None] == rng.integers(0, t, c)[None, :]), 0.0)
+            y = np.maximum(np.roll(x, 2, axis=0) * rng.uniform(0.6, 1.4, (t, c)), 0.0)
         conf = rng.uniform(0.01, 0.4, (t, c))
         thr, t_tol, v_tol = 0.5, min(2, t - 1), 0.1
         x_mts, y_mts = np.argmax(x, axis=0), np.argmax(y, axis=0)
@@ -132,8 +137,45 @@ def make_metrics():
             rmse_cell_toi=met.rmse_cell_toi(x, y), err_cell_mts=met.err_cell_mts(x, y, x_mts, y_mts),
             err_cell_toi=met.err_cell_toi(x, y), conf_cell_toi=met.conf_cell_toi(conf), x_mts=x_mts, y_mts=y_mts,
         )
+        # the *_mts functions with caller-supplied rows that are NOT the arg-max rows (drawn after everything above, so the
+        # earlier cases keep their values)
+        xr, yr = rng.integers(0, t, c), rng.integers(0, t, c)
+        with np.errstate(all="ignore"):
+            vals.update(
+                rows_x=xr, rows_y=yr, rows_rmse_aoi_mts=met.rmse_aoi_mts(x, y, xr, yr), rows_nse_aoi_mts=met.nse_aoi_mts(x, y, xr, yr),
+                rows_err_aoi_mts=met.err_aoi_mts(x, y, xr, yr), rows_err_cell_mts=met.err_cell_mts(x, y, xr, yr),
+                rows_pod_mts=met.pod_mts(x, y, thr, xr, yr), rows_rfa_mts=met.rfa_mts(x, y, thr, xr, yr),
+                rows_csi_mts=met.csi_mts(x, y, thr, xr, yr), rows_f2_mts=met.f2_mts(x, y, thr, xr, yr),
+                rows_f3_mts=met.f3_mts(x, y, thr, xr, yr),
+            )
         for key, val in vals.items():
             out[f"{name}.{key}"] = np.asarray(val)
+    # the reference's export_metric_summary itself, on two events whose truth / prediction peaks fall on different rows
+    import sqlite3
+    import tempfile
+
+    import pandas as pd
+
+    rng = np.random.default_rng(35)
+    t, c = 12, 37
+    idx = pd.MultiIndex.from_product([["e1", "e2"], range(t)], names=["event", "t"])
+    cols = [f"c{i}" for i in range(c)]
+    xv = 3.0 * rng.random((2 * t, c)) ** 2
+    yv = np.maximum(np.roll(xv, 1, axis=0) * rng.uniform(0.5, 1.5, (2 * t, c)), 0.0)
+    cv = rng.uniform(0.1, 0.3, (2 * t, c))
+    with tempfile.TemporaryDirectory() as tmp:
+        db = Path(tmp) / "m.db"
+        met.export_metric_summary(pd.DataFrame(xv, index=idx, columns=cols), pd.DataFrame(yv, index=idx, columns=cols),
+                                  pd.DataFrame(cv, index=idx, columns=cols), db, depth_threshold=0.5, t_tol=1, v_tol=0.05)
+        with sqlite3.connect(db) as con:
+            sc = pd.read_sql("select * from scalar_metrics", con)
+            ts = pd.read_sql("select * from timeseries_metrics", con)
+            ce = pd.read_sql("select * from cell_metrics", con)
+    out["export.x"], out["export.y"], out["export.conf"] = xv, yv, cv
+    out["export.scalar_columns"] = np.array(list(sc.columns))
+    out["export.scalar"] = sc.drop(columns=["event"]).to_numpy(np.float64)
+    out["export.timeseries"] = ts.drop(columns=["event", "timestep"]).to_numpy(np.float64)
+    out["export.cells"] = ce.drop(columns=["event", "cell_id"]).to_numpy(np.float64)
     np.savez_compressed(HERE / "metrics_reference.npz", **out)
     print("wrote metrics_reference.npz")
 
@@ -188,6 +230,12 @@ def make_edge_cases():
 
 
 if __name__ == "__main__":
-    make_preprocess()
-    make_metrics()
-    make_edge_cases()
+    import sys
+
+    which = sys.argv[1:] or ["preprocess", "metrics", "edge"]
+    if "preprocess" in which:
+        make_preprocess()
+    if "metrics" in which:
+        make_metrics()
+    if "edge" in which:
+        make_edge_cases()

@@ -67,6 +67,20 @@ def test_reference_function_set(cuda, met_golden, name):
     np.testing.assert_allclose(gm.f3_mts(x, y, 0, xm, ym), float(c["f3_mts"]), **tol)
     np.testing.assert_allclose(gm.f2_mts(x, y, xm, ym), float(c["f2_mts_as_called"]), **tol)
     np.testing.assert_allclose(gm.f3_mts(x, y, xm, ym), float(c["f3_mts_as_called"]), **tol)
+    # caller-supplied rows that are not the arg-max rows are honoured (gpras/metrics.py:111-318 index with them)
+    xr, yr = c["rows_x"], c["rows_y"]
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(gm.rmse_aoi_mts(x, y, xr, yr), float(c["rows_rmse_aoi_mts"]), **tol)
+        np.testing.assert_allclose(gm.nse_aoi_mts(x, y, xr, yr), float(c["rows_nse_aoi_mts"]), **tol)
+        np.testing.assert_allclose(gm.err_aoi_mts(x, y, xr, yr), float(c["rows_err_aoi_mts"]), **tol)
+        np.testing.assert_allclose(gm.err_cell_mts(x, y, xr, yr), c["rows_err_cell_mts"], **tol)
+        np.testing.assert_allclose(gm.pod_mts(x, y, thr, xr, yr), float(c["rows_pod_mts"]), **tol)
+        np.testing.assert_allclose(gm.rfa_mts(x, y, thr, xr, yr), float(c["rows_rfa_mts"]), **tol)
+        np.testing.assert_allclose(gm.csi_mts(x, y, thr, xr, yr), float(c["rows_csi_mts"]), **tol)
+        np.testing.assert_allclose(gm.f2_mts(x, y, thr, xr, yr), float(c["rows_f2_mts"]), **tol)
+        np.testing.assert_allclose(gm.f3_mts(x, y, thr, xr, yr), float(c["rows_f3_mts"]), **tol)
+        # only one side supplied: the other comes from the device pass
+        np.testing.assert_allclose(gm.err_cell_mts(x, y, xr, None), gm._gather_rows(x, xr) - y.max(axis=0), **tol)
 
 
 @pytest.mark.parametrize("t,c,blocks", [(333, 1000, 1), (2500, 777, 3), (70, 40000, 2)])
@@ -181,6 +195,32 @@ def test_export_metric_summary_tables(cuda, tmp_path):
     np.testing.assert_allclose(sc.rmse_aoi_toi[0], np.sqrt((e1 ** 2).mean()), rtol=1e-12)
     np.testing.assert_allclose(ts.err_aoi_ts[:12], e1.mean(axis=1), rtol=1e-11, atol=1e-14)
     np.testing.assert_allclose(ce.rmse_cell_toi[:37], np.sqrt((e1 ** 2).mean(axis=0)), rtol=1e-12)
+
+
+def test_export_metric_summary_matches_the_reference_export(cuda, met_golden, tmp_path):
+    """All three sqlite tables against the reference's own export_metric_summary run on the same frames (golden), including its
+    positional f2 / f3 call (gpras/metrics.py:53-54) on events whose truth and prediction peak on different rows, t_tol > 0."""
+    import sqlite3
+
+    import pandas as pd
+
+    from gpras_b200 import metrics as gm
+
+    g = sub(met_golden, "export")
+    t, c = 12, 37
+    idx = pd.MultiIndex.from_product([["e1", "e2"], range(t)], names=["event", "t"])
+    cols = [f"c{i}" for i in range(c)]
+    frames = [pd.DataFrame(g[k], index=idx, columns=cols) for k in ("x", "y", "conf")]
+    out = tmp_path / "m.db"
+    gm.export_metric_summary(*frames, out, depth_threshold=0.5, t_tol=1, v_tol=0.05)
+    with sqlite3.connect(out) as con:
+        sc = pd.read_sql("select * from scalar_metrics", con)
+        ts = pd.read_sql("select * from timeseries_metrics", con)
+        ce = pd.read_sql("select * from cell_metrics", con)
+    assert list(sc.columns) == [str(v) for v in g["scalar_columns"]]
+    np.testing.assert_allclose(sc.drop(columns=["event"]).to_numpy(np.float64), g["scalar"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(ts.drop(columns=["event", "timestep"]).to_numpy(np.float64), g["timeseries"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(ce.drop(columns=["event", "cell_id"]).to_numpy(np.float64), g["cells"], rtol=1e-12, atol=1e-14)
 
 
 def test_full_size_properties_cfg5_block(cuda):

@@ -8,7 +8,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from gpras_b200 import _lib, gpr
+from gpras_b200 import _lib, gpr, sparse
 from gpras_b200.synth import make_gp_data
 from oracle.exact_gp import Objective, Theta, lml_and_grad
 
@@ -31,9 +31,34 @@ class OracleBackedModel(gpr.ExactModel):
             lml, gv, gn, gl = lml_and_grad(m.kernel.name, m.x, m.y, Theta(theta[0], theta[1], theta[2:]), want_grad=want_grad)
             return lml, (np.concatenate([[gv, gn], gl]) if want_grad else None)
 
-    def __init__(self, kernel_name, x, y, lengthscales, priors=True):
-        super().__init__(kernel_name, x, y, lengthscales, slot=None, priors=priors)
+    def __init__(self, kernel_name, x, y, lengthscales, priors=True, parameterisation="softplus"):
+        super().__init__(kernel_name, x, y, lengthscales, slot=None, priors=priors, parameterisation=parameterisation)
         self._slot = OracleBackedModel._Slot(self)
+
+
+class OracleBackedSparseModel(sparse.SparseModel):
+    """SparseModel whose device evaluation is replaced by the torch-CPU SGPR oracle (autograd).  Test infrastructure only."""
+
+    class _GP:
+        def __init__(self, outer):
+            self.outer = outer
+
+        def elbo_grad(self, theta, z, jitter=1e-6, want_grad=True):
+            import torch
+
+            from oracle import sgpr
+
+            m = self.outer
+            t = lambda a, g=False: torch.tensor(np.asarray(a, np.float64), requires_grad=g)  # noqa: E731
+            tv, tn, tl, tz = t(theta[0], want_grad), t(theta[1], want_grad), t(theta[2:], want_grad), t(z, want_grad)
+            e = sgpr.elbo(m.kernel.name, t(m.x), t(m.y), tz, tv, tl, tn, jitter)
+            if not want_grad:
+                return float(e), None, None
+            gv, gn, gl, gz = torch.autograd.grad(e, [tv, tn, tl, tz])
+            return float(e.detach()), np.concatenate([[float(gv) * theta[0], float(gn) * theta[1]], gl.numpy() * theta[2:]]), gz.numpy()
+
+    def _gp(self):
+        return OracleBackedSparseModel._GP(self)
 
 
 def test_module_surface_matches_reference():
@@ -188,3 +213,110 @@ def test_multi_start_lockstep_equals_sequential(pick_best):
         gpr._optimize_multi_start(m, n_starts=5, iter_initial=6, iter_final=8, seed=3, pick_best=pick_best, lockstep=lock)
         res.append(np.concatenate([m.theta(), [m.training_loss()]]))
     np.testing.assert_array_equal(res[0], res[1])
+
+
+# ---- round-2 host logic ----------------------------------------------------------------------
+def test_log_parameterisation_matches_sklearn_style_objective():
+    """parameterisation="log" is scikit-learn's variable: theta = exp(u), no floor on the noise, no priors."""
+    d = make_gp_data(50, 3, 2, seed=4)
+    for ard in (False, True):
+        ls0 = np.full(3, 1.4) if ard else 1.4
+        m = OracleBackedModel("Matern32", d.x, d.y, ls0, priors=False, parameterisation="log")
+        m.kernel.variance.assign(0.8)
+        m.likelihood.variance.assign(0.03)
+        np.testing.assert_allclose(m.get_u(), np.log(np.concatenate([[0.8, 0.03], np.atleast_1d(ls0)])), rtol=1e-15)
+        loss, g = m.loss_and_grad()
+        obj = Objective("Matern32", d.x, d.y, ard=ard, space="log", priors=False)
+        f, go = obj(np.log(np.concatenate([[0.8, 0.03], np.atleast_1d(ls0)])))
+        assert abs(loss - f) <= 1e-13 * abs(f)
+        np.testing.assert_allclose(g, go, rtol=1e-12, atol=1e-13)
+    # same optimum from the same start as the oracle-driven SciPy run, bounds passed through
+    m = OracleBackedModel("RBF", d.x, d.y, 1.0, priors=False, parameterisation="log")
+    bounds = [(-11.5, 11.5)] * 3
+    gpr._optimize_bfgs(m, 200, bounds=bounds)
+    from scipy.optimize import minimize
+
+    obj = Objective("RBF", d.x, d.y, ard=False, space="log", priors=False)
+    r = minimize(obj, np.zeros(3), jac=True, method="L-BFGS-B", bounds=bounds, options={"maxiter": 200})
+    np.testing.assert_allclose(m.get_u(), r.x, rtol=1e-10)
+
+
+def test_bfgs_survives_a_non_positive_definite_trial_point():
+    class Wall(OracleBackedModel):
+        calls = 0
+
+        def loss_and_grad(self, u=None):
+            Wall.calls += 1
+            if Wall.calls == 2:  # the first line-search trial point
+                raise _lib.NotPositiveDefiniteError("pivot 3")
+            return super().loss_and_grad(u)
+
+    d = make_gp_data(40, 2, 1, seed=2)
+    m = Wall("RBF", d.x, d.y, 1.0)
+    before = m.training_loss()
+    res = gpr._optimize_bfgs(m, 30)
+    assert np.isfinite(res.fun) and m.training_loss() < before
+
+
+def test_run_restarts_scores_bad_starts_inf_and_keeps_z_with_theta():
+    from gpras_b200 import parallel
+
+    d = make_gp_data(60, 2, 1, seed=5)
+    z0 = d.x[:6].copy()
+    m = OracleBackedSparseModel("RBF", d.x, d.y, z0.copy(), 1.0)
+    starts = np.array([[1.0, 0.1, 1.0], [0.5, 0.3, 2.0], [2.0, 0.05, 0.6]])
+    seen_z, seen_flags = [], []
+
+    def recipe(model, max_iter):
+        seen_z.append(np.array(model.inducing_variable.Z))
+        seen_flags.append((model.inducing_variable.trainable, [p.trainable for p in model.parameters]))
+        if len(seen_z) == 2:
+            raise _lib.NotPositiveDefiniteError("pivot 1")
+        gpr._optimize_two_stage(model, max_iter)
+        model.set_trainable(False)  # like the reference's DE recipe, which leaves the hyperparameters frozen (gpr.py:48-49)
+
+    table = parallel.run_restarts(m, recipe, starts, dict(max_iter=4))
+    for z, fl in zip(seen_z, seen_flags):  # every restart begins from the initial Z and trainable flags
+        np.testing.assert_array_equal(z, z0)
+        assert fl == (True, [True, True, True])
+    assert np.isinf(table[1, 1]) and np.all(np.isfinite(table[[0, 2], 1]))
+    best = int(np.argmin(table[:, 1]))
+    assert best != 1
+    # the model ends with the winner's theta AND the winner's Z: its loss is the reported one
+    np.testing.assert_allclose(m.theta()[:3], table[best, 2:5], rtol=1e-14)
+    assert not np.array_equal(m.inducing_variable.Z, z0)
+    assert all(p.trainable for p in m.parameters) and m.inducing_variable.trainable  # flags restored after the last restart
+    m.set_trainable(False)  # the table's losses were taken in the state the recipe left (priors count on trainable parameters only)
+    np.testing.assert_allclose(m.training_loss(), table[best, 1], rtol=1e-10)
+    with pytest.raises(np.linalg.LinAlgError):
+        def always_bad(model, **kw):
+            raise _lib.NotPositiveDefiniteError("pivot 1")
+        parallel.run_restarts(m, always_bad, starts, {})
+
+
+def test_stochastic_freezes_redrawn_z_like_the_reference():
+    """gpr.py:91 replaces the GPflow Parameter by a raw array: after the redraw Z is no longer trained."""
+    d = make_gp_data(50, 2, 1, seed=6)
+    m = OracleBackedSparseModel("Matern52", d.x, d.y, d.x[:5].copy(), 1.0)
+    drawn = []
+    orig = gpr._optimize_adam
+
+    def spy(model, max_iter, *a, **k):
+        drawn.append(np.array(model.inducing_variable.Z))
+        return orig(model, max_iter, *a, **k)
+
+    gpr._optimize_adam, keep = spy, gpr._optimize_adam
+    try:
+        gpr._optimize_multi_start(m, n_starts=2, iter_initial=2, iter_final=3, seed=1)
+    finally:
+        gpr._optimize_adam = keep
+    np.testing.assert_array_equal(m.inducing_variable.Z, drawn[-1])  # neither Adam nor L-BFGS moved the last draw
+    m2 = OracleBackedSparseModel("Matern52", d.x, d.y, d.x[:5].copy(), 1.0)
+    gpr._optimize_multi_start(m2, n_starts=2, iter_initial=2, iter_final=3, seed=1, train_z=True)
+    assert not np.array_equal(m2.inducing_variable.Z, drawn[-1])
+
+
+def test_pool_cache_is_bounded():
+    assert gpr._POOL_CACHE_MAX_SHAPES <= 8
+    gpr.release_pools()
+    assert len(gpr._POOL_CACHE) == 0

@@ -39,6 +39,31 @@ def test_summary_closed_forms_match_reference(met_golden, name):
     assert s["fi_aoi_toi"] == float(c["fi_aoi_toi_0"])
 
 
+@pytest.mark.parametrize("name", MET_CASES)
+def test_peak_metrics_honour_caller_rows_and_the_reference_call(met_golden, name):
+    """The O(cells) host closed form behind every ``*_mts`` function: caller-supplied rows that are not the arg-max rows, and the
+    reference's own positional call of f2 / f3 (``gpras/metrics.py:53-54``: threshold = arg-max rows of x, truth peak read at the
+    arg-max rows of y)."""
+    c = sub(met_golden, name)
+    x, y, thr = c["x"], c["y"], float(c["depth_threshold"])
+    xr, yr = c["rows_x"], c["rows_y"]
+    m = gm._peak_metrics(gm._gather_rows(x, xr), gm._gather_rows(y, yr), thr)
+    np.testing.assert_allclose(m["err_cell_mts"], c["rows_err_cell_mts"], rtol=1e-12, atol=1e-14)
+    for k in ("rmse_aoi_mts", "nse_aoi_mts", "err_aoi_mts", "pod_mts", "rfa_mts", "csi_mts", "f2_mts", "f3_mts"):
+        np.testing.assert_allclose(m[k], float(c["rows_" + k]), rtol=1e-12, atol=1e-14, err_msg=k)
+    called = gm._peak_metrics(gm._gather_rows(x, c["y_mts"]), y.max(axis=0), c["x_mts"])
+    np.testing.assert_allclose(called["f2_mts"], float(c["f2_mts_as_called"]), rtol=1e-12)
+    np.testing.assert_allclose(called["f3_mts"], float(c["f3_mts_as_called"]), rtol=1e-12)
+
+
+def test_advisor_counter_example_for_f2_f3():
+    # x and y peak on different rows and the thresholds (row indices 1, 1) are small: the reference gives 0.5 and 0.0
+    x = np.array([[0, 0], [3, 3], [0.5, 0.5]], float)
+    y = np.array([[0, 0], [1, 2.5], [2, 1]], float)
+    called = gm._peak_metrics(gm._gather_rows(x, np.argmax(y, 0)), y.max(axis=0), np.argmax(x, 0))
+    assert called["f2_mts"] == 0.5 and called["f3_mts"] == 0.0
+
+
 def test_metrics_module_surface_matches_reference():
     # gpras/metrics.py:11-324
     names = ["export_metric_summary", "rmse_aoi_toi", "mae_aoi_toi", "conf_aoi_toi", "rmse_aoi_ts", "rmse_cell_toi", "rmse_aoi_mts",
