@@ -43,6 +43,7 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 template <typename K>
 int opt_in_smem(K kernel, int bytes) {
+  // (Asking for the maximum shared-memory carveout as well was measured and rejected: the Cholesky got 2 % slower.)
   CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return 0;
 }
@@ -70,6 +71,9 @@ int prepare_device() {
   if ((r = opt_in_smem(gemm_tile_kernel<CfgN, false, true>, CfgN::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(gemm_tile_kernel<CfgN, true, true>, CfgN::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(leaf_potrf_inv_kernel, LEAF_SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(leaf_potrf_kernel, LEAF_SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(leaf_inv_kernel, LEAF_SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(trsm_panel_kernel, TRSM_SMEM_BYTES))) return r;
   if ((r = prepare_kid<K_RBF>())) return r;
   if ((r = prepare_kid<K_MATERN12>())) return r;
   if ((r = prepare_kid<K_MATERN32>())) return r;
@@ -148,30 +152,59 @@ int launch_skinny(cudaStream_t s, bool akm, GemmDesc d, double* part, int rows, 
   return 0;
 }
 constexpr int SKINNY_MAX_SLABS = 16;
-constexpr int PANEL_GROUP = 2;    // Cholesky: trailing updates for groups of this many panels ...
-constexpr int PAIR_MIN_REM = 36;  // ... while more than this many block rows remain
+constexpr int PANEL_GROUP = 4;    // Cholesky: trailing updates for groups of this many panels ...
+constexpr int PAIR_MIN_REM = 24;  // ... while more than this many block rows remain ...
+constexpr int TAIL_GROUP = 1;     // ... and of this many afterwards
+constexpr int WIDE_COL_REM = 32;  // the side stream's block-column update uses the 128x64 shape above this many remaining rows
 
 // ---- dense building blocks -------------------------------------------------------------------
-// Side stream + events for the one-panel look-ahead of the Cholesky.
-struct LookAhead {
-  cudaStream_t side = nullptr;
-  std::vector<cudaEvent_t> ev;
-  double* scratch = nullptr;  // n x 128 column block of the Cholesky chain
-  size_t scratch_count = 0;
-  int ensure_scratch(size_t count) {
-    if (count <= scratch_count) return 0;
-    if (scratch) cudaFree(scratch);
-    scratch = nullptr, scratch_count = 0;
-    cudaError_t e = cudaMalloc((void**)&scratch, count * sizeof(double));
-    if (e != cudaSuccess) return fail(GPRAS_E_NOMEM, "cudaMalloc (Cholesky scratch)", e);
-    scratch_count = count;
-    return 0;
+// Tunables of the Cholesky driver, read from the environment once per process (development sweeps).
+struct PotrfTuning {
+  int group = PANEL_GROUP, min_rem = PAIR_MIN_REM, tail_group = TAIL_GROUP, wide_col_rem = WIDE_COL_REM;
+  PotrfTuning() {
+    if (const char* e = getenv("GPRAS_B200_PANEL_GROUP")) group = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char* e = getenv("GPRAS_B200_PAIR_MIN_REM")) min_rem = atoi(e);
+    if (const char* e = getenv("GPRAS_B200_TAIL_GROUP")) tail_group = atoi(e) > 0 ? atoi(e) : 1;
+    if (const char* e = getenv("GPRAS_B200_WIDE_COL_REM")) wide_col_rem = atoi(e);
   }
+};
+inline const PotrfTuning& potrf_tuning() {
+  static const PotrfTuning t;
+  return t;
+}
+
+#ifdef POTRF_TIMELINE
+// development only (tools/microbench/chain_timing.cu): timestamps of every step's kernels
+struct PotrfTimeline {
+  std::vector<cudaEvent_t> ev;  // per step: [bulk start, bulk end, trsm end, diag end, leaf end, col end]
+  cudaEvent_t t0;
+  cudaEvent_t get(int j, int k) {
+    const size_t i = (size_t)j * 6 + k;
+    while (ev.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    return ev[i];
+  }
+};
+inline PotrfTimeline* g_timeline = nullptr;
+#define TL(j, k, st) do { if (g_timeline) cudaEventRecord(g_timeline->get(j, k), st); } while (0)
+#else
+#define TL(j, k, st)
+#endif
+
+// Side streams + events of the Cholesky's look-ahead.
+struct LookAhead {
+  cudaStream_t side = nullptr;   // the chain: panel solve -> diagonal-block update -> leaf (highest priority)
+  cudaStream_t side2 = nullptr;  // the rest of the next block column (needed one leaf later)
+  std::vector<cudaEvent_t> ev;
   int ensure(size_t n) {
     if (!side) {
       int lo = 0, hi = 0;
-      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      CU(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));  // `hi` is the greatest priority
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // `hi` is the greatest priority (numerically lowest)
+      CU(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+      CU(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, hi < lo ? hi + 1 : hi));
     }
     while (ev.size() < n) {
       cudaEvent_t e;
@@ -184,100 +217,140 @@ struct LookAhead {
     for (auto e : ev) cudaEventDestroy(e);
     ev.clear();
     if (side) cudaStreamDestroy(side);
-    side = nullptr;
-    if (scratch) cudaFree(scratch);
-    scratch = nullptr, scratch_count = 0;
+    if (side2) cudaStreamDestroy(side2);
+    side = side2 = nullptr;
   }
 };
 
-// Right-looking blocked Cholesky, panel width 128, with one panel of look-ahead on a high-priority side stream:
-//   leaf   (1 CTA)   potrf + inverse of the diagonal block  -> L_jj, W_jj
-//   panel  (CfgT)    L21 = A21 W_jj^T, from the scratch column block S into A (first panel: CfgP, in place)
-//   col    (CfgT)    S = block column j+1 of the trailing matrix - panel_j panel_j^T      [side stream]
-//   rest   (CfgS)    the trailing triangle right of block column j+1 -= panel_j panel_j^T  [main stream]
-// so leaf(j+1) and panel(j+1) run while rest(j) occupies the machine.  The chain col -> leaf -> panel is what bounds
-// the factorisation once rest(j) gets short, so its two products use 64x32 tiles (16x the CTAs of a 128x128 tiling)
-// and go through the scratch block S (n x 128): out of place, any tile shape is race free.
+// Right-looking blocked Cholesky, panel width 128, everything in place in A.  Per step j three streams cooperate:
+//   chain (high priority)  panel  L[j+1.., j] = A[j+1.., j] L_jj^-T     triangular solve, 32 rows per CTA (trsm_panel_kernel)
+//                          diag   A[j+1, j+1] -= sum_pending L[j+1, k] L[j+1, k]^T           (CfgT, 8 CTAs)
+//                          leaf   L_{j+1, j+1} = chol(A[j+1, j+1])                           (leaf_potrf_kernel, 1 CTA)
+//   side                   col    A[j+2.., j+1] -= sum_pending L[j+2.., k] L[j+1, k]^T       (CfgT) -- needed by panel j+1 only
+//   main                   rest   the trailing triangle right of block column j+1 -= (group of panels)(...)^T   (CfgS)
+// The chain is what bounds the factorisation once `rest` gets short, so it carries only what the next leaf needs: the
+// leaf does not invert its block (the panel is a SOLVE against L_jj, not a product with its inverse), and of block
+// column j+1 only the diagonal block is updated on the chain.  The inverses W_jj of all diagonal blocks, which the
+// triangular inverse starts from, come from ONE launch after the factorisation (leaf_inv_kernel, one CTA per block).
+// (Round 1 had leaf + inverse 42 us, column update and panel product on the chain: ~60 us per step.)
 int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, long ldw, int n, double* logdet_parts,
                int* info, int* launches) {
   const int nt = n / 128;
   int r;
-  if ((r = la.ensure(2 * (size_t)nt + 2))) return r;
-  if ((r = la.ensure_scratch((size_t)n * 128))) return r;
-  double* S = la.scratch;  // S[i][0..127] = updated block column for global row i
-  cudaStream_t s2 = la.side;
-  cudaEvent_t* evPanel = la.ev.data();        // [nt]
-  cudaEvent_t* evRest = la.ev.data() + nt;    // [nt]
-  cudaEvent_t evFork = la.ev[2 * nt], evJoin = la.ev[2 * nt + 1];
-  auto leaf = [&](cudaStream_t st, int jb, const double* in, long ldin) -> int {
-    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(in, ldin, A, lda, W, ldw, logdet_parts, info, jb);
+  if (nt == 1) {  // single block: one kernel factors and inverts, no side streams
+    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, s>>>(A, lda, A, lda, W, ldw, logdet_parts, info, 0);
+    if (launches) ++*launches;
+    CU(cudaGetLastError());
+    return 0;
+  }
+  if ((r = la.ensure(4 * (size_t)nt + 3))) return r;
+  cudaStream_t s2 = la.side, s3 = la.side2;
+  cudaEvent_t* evPanel = la.ev.data();            // [nt] panel j solved
+  cudaEvent_t* evAhead = la.ev.data() + nt;       // [nt] look-ahead part of the bulk update issued at step j done
+  cudaEvent_t* evCol = la.ev.data() + 2 * nt;     // [nt] rows below the diagonal of block column j up to date
+  cudaEvent_t evFork = la.ev[4 * nt], evJoin = la.ev[4 * nt + 1], evJoin2 = la.ev[4 * nt + 2];
+  auto leaf = [&](cudaStream_t st, int jb) -> int {
+    leaf_potrf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_BYTES, st>>>(A, lda, logdet_parts, info, jb);
     if (launches) ++*launches;
     CU(cudaGetLastError());
     return 0;
   };
-  if ((r = leaf(s, 0, A, lda))) return r;
-  if (nt == 1) return 0;  // single block: nothing to overlap, the side stream stays out of it
+  if ((r = leaf(s, 0))) return r;
   CU(cudaEventRecord(evFork, s));
   CU(cudaStreamWaitEvent(s2, evFork, 0));
-  {  // first panel, in place (rows of tiles 1.., columns of block 0)
-    double* pn = A + (long)128 * lda;
-    GemmDesc p = make_desc(pn, lda, W, ldw, pn, lda, 2 * (nt - 1), 1, 128);
-    if ((r = launch_gemm(s, false, false, p, 1, launches, SHAPE_P))) return r;
-  }
-  CU(cudaEventRecord(evPanel[0], s));
+  CU(cudaStreamWaitEvent(s3, evFork, 0));
   // Trailing updates are applied for GROUPS of G panels (rank 128 G) while the trailing matrix is large: that divides the
-  // read-modify-write traffic on the trailing matrix by G and multiplies the k extent per tile of the short-k kernel.  The
-  // chain's column update brings block column j+1 fully up to date itself (1 .. G pending panels).  Grouping pays while the
-  // bulk update dominates the step; once the leaf -> panel chain does (short trailing matrix), single panels keep the pipeline
-  // fine-grained.  The switch happens at a multiple of G, where no panel is pending.
-  int G = PANEL_GROUP, min_rem = PAIR_MIN_REM;
-  if (const char* e = getenv("GPRAS_B200_PANEL_GROUP")) G = atoi(e) > 0 ? atoi(e) : 1;
-  if (const char* e = getenv("GPRAS_B200_PAIR_MIN_REM")) min_rem = atoi(e);
-  int j_single = nt - 1 - min_rem;  // first step whose trailing matrix is short enough for single panels ...
+  // read-modify-write traffic on the trailing matrix by G and multiplies the k extent per tile of the short-k kernel
+  // (measured alone: DMMA pipe 76 % active at rank 128, 82 % at 256, 91 % at 512).  The chain brings block column j+1 fully
+  // up to date itself (1 .. G pending panels).  Every bulk update is issued in two launches: first the block columns the
+  // NEXT group's chain works on (look-ahead part), then the rest; the next group's chain waits for the first only, so the
+  // bulk stream never idles behind the chain (with one launch it did: ~63 us per group, which cancelled the gain of
+  // grouping).  Once the chain bounds the step (short trailing matrix), single panels keep the pipeline fine-grained.  The
+  // switch happens at a multiple of G, where no panel is pending.
+  const int G = potrf_tuning().group, Gt = potrf_tuning().tail_group;
+  int j_single = nt - 1 - potrf_tuning().min_rem;  // first step whose trailing matrix is short enough for the tail grouping ...
   if (j_single < 0) j_single = 0;
   j_single = (j_single + G - 1) / G * G;  // ... rounded up to a group boundary
+  int last_bulk = -1;  // step of the most recent bulk update
   for (int j = 0; j + 1 < nt; j++) {
     const int rem = nt - j - 1;  // tiles below / right of block j
     const bool grouped = j < j_single;
-    const int pc = grouped ? (j % G) + 1 : 1;         // pending panels at this step
-    const bool bulk = pc == (grouped ? G : 1);        // the group is complete: apply it to the rest of the trailing matrix
-    const int kp = 128 * pc;                          // k extent of the chain's column update
+    const int gsz = grouped ? G : Gt;                 // size of this step's group
+    const int pc = (grouped ? j % G : (j - j_single) % Gt) + 1;  // pending panels at this step
+    const bool bulk = pc == gsz;                      // the group is complete: apply it to the rest of the trailing matrix
+    const int kp = 128 * pc;                          // k extent of the chain's updates
     const long pcol = (long)(j - (pc - 1)) * 128;     // first column of the pending panel(s)
     double* pn = A + (long)(j + 1) * 128 * lda + pcol;  // pending panel(s), rows from tile j+1
-    // ---- side stream: block column j+1 -> S, then the next diagonal block and panel ----
-    CU(cudaStreamWaitEvent(s2, evPanel[j], 0));
-    if (pc == 1 && j > 0) CU(cudaStreamWaitEvent(s2, evRest[j - 1], 0));  // (later steps of a group: waited at its first step)
-    double* Sj = S + (long)(j + 1) * 128 * 128;  // rows from tile j+1
+    // ---- chain: solve panel j, bring the next diagonal block up to date, factor it ----
+    if (j > 0) CU(cudaStreamWaitEvent(s2, evCol[j], 0));
+    trsm_panel_kernel<<<rem * (LEAF_N / TRSM_ROWS), TRSM_THREADS, TRSM_SMEM_BYTES, s2>>>(A, lda, j);
+    if (launches) ++*launches;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(evPanel[j], s2));
+    TL(j, 2, s2);
+    // (first step of a group: the previous group's bulk update must have reached this group's block columns)
+    if (pc == 1 && last_bulk >= 0) CU(cudaStreamWaitEvent(s2, evAhead[last_bulk], 0));
     {
-      const double* col = A + (long)(j + 1) * 128 * (lda + 1);
-      GemmDesc c = make_desc(pn, lda, pn, lda, Sj, 128, 2 * rem, 4, kp);
+      double* djj = A + (long)(j + 1) * 128 * (lda + 1);
+      GemmDesc c = make_desc(pn, lda, pn, lda, djj, lda, 2, 4, kp);
       c.alpha = -1.0, c.beta = 1.0;
-      c.Cin = col, c.ldcin = lda;
       if ((r = launch_gemm(s2, false, false, c, 1, launches, SHAPE_T))) return r;
     }
-    if ((r = leaf(s2, j + 1, Sj, 128))) return r;
+    TL(j, 3, s2);
+    if ((r = leaf(s2, j + 1))) return r;
+    TL(j, 4, s2);
     if (rem > 1) {
-      {  // panel j+1: rows of tiles j+2.. of S times W_{j+1}^T -> A
-        const double* wjj = W + (long)(j + 1) * 128 * (ldw + 1);
-        double* out = A + (long)(j + 2) * 128 * lda + (long)(j + 1) * 128;
-        GemmDesc p = make_desc(Sj + (long)128 * 128, 128, wjj, ldw, out, lda, 2 * (rem - 1), 4, 128);
-        if ((r = launch_gemm(s2, false, false, p, 1, launches, SHAPE_T))) return r;
+      // ---- side: the rest of block column j+1 (rows from tile j+2), needed when leaf j+1 is done ----
+      CU(cudaStreamWaitEvent(s3, evPanel[j], 0));
+      if (pc == 1 && last_bulk >= 0) CU(cudaStreamWaitEvent(s3, evAhead[last_bulk], 0));
+      {
+        double* pn2 = pn + (long)128 * lda;                                     // pending panel(s), rows from tile j+2
+        double* col = A + (long)(j + 2) * 128 * lda + (long)(j + 1) * 128;      // block column j+1, rows from tile j+2
+        // many small tiles while this update sits next to the critical path, the throughput shape while the bulk update
+        // leaves it an order of magnitude of slack
+        const bool wide = rem > potrf_tuning().wide_col_rem;
+        GemmDesc c = make_desc(pn2, lda, pn, lda, col, lda, wide ? rem - 1 : 2 * (rem - 1), wide ? 2 : 4, kp);
+        c.alpha = -1.0, c.beta = 1.0;
+        if ((r = launch_gemm(s3, false, false, c, 1, launches, wide ? SHAPE_S : SHAPE_T))) return r;
       }
-      CU(cudaEventRecord(evPanel[j + 1], s2));
-      // ---- main stream: the rest of the trailing triangle, the whole group of panels together ----
+      CU(cudaEventRecord(evCol[j + 1], s3));
+      TL(j, 5, s3);
+      // ---- main stream: the trailing triangle from block column j+2, the whole group of panels together ----
       if (bulk) {
         CU(cudaStreamWaitEvent(s, evPanel[j], 0));
         double* pn2 = pn + (long)128 * lda;  // pending panel(s): rows from tile j+2
-        double* trail = A + (long)(j + 2) * 128 * (lda + 1);
-        GemmDesc u = make_desc(pn2, lda, pn2, lda, trail, lda, rem - 1, 2 * (rem - 1), kp);
-        u.tri = 1, u.alpha = -1.0, u.beta = 1.0;
-        if ((r = launch_gemm(s, false, false, u, 1, launches, SHAPE_S))) return r;
-        CU(cudaEventRecord(evRest[j], s));
+        // look-ahead part: the block columns of the next group (rectangular launch over rows j+2.. x those columns; the few
+        // tiles above the diagonal it touches are never read)
+        const int next_g = (j + 1 < j_single) ? G : Gt;
+        const int wa = next_g < rem - 1 ? next_g : rem - 1;  // its width in block columns
+        TL(j, 0, s);
+        {
+          double* ahead = A + (long)(j + 2) * 128 * (lda + 1);
+          GemmDesc u = make_desc(pn2, lda, pn2, lda, ahead, lda, rem - 1, 2 * wa, kp);
+          u.alpha = -1.0, u.beta = 1.0;
+          if ((r = launch_gemm(s, false, false, u, 1, launches, SHAPE_S))) return r;
+        }
+        CU(cudaEventRecord(evAhead[j], s));
+        last_bulk = j;
+        if (rem - 1 > wa) {  // the rest: lower triangle from block column j+2+wa
+          double* pn3 = pn2 + (long)wa * 128 * lda;
+          double* trail = A + (long)(j + 2 + wa) * 128 * (lda + 1);
+          GemmDesc u = make_desc(pn3, lda, pn3, lda, trail, lda, rem - 1 - wa, 2 * (rem - 1 - wa), kp);
+          u.tri = 1, u.alpha = -1.0, u.beta = 1.0;
+          if ((r = launch_gemm(s, false, false, u, 1, launches, SHAPE_S))) return r;
+        }
+        TL(j, 1, s);
       }
     }
   }
   CU(cudaEventRecord(evJoin, s2));
+  CU(cudaEventRecord(evJoin2, s3));
   CU(cudaStreamWaitEvent(s, evJoin, 0));
+  CU(cudaStreamWaitEvent(s, evJoin2, 0));
+  // inverses of all diagonal blocks, one CTA each
+  leaf_inv_kernel<<<nt, LEAF_THREADS, LEAF_SMEM_BYTES, s>>>(A, lda, W, ldw);
+  if (launches) ++*launches;
+  CU(cudaGetLastError());
   return 0;
 }
 

@@ -55,9 +55,13 @@ static __device__ long long* g_leaf_timing;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(lt_d) : "r"(lt_sa)); \
     asm volatile("{ .reg .pred p; setp.eq.u32 p, %1, 0x7fc12345; @p trap; mov.u64 %0, %%clock64; }" : "=l"(lt_now) : "r"(lt_d)); \
     lt_acc[i] += lt_now - lt_prev; lt_prev = lt_now; } while (0)
+#define LT_DUMP do { __syncthreads(); LT_MARK(12); if (tid == 0 || tid == 128) { \
+    for (int i = 0; i < 13; i++) if ((tid == 0) != (i == 4 || i == 5)) g_leaf_timing[i] = lt_acc[i]; \
+    if (tid == 0) g_leaf_timing[13] = clock64() - lt_start; } } while (0)
 #else
 #define LT_DECL
 #define LT_MARK(i)
+#define LT_DUMP
 #endif
 
 __device__ __forceinline__ double leaf_getW(const double* S, const double* dvec, int i, int k) {
@@ -223,20 +227,18 @@ __device__ __forceinline__ void leaf_inverse_level(double* S, const double* dvec
   __syncthreads();
 }
 
-static __global__ void __launch_bounds__(LEAF_THREADS, 1)
-leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* __restrict__ W,
-                      long ldw, double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
+// Body shared by the three leaf kernels.  POTRF: factor the block (else the block already holds L and only 1 / L_ii is
+// formed); INVERSE: build W = L^-1 and store it.  `In` points at the 128 x 128 block to read (pitch ldin), `A` at where L
+// goes (pitch lda; only written when POTRF), `W` at where the inverse goes.
+template <bool POTRF, bool INVERSE>
+__device__ __forceinline__ void leaf_body(const double* In, long ldin, double* A, long lda, double* __restrict__ W, long ldw,
+                                          double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double logred[4];
   double* S = smem;
   double* dvec = smem + LEAF_N * LEAF_LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
-  // In points at the 128 x 128 block to factor (pitch ldin): the diagonal block of A itself, or the chain's scratch
-  // column block; L goes to the diagonal block jb of A, W = L^-1 to that of W.
-  if (In == A) In += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
-  A += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
-  W += (long)jb * LEAF_N * ldw + (long)jb * LEAF_N;
 
   LT_DECL;
   // ---- load: every 16-byte chunk that touches the lower triangle, all in flight at once (cp.async).  The strictly
@@ -251,38 +253,58 @@ leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* 
   __syncthreads();
   LT_MARK(0);
 
-  // ---- 1. blocked Cholesky, right-looking over 16 panels of 8 columns with one panel of look-ahead ----
-  if (warp < 4) leaf_factor_panel(S, dvec, 0, warp, lane, info, jb * LEAF_N);
-  __syncthreads();
-  LT_MARK(1);
-  for (int J = 0; J < 15; J++) {
-    const int j0 = 8 * J;
-    // phase A: block column J+1 (<= 15 tiles, <= 2 per warp) gets panel J's update
-    leaf_update_tiles<2>(S, c_leaf_tiles.off[J + 1] + warp, 8, c_leaf_tiles.off[J + 2], j0, g, q);
+  if (POTRF) {
+    // ---- 1. blocked Cholesky, right-looking over 16 panels of 8 columns with one panel of look-ahead ----
+    if (warp < 4) leaf_factor_panel(S, dvec, 0, warp, lane, info, jb * LEAF_N);
     __syncthreads();
-    LT_MARK(2);
-    if (warp < 4) {
-      // phase B, warps 0..3: factor panel J+1
-      leaf_factor_panel(S, dvec, j0 + 8, warp, lane, info, jb * LEAF_N);
-      LT_MARK(3);
-    } else {
-      // phase B, warps 4..7: the rest of the trailing triangle (block columns >= J+2) gets panel J's update
-      const int te = c_leaf_tiles.off[16];
-      for (int t = c_leaf_tiles.off[J + 2] + (warp - 4); t < te; t += 16) leaf_update_tiles<4>(S, t, 4, te, j0, g, q);
-      LT_MARK(4);
+    LT_MARK(1);
+    for (int J = 0; J < 15; J++) {
+      const int j0 = 8 * J;
+      // phase A: block column J+1 (<= 15 tiles, <= 2 per warp) gets panel J's update
+      leaf_update_tiles<2>(S, c_leaf_tiles.off[J + 1] + warp, 8, c_leaf_tiles.off[J + 2], j0, g, q);
+      __syncthreads();
+      LT_MARK(2);
+      if (warp < 4) {
+        // phase B, warps 0..3: factor panel J+1
+        leaf_factor_panel(S, dvec, j0 + 8, warp, lane, info, jb * LEAF_N);
+        LT_MARK(3);
+      } else {
+        // phase B, warps 4..7: the rest of the trailing triangle (block columns >= J+2) gets panel J's update
+        const int te = c_leaf_tiles.off[16];
+        for (int t = c_leaf_tiles.off[J + 2] + (warp - 4); t < te; t += 16) leaf_update_tiles<4>(S, t, 4, te, j0, g, q);
+        LT_MARK(4);
+      }
+      __syncthreads();
+      LT_MARK(5);
+    }
+    // sum(log L_ii) = -sum(log dvec): 128 logs in parallel, fixed-shape reduction
+    if (tid < 128) {
+      double lg = -log(dvec[tid]);
+      lg = warp_sum(lg);
+      if (lane == 0) logred[warp] = lg;
     }
     __syncthreads();
-    LT_MARK(5);
+    if (tid == 0) logdet_part[jb] = (logred[0] + logred[1]) + (logred[2] + logred[3]);
+    LT_MARK(6);
+    // ---- write L back: the chunks that touch the lower triangle (the strictly upper part of L's diagonal block is
+    //      unspecified: no kernel reads it) ----
+#pragma unroll 8
+    for (int e = tid; e < LEAF_N * (LEAF_N / 2); e += LEAF_THREADS) {
+      const int r = e >> 6, c2 = (e & 63) * 2;
+      if (c2 <= r) {
+        double2 v = *reinterpret_cast<const double2*>(S + r * LEAF_LD + c2);
+        if (c2 + 1 > r) v.y = 0.0;
+        *reinterpret_cast<double2*>(A + (long)r * lda + c2) = v;
+      }
+    }
+  } else {
+    if (tid < 128) dvec[tid] = 1.0 / S[tid * LEAF_LD + tid];
+    __syncthreads();
   }
-  // sum(log L_ii) = -sum(log dvec): 128 logs in parallel, fixed-shape reduction
-  if (tid < 128) {
-    double lg = -log(dvec[tid]);
-    lg = warp_sum(lg);
-    if (lane == 0) logred[warp] = lg;
+  if (!INVERSE) {
+    LT_DUMP;
+    return;
   }
-  __syncthreads();
-  if (tid == 0) logdet_part[jb] = (logred[0] + logred[1]) + (logred[2] + logred[3]);
-  LT_MARK(6);
 
   // ---- 2. inverse: 8x8 diagonal blocks (thread = one column of one block) ----
   if (tid < 128) {
@@ -311,19 +333,9 @@ leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* 
   leaf_inverse_level<64>(S, dvec, warp, g, q, W, ldw);
   LT_MARK(11);
 
-  // ---- 3. write back.  L: the chunks that touch the lower triangle (the strictly upper part of L's diagonal block
-  //         is unspecified: no kernel reads it).  W: 8 x 4 element blocks of the two diagonal 64 x 64 triangles,
-  //         transposed conflict-free reads; blocks above the diagonal are never written (the W buffer is zero-initialised
-  //         once and the engine relies on those zeros), the lower-left 64 x 64 block is already in global memory ----
-#pragma unroll 8
-  for (int e = tid; e < LEAF_N * (LEAF_N / 2); e += LEAF_THREADS) {
-    const int r = e >> 6, c2 = (e & 63) * 2;
-    if (c2 <= r) {
-      double2 v = *reinterpret_cast<const double2*>(S + r * LEAF_LD + c2);
-      if (c2 + 1 > r) v.y = 0.0;
-      *reinterpret_cast<double2*>(A + (long)r * lda + c2) = v;
-    }
-  }
+  // ---- 3. W: 8 x 4 element blocks of the two diagonal 64 x 64 triangles, transposed conflict-free reads; blocks above the
+  //         diagonal are never written (the W buffer is zero-initialised once and the engine relies on those zeros), the
+  //         lower-left 64 x 64 block is already in global memory ----
 #pragma unroll 4
   for (int blk = warp; blk < 16 * 32; blk += 8) {  // 16 row groups of 8 x 32 column groups of 4
     const int rb = 8 * (blk >> 5), cb = 4 * (blk & 31);
@@ -332,15 +344,123 @@ leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* 
       W[(long)r * ldw + c] = leaf_getW(S, dvec, r, c);
     }
   }
-#ifdef LEAF_TIMING
-  __syncthreads();
-  LT_MARK(12);
-  if (tid == 0 || tid == 128) {
-    for (int i = 0; i < 13; i++)
-      if ((tid == 0) != (i == 4 || i == 5)) g_leaf_timing[i] = lt_acc[i];
-    if (tid == 0) g_leaf_timing[13] = clock64() - lt_start;
+  LT_DUMP;
+}
+
+// Factor + invert one diagonal block (single-block matrices: M <= 128 of the sparse model, and the microbenchmark).
+static __global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* __restrict__ W,
+                      long ldw, double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
+  // In points at the 128 x 128 block to factor (pitch ldin): the diagonal block of A itself, or a scratch block;
+  // L goes to the diagonal block jb of A, W = L^-1 to that of W.
+  if (In == A) In += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
+  A += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
+  W += (long)jb * LEAF_N * ldw + (long)jb * LEAF_N;
+  leaf_body<true, true>(In, ldin, A, lda, W, ldw, logdet_part, info, jb);
+}
+
+// The Cholesky chain's leaf: factor diagonal block jb of A in place, nothing else (the inverse of the block is not
+// on the factorisation's critical path any more: the panel below it is a triangular SOLVE, trsm_panel_kernel).
+static __global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_potrf_kernel(double* A, long lda, double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
+  A += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
+  leaf_body<true, false>(A, lda, A, lda, nullptr, 0, logdet_part, info, jb);
+}
+
+// W_jj = L_jj^-1 for ALL diagonal blocks in one launch (blockIdx.x = block), after the factorisation.
+static __global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_inv_kernel(const double* A, long lda, double* __restrict__ W, long ldw) {
+  const int jb = blockIdx.x;
+  A += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
+  W += (long)jb * LEAF_N * ldw + (long)jb * LEAF_N;
+  leaf_body<false, true>(A, lda, nullptr, 0, W, ldw, nullptr, nullptr, jb);
+}
+
+// ---- triangular-solve panel --------------------------------------------------------------------------------------
+// X = B L^-T in place, for the rows of A below diagonal block jb (B = A[rows, block column jb], L = the factored
+// diagonal block).  One warp owns 8 rows and keeps them in registers as sixteen 8 x 8 DMMA accumulator tiles; the lower
+// 8 x 8 blocks of L, the diagonal ones inverted, sit in shared memory.  Right-looking over the
+// 8-column blocks: X_b = B_b inv(L_bb)^T (two DMMAs), then B_c -= X_b L_cb^T for every c > b (independent
+// accumulators, two DMMAs each).  The accumulator -> A-operand re-layout is four quad shuffles; there is no barrier
+// and no shared-memory traffic for X inside the loop, so a row tile finishes in ~16 x (solve + first update) DMMA
+// latencies while the other updates fill the pipe.
+constexpr int TRSM_WARPS = 4, TRSM_ROWS = 8 * TRSM_WARPS, TRSM_THREADS = 32 * TRSM_WARPS;
+// L_jj sits in shared memory as its 136 lower 8 x 8 blocks, block (c, b) at (c (c + 1) / 2 + b) * TRSM_BLK with row pitch 12
+// (== 12 mod 16: conflict-free fragment reads); the diagonal slots end up holding the INVERSE of their block.  104 KB, so a
+// panel CTA shares an SM with a trailing-update CTA instead of evicting it (with a 135 KB square tile it could not).
+constexpr int TRSM_DLD = 12, TRSM_BLK = 8 * TRSM_DLD + 2;  // (+2: the diagonal slots of blocks w, w+4, w+8, w+12 fall in different banks)
+constexpr int TRSM_SMEM_BYTES = 136 * TRSM_BLK * (int)sizeof(double);
+__device__ __forceinline__ int trsm_blk(int c, int b) { return (c * (c + 1) / 2 + b) * TRSM_BLK; }
+
+// C-fragment (lane (g, q) holds columns 2q, 2q+1 of row g) -> the two A-fragments of the k = 0..3 / 4..7 halves
+// (lane (g, q) holds column q / column 4 + q of row g)
+__device__ __forceinline__ void trsm_c_to_a(double cx, double cy, int lane, int q, double& a_lo, double& a_hi) {
+  const int base = lane & ~3, src_lo = base | (q >> 1), src_hi = base | (2 + (q >> 1));
+  const double lx = __shfl_sync(0xffffffffu, cx, src_lo), ly = __shfl_sync(0xffffffffu, cy, src_lo);
+  const double hx = __shfl_sync(0xffffffffu, cx, src_hi), hy = __shfl_sync(0xffffffffu, cy, src_hi);
+  a_lo = (q & 1) ? ly : lx;
+  a_hi = (q & 1) ? hy : hx;
+}
+
+static __global__ void __launch_bounds__(TRSM_THREADS, 2)
+trsm_panel_kernel(double* A, long lda, int jb) {
+  extern __shared__ __align__(16) double smem[];
+  double* S = smem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const double* Ljj = A + (long)jb * LEAF_N * lda + (long)jb * LEAF_N;
+  for (int e = tid; e < LEAF_N * (LEAF_N / 2); e += TRSM_THREADS) {
+    const int r = e >> 6, c2 = (e & 63) * 2;
+    // (the chunk that straddles the diagonal brings one element of the upper triangle along: it lands in the diagonal
+    //  block's slot and is never read)
+    if (c2 <= r) cp_async16(S + trsm_blk(r >> 3, c2 >> 3) + (r & 7) * TRSM_DLD + (c2 & 7), Ljj + (long)r * lda + c2);
   }
-#endif
+  cp_async_commit();
+  // this warp's 8 rows: sixteen accumulator tiles, loaded while L streams in
+  double* X = A + ((long)(jb + 1) * LEAF_N + (long)blockIdx.x * TRSM_ROWS + 8 * warp + g) * lda + (long)jb * LEAF_N + 2 * q;
+  double2 acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; c++) acc[c] = *reinterpret_cast<const double2*>(X + 8 * c);
+  cp_async_wait<0>();
+  __syncthreads();
+  {  // inverses of the 8 x 8 diagonal blocks, in place: thread = one column of one block (forward substitution)
+    const int blk = 4 * ((tid >> 3) & 3) + warp, c = tid & 7;  // a warp's four blocks sit in four different banks
+    double* Dg = S + trsm_blk(blk, blk);
+    double w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (k < i && k >= c) s -= Dg[i * TRSM_DLD + k] * w[k];
+      w[i] = (i >= c) ? s / Dg[i * TRSM_DLD + i] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; i++) Dg[i * TRSM_DLD + c] = w[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    double a_lo, a_hi;
+    trsm_c_to_a(acc[b].x, acc[b].y, lane, q, a_lo, a_hi);
+    // X_b[r][n] = sum_k B_b[r][k] inv(L_bb)[n][k]:  DMMA operand B[k][n] = inv(L_bb)[n][k], lane (g, q) reads n = g, k = q
+    const double* Dg = S + trsm_blk(b, b) + g * TRSM_DLD + q;
+    double x0 = 0.0, x1 = 0.0;
+    dmma(x0, x1, a_lo, Dg[0]);
+    dmma(x0, x1, a_hi, Dg[4]);
+    *reinterpret_cast<double2*>(X + 8 * b) = make_double2(x0, x1);
+    if (b < 15) {
+      trsm_c_to_a(-x0, -x1, lane, q, a_lo, a_hi);
+#pragma unroll
+      for (int c = b + 1; c < 16; c++) {
+        // B_c -= X_b L_cb^T:  operand B[k][n] = L[8c + n][8b + k]
+        const double* Lg = S + trsm_blk(c, b) + g * TRSM_DLD + q;
+        dmma(acc[c].x, acc[c].y, a_lo, Lg[0]);
+        dmma(acc[c].x, acc[c].y, a_hi, Lg[4]);
+      }
+    }
+  }
 }
 
 }  // namespace gpras

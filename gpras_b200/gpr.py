@@ -258,6 +258,22 @@ class ExactModel:
         self._slot = slot
         self.n_evals = 0
 
+    def clone(self) -> "ExactModel":
+        """A second model object on the same data and device slot with its own parameters (one per restart lane: the slot
+        hands every calling thread its own device handle)."""
+        ls = self.kernel.lengthscales.numpy()
+        m = ExactModel(self.kernel.name, self.x, self.y, np.array(ls) if np.ndim(ls) else float(ls), self._slot, self.device,
+                       True, self.kernel.variance.transform)
+        for src, dst in zip(self.parameters, m.parameters):
+            dst.prior, dst.trainable, dst.lower = src.prior, src.trainable, src.lower
+            dst.unconstrained = src.unconstrained.copy()
+        return m
+
+    def release_other_threads(self) -> None:
+        release = getattr(self._slot, "release_other_threads", None)
+        if release is not None:
+            release()
+
     # -- parameter plumbing --
     @property
     def parameters(self):
@@ -688,6 +704,7 @@ class GPRAS:
         device: int | None = None,
         initial_theta: NDArray[Any] | None = None,
         restarts: NDArray[Any] | None = None,
+        restart_lanes: int | None = None,
         n_jobs: int = 1,
         lockstep_models: bool = True,
         **opt_kwargs: Any,
@@ -702,7 +719,8 @@ class GPRAS:
         under ``torch.distributed``); ``initial_theta``
         ([variance, noise, lengthscale(s)]) overrides the initial values; ``restarts`` ((R, 2 + n_ls) constrained
         start points, column order [variance, noise, lengthscale(s)]) runs the recipe from every start and keeps
-        the lowest final loss (sharded across ranks when ``torch.distributed`` is initialised); ``n_jobs > 1``
+        the lowest final loss (handed out to ranks by a ticket counter when ``torch.distributed`` is initialised;
+        ``restart_lanes`` restarts in flight per GPU, default 2 for exact models above 4096 rows, else 1); ``n_jobs > 1``
         optimises that many per-column models concurrently on the GPU (host threads, one device handle each; the
         reference loops sequentially, ``gpr.py:273-274``, and so does the default).  Under ``torch.distributed`` (one
         process per GPU) per-column models are sharded round-robin over ranks and their parameters all-gathered.
@@ -729,7 +747,8 @@ class GPRAS:
             else:
                 from .parallel import run_restarts
 
-                run_restarts(model, opt, np.asarray(restarts, np.float64), opt_kwargs)
+                lanes = restart_lanes if restart_lanes is not None else (2 if exact and self.x.shape[0] > 4096 else 1)
+                run_restarts(model, opt, np.asarray(restarts, np.float64), opt_kwargs, lanes=lanes)
 
         from .parallel import dist_info
 

@@ -63,17 +63,56 @@ def all_gather_rows(local: np.ndarray, n_cols: int) -> np.ndarray:
     return np.concatenate([out[r, : int(counts[r].item())] for r in range(world)], axis=0)
 
 
-def run_restarts(model, opt, starts: np.ndarray, opt_kwargs: dict) -> np.ndarray:
-    """Run recipe ``opt`` from every start (rows of constrained [variance, noise, lengthscale(s)]), sharded
-    round-robin over ranks; every rank ends with the parameters of the lowest final loss (ties -> lowest
-    restart index).  Returns the gathered table with rows [restart, loss, theta...] sorted by restart.
+_TICKET_CALLS = [0]
+
+
+class _Tickets:
+    """Work queue over ranks without a data-path collective: an atomic counter in torch.distributed's key-value store (the
+    rendezvous TCPStore on rank 0) hands out restart indices, so a rank whose restarts converge early takes more of them.
+    ``dynamic=False`` (or no store) gives the static round-robin ``r -> rank r mod world``."""
+
+    def __init__(self, n_items: int, rank: int, world: int, dynamic: bool):
+        import threading
+
+        self.n, self.rank, self.world = n_items, rank, world
+        self._lock = threading.Lock()
+        self._static = iter(shard_indices(n_items, rank, world).tolist())
+        self.store, self.key = None, None
+        _TICKET_CALLS[0] += 1  # every rank makes the same sequence of calls, so the key names agree
+        if dynamic and world > 1:
+            try:
+                import torch.distributed as dist
+
+                self.store = dist.distributed_c10d._get_default_store()
+                self.key = f"gpras_b200/tickets/{_TICKET_CALLS[0]}"
+            except Exception:  # pragma: no cover
+                self.store = None
+
+    def next(self):
+        with self._lock:
+            if self.store is None:
+                return next(self._static, None)
+            r = int(self.store.add(self.key, 1)) - 1
+            return r if r < self.n else None
+
+
+def run_restarts(model, opt, starts: np.ndarray, opt_kwargs: dict, lanes: int = 1, dynamic: bool = True) -> np.ndarray:
+    """Run recipe ``opt`` from every start (rows of constrained [variance, noise, lengthscale(s)]), sharded over ranks;
+    every rank ends with the parameters of the lowest final loss (ties -> lowest restart index).  Returns the gathered
+    table with rows [restart, loss, theta...] sorted by restart.
+
+    Restarts are handed out by a ticket counter (``_Tickets``): independent restarts differ in how many L-BFGS iterations
+    they need, and a static split leaves ranks idle at the end.  ``lanes > 1`` runs that many restarts concurrently per rank
+    (host threads, one clone of the model and one device handle each): at N = 8192 a single evaluation leaves the GPU idle
+    behind the Cholesky's serial chain, two in flight fill it.
 
     Every restart begins from the same state: the start's hyperparameters, the model's INITIAL inducing inputs and
     trainable flags (the Z-training recipes move Z, and "diffential_evolution" leaves the hyperparameters frozen), and the
     winner's inducing inputs travel with its hyperparameters, so the model every rank ends with is the one whose loss is
     reported.  A start whose covariance matrix is not positive definite (the reference's ranges reach noise 1e-3 with
     lengthscales of 10, ``gpr.py:88-90``) scores ``+inf`` instead of aborting the whole fit."""
-    from ._lib import NotPositiveDefiniteError
+    import time
+
     from .gpr import _assign_theta
 
     rank, world, _ = dist_info()
@@ -84,33 +123,62 @@ def run_restarts(model, opt, starts: np.ndarray, opt_kwargs: dict) -> np.ndarray
     z_trainable0 = bool(model.inducing_variable.trainable) if has_z else False
     flags0 = [p.trainable for p in model.parameters]
     width = 2 + n_theta + z0.size
-    rows = []
-    for r in shard_indices(starts.shape[0], rank, world):
-        _assign_theta(model, starts[r])
-        for p, f in zip(model.parameters, flags0):
+    tickets = _Tickets(starts.shape[0], rank, world, dynamic)
+    lanes = max(1, min(int(lanes), starts.shape[0]))
+    if lanes > 1 and not hasattr(model, "clone"):
+        lanes = 1
+
+    def reset(mdl, theta):
+        _assign_theta(mdl, theta)
+        for p, f in zip(mdl.parameters, flags0):
             p.trainable = f
         if has_z:
-            model.inducing_variable.Z = z0.copy()
-            model.inducing_variable.trainable = z_trainable0
-        try:
-            opt(model, **opt_kwargs)
-            loss = float(model.training_loss())
-        except np.linalg.LinAlgError:  # NotPositiveDefiniteError is one
-            loss = float("inf")
-        z = np.asarray(model.inducing_variable.Z, np.float64).ravel() if has_z else np.zeros(0)
-        rows.append(np.concatenate([[float(r), loss], model.theta()[: 2 + nls], z]))
+            mdl.inducing_variable.Z = z0.copy()
+            mdl.inducing_variable.trainable = z_trainable0
+
+    def lane(mdl):
+        rows, busy = [], 0.0
+        while True:
+            r = tickets.next()
+            if r is None:
+                break
+            t0 = time.perf_counter()
+            reset(mdl, starts[r])
+            try:
+                opt(mdl, **opt_kwargs)
+                loss = float(mdl.training_loss())
+            except np.linalg.LinAlgError:  # NotPositiveDefiniteError is one
+                loss = float("inf")
+            z = np.asarray(mdl.inducing_variable.Z, np.float64).ravel() if has_z else np.zeros(0)
+            rows.append(np.concatenate([[float(r), loss], mdl.theta()[: 2 + nls], z]))
+            busy += time.perf_counter() - t0
+        return rows, busy, getattr(mdl, "n_evals", 0)
+
+    if lanes == 1:
+        results = [lane(model)]
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+
+        clones = [model] + [model.clone() for _ in range(lanes - 1)]
+        with ThreadPoolExecutor(max_workers=lanes) as ex:
+            results = list(ex.map(lane, clones))
+        model.n_evals = sum(r[2] for r in results)
+        release = getattr(model, "release_other_threads", None)
+        if release is not None:
+            release()
+    rows = [row for res in results for row in res[0]]
+    model.restart_busy_s = max((res[1] for res in results), default=0.0)
     table = all_gather_rows(np.array(rows).reshape(-1, width), width)
     table = table[np.argsort(table[:, 0], kind="stable")]
     finite = np.where(np.isfinite(table[:, 1]), table[:, 1], np.inf)
     best = int(np.argmin(finite))
-    for p, f in zip(model.parameters, flags0):
-        p.trainable = f
-    _assign_theta(model, table[best, 2 : 2 + n_theta])
+    reset(model, table[best, 2 : 2 + n_theta])
     if has_z:
         model.inducing_variable.Z = table[best, 2 + n_theta :].reshape(z0.shape).copy()
-        model.inducing_variable.trainable = z_trainable0
     model.restart_table = table[:, : 2 + n_theta]
     if not np.isfinite(finite[best]):
+        from ._lib import NotPositiveDefiniteError
+
         raise NotPositiveDefiniteError("every restart ended at a hyperparameter vector whose covariance matrix is not positive definite")
     return model.restart_table
 

@@ -320,3 +320,20 @@ def test_pool_cache_is_bounded():
     assert gpr._POOL_CACHE_MAX_SHAPES <= 8
     gpr.release_pools()
     assert len(gpr._POOL_CACHE) == 0
+
+
+def test_run_restarts_lanes_match_single_lane():
+    """Two restarts in flight per rank (host threads on clones of the model) give the table of the one-at-a-time loop."""
+    from gpras_b200 import parallel
+
+    d = make_gp_data(50, 2, 2, seed=7)
+    starts = np.array([[1.0, 0.1, 1.0], [0.3, 0.5, 2.5], [2.0, 0.05, 0.7], [0.7, 0.2, 1.3], [1.5, 0.4, 0.9]])
+    tabs = []
+    for lanes in (1, 2, 3):
+        m = OracleBackedModel("Matern52", d.x, d.y, 1.0)
+        tabs.append(parallel.run_restarts(m, gpr.OPTIMIZERS["L-BFGS-B"], starts, dict(max_iter=25), lanes=lanes))
+        best = int(np.argmin(tabs[-1][:, 1]))
+        np.testing.assert_allclose(m.theta()[:3], tabs[-1][best, 2:5], rtol=1e-14)
+        assert m.n_evals > 0
+    np.testing.assert_array_equal(tabs[0], tabs[1])
+    np.testing.assert_array_equal(tabs[0], tabs[2])
