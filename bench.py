@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the GPR hot path: LML+grad evaluations/s at N=8192 (BASELINE.json metric, config 3).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--concurrent C] [--quick]
 
 One "step" is one exact-GP log-marginal-likelihood + analytic-gradient evaluation at a fresh hyperparameter
 vector (covariance build, Cholesky, triangular inverse, K^-1, alpha, fused trace pass) on synthetic storm-event
@@ -9,15 +9,22 @@ data of BASELINE config 3: N=8192 training rows x 32 features, 32 target columns
 With N GPUs (torchrun, one rank per GPU) every rank evaluates its own shard of optimiser restarts -- K steps per
 rank, no data-path collective, one tiny all-gather of the [LML, grad] rows at the end ("weak" scaling).
 
-Printed JSON line (rank 0): `value` = evaluations/s with inputs resident in HBM, timed with CUDA events on the
-launching stream; `e2e` = the same through the host-buffer C-ABI call (X, Y, theta uploaded from pinned host memory
-and LML+grad read back every step); `roofline` = the DMMA tile-GEMM engine's algorithmic FP64 FLOP/s against the
-measured cuBLAS DGEMM rate; `cpu_baseline` = the oracle port timed on this box's host cores.
-`--impl reference` times that CPU port (the reference's GPflow/TensorFlow stack cannot be installed offline).
+Printed JSON line (rank 0):
+  value      evaluations/s with inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        the same work through the host-buffer C-ABI call (X, Y, theta uploaded from pinned host memory, LML +
+             gradient read back, every evaluation) including the same all-gather
+  roofline   job level: F_eval x evals/s per GPU against the cuBLAS DGEMM rate MEASURED IN THIS RUN; per-stage and
+             per-launch figures in `roofline.detail`
+  sustained  the same loop kept up for >= 3 s
+  predict    predicted cell-depths/s (BASELINE's second headline) with its own roofline (FP64 N^2 T and HBM 16 B/cell-depth)
+  cfg4, cfg5_sweep, strong   BASELINE configs 4 and 5 and config 3's fixed 64 restarts (strong scaling: fixed total work)
+  cpu_baseline   the oracle port on this box's host cores (N = 1 only)
+`--impl reference` times that CPU port alone (the reference's GPflow/TensorFlow stack cannot be installed offline).
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import sys
@@ -33,18 +40,42 @@ sys.path.insert(0, str(ROOT))
 WORKLOAD = dict(n=8192, d=32, p=32, kernel="Matern52", ard=True)
 METRIC = "LML+grad evals/s at N=8192"
 UNIT = "evals/s"
-# measured on this pool's B200 (profiles/r01/lib_bars_cublas_cusolver.json): cuBLAS DGEMM 8192^3, sustained
-FP64_DGEMM_TFLOPS = 35.4
-# one `ncu --set full` capture per kernel (cold cache, one launch each), summarised in profiles/
-NCU = {"source": "profiles/r01/ncu_full_final_r01b.json, ncu_eval_traffic_final_summary.json (one launch each, cold cache)",
-       "lauum_dram_bytes": 1.634e9, "lauum_dmma_pct": 96.7, "syrk_dram_bytes": 4.668e8, "syrk_dmma_pct": 75.8,
-       "eval_dram_bytes": 11.2e9, "eval_launches": 262}
-FP64_PEAK_SOURCE = "measured cuBLAS Dgemm 8192^3 on this pool (profiles/r01/lib_bars_cublas_cusolver.json); MEASURED_PEAKS.json has no FP64 entry"
+HBM_PEAK_GBS = 6543.7  # MEASURED_PEAKS.json (driver-written copy bandwidth on this pool's B200s)
+
+
+def workload_string() -> str:
+    w = WORKLOAD
+    return f"cfg3: exact GP LML+grad, N={w['n']}, D={w['d']}, P={w['p']}, {w['kernel']} ARD + noise, shared theta"
+
+
+def config_block() -> dict:
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": workload_string(), "l2": "working set 1.5 GiB per evaluation >> 126 MB L2 (no flush needed)"}
 
 
 def f_eval(n: int, p: int) -> float:
     """Algorithmic FP64 FLOPs of one evaluation's dense stages: N^3 + 3 N^2 P."""
     return float(n) ** 3 + 3.0 * float(n) ** 2 * p
+
+
+def hbm_peak() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    return HBM_PEAK_GBS, "MEASURED_PEAKS.json absent: value recorded by the driver for this pool in round 1"
+
+
+def ncu_inputs() -> dict:
+    """Figures taken from committed ncu captures (never typed into this file): the newest profiles/r*/bench_ncu_inputs.json."""
+    files = sorted(glob.glob(str(ROOT / "profiles" / "r*" / "bench_ncu_inputs.json")))
+    if not files:
+        return {"source": None}
+    d = json.loads(Path(files[-1]).read_text())
+    d["file"] = str(Path(files[-1]).relative_to(ROOT))
+    return d
 
 
 class ClockSampler(threading.Thread):
@@ -53,7 +84,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int, period: float = 0.05):
         super().__init__(daemon=True)
         self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self._stop_evt = threading.Event()
         try:
             import pynvml
@@ -79,6 +110,7 @@ class ClockSampler(threading.Thread):
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in names.items():
                     if mask & bit:
@@ -95,6 +127,7 @@ class ClockSampler(threading.Thread):
             "sm_max_mhz": self.max_mhz,
             "reasons": sorted(self.reasons),
             "samples": len(self.samples),
+            "power_w_max": max(self.power) if self.power else None,
         }
 
 
@@ -138,16 +171,16 @@ def run_reference(args) -> None:
     w = WORKLOAD
     data = make_gp_data(w["n"], w["d"], w["p"], 0, seed=0)
     thetas = make_thetas(8, w["d"])
-    n_evals = max(1, min(args.steps, 2))
+    n_evals = max(1, min(args.steps, 3))  # one evaluation takes ~10 s on 16 cores: a bounded sample of the K requested
     warm = 1 if args.warmup > 0 else 0
     dt, cores = cpu_port_eval_seconds(data, thetas, n_evals, warm)
     value = n_evals / dt
-    sample = f"{n_evals} full LML+grad evals at N={w['n']} (of {args.steps} requested) after {warm} warm-up, NumPy/SciPy-OpenBLAS oracle port"
+    sample = (f"{n_evals} full LML+grad evaluations at N={w['n']} timed (min(steps, 3) of the {args.steps} requested; ms_per_step is the mean "
+              f"of those) after {warm} warm-up, NumPy/SciPy-OpenBLAS oracle port on all host threads")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / n_evals, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg3: exact GP LML+grad, N={w['n']}, D={w['d']}, P={w['p']}, {w['kernel']} ARD + noise, shared theta"},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n_evals,
+        "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * dt / n_evals, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_block(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -155,13 +188,47 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def measure_fp64_peak(torch, seconds: float = 1.5) -> dict:
+    """cuBLAS DGEMM 8192^3 on this GPU, now: best of 5 (burst) and back to back for `seconds` (sustained).  The library call is
+    the roofline DENOMINATOR only (MEASURED_PEAKS.json records no FP64 figure); nothing on the product path calls cuBLAS."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(4):
+            torch.matmul(a, b, out=c)
+        reps += 4
+        torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = reps * 2.0 * n**3 / (e0.elapsed_time(e1) * 1e-3) * 1e-12
+    del a, b, c
+    torch.cuda.empty_cache()
+    return {"burst_tflops": 2.0 * n**3 / (best * 1e-3) * 1e-12, "sustained_tflops": sustained,
+            "how": f"torch.matmul float64 {n}^3 (cuBLAS Dgemm) in this process: best of 5, and back to back for {seconds} s"}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
+    from gpras_b200.cells import fold_cell_map
     from gpras_b200.engine import ExactGP
     from gpras_b200.synth import make_cell_map, make_gp_data
-    from gpras_b200.cells import fold_cell_map
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,6 +244,23 @@ def run_ours(args) -> None:
     data = make_gp_data(n, d, p, 4096, seed=0)
     thetas = make_thetas(W + K, d, seed=2 + rank)  # every rank = its own shard of restarts / candidates
     stream = torch.cuda.current_stream()
+    hbm_gbs, hbm_src = hbm_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- FP64 roofline denominator, measured here and now ----------------------------------------
+    fp64 = measure_fp64_peak(torch)
+    barrier()
+
     # C independent evaluations in flight per GPU (independent restarts / candidates): each handle owns its workspace
     # and stream, so one evaluation's latency-bound Cholesky tail overlaps another's dense products.
     C = max(1, args.concurrent)
@@ -189,12 +273,7 @@ def run_ours(args) -> None:
         gps.append(g_)
     gp = gps[0]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def run_evals(idx0, count, out=None, host_xy=None):
+    def run_evals(th, count, out=None, host_xy=None):
         """Round-robin `count` evaluations over the C handles; returns when all results are on the host.
         host_xy = (x, y) pinned host arrays: upload them before every evaluation (the end-to-end path)."""
         pending = [None] * C
@@ -206,7 +285,7 @@ def run_ours(args) -> None:
                     out[pending[c], 0], out[pending[c], 1:] = lml, g
             if host_xy is not None:
                 gps[c].set_data(*host_xy)
-            gps[c].enqueue(thetas[idx0 + i])
+            gps[c].enqueue(th[i % len(th)])
             pending[c] = i
         for c in range(C):
             if pending[c] is not None:
@@ -214,31 +293,38 @@ def run_ours(args) -> None:
                 if out is not None:
                     out[pending[c], 0], out[pending[c], 1:] = lml, g
 
-    results = np.zeros((K, 3 + d))
-    # ---- resident-input throughput -------------------------------------------------------------
-    run_evals(0, W)
+    def gather_results(res):
+        """The path's only exchange: all-gather of the per-restart [LML, grad] rows."""
+        if world > 1:
+            loc = torch.from_numpy(res).cuda()
+            allr = torch.empty((world * res.shape[0], res.shape[1]), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allr, loc)
+            return allr
+        return None
+
+    def timed_region(th, count, host_xy=None):
+        """`count` evaluations per rank + the all-gather, bracketed by barrier + synchronize; device time, max over ranks."""
+        res = np.zeros((count, 3 + d))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for st in streams:
+            st.wait_stream(stream)
+        run_evals(th, count, res, host_xy)
+        for st in streams:
+            stream.wait_stream(st)
+        gather_results(res)
+        e1.record(stream)
+        barrier()
+        return reduce_max(e0.elapsed_time(e1)), res
+
+    # ---- resident-input throughput (the headline `value`) ------------------------------------------
+    run_evals(thetas[:W], W)
     launches_per_eval = gp.last_launches()
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for st in streams:
-        st.wait_stream(stream)
-    run_evals(W, K, results)
-    for st in streams:
-        stream.wait_stream(st)
-    if world > 1:  # the path's only exchange: all-gather of per-restart [LML, grad] rows
-        loc = torch.from_numpy(results).cuda()
-        allr = torch.empty((world * K, 3 + d), dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(allr, loc)
-    e1.record(stream)
-    barrier()
+    ms_total, results = timed_region(thetas[W:], K)
     clocks = sampler.stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
     value = world * K / (ms_total * 1e-3)
 
     # ---- the timed results must not depend on what else was in flight: recompute two of them alone ----
@@ -247,93 +333,210 @@ def run_ours(args) -> None:
         lml1, g1 = gp.lml_grad(thetas[W + i])
         verified = verified and lml1 == results[i, 0] and bool(np.array_equal(g1, results[i, 1:]))
 
-    # ---- stage timing for the roofline (separate pass; event records perturb nothing measurable) --
+    # ---- end to end through the host-buffer C-ABI entry point: same work, same all-gather --------------
+    xp = torch.from_numpy(data.x).pin_memory().numpy()
+    yp = torch.from_numpy(data.y).pin_memory().numpy()
+    run_evals(thetas[:2], 2, host_xy=(xp, yp))
+    ms_e2e, _ = timed_region(thetas[W:], K, host_xy=(xp, yp))
+    e2e_value = world * K / (ms_e2e * 1e-3)
+    h2d = 8 * (n * d + n * p + 2 + d)
+    d2h = 8 * (3 + d) + 4
+
+    # ---- sustained: the same loop for >= 3 s (power / clock behaviour of a long run) -------------------
+    sustained = None
+    if not args.quick:
+        per = max(K, 10)
+        sampler = ClockSampler(local)
+        sampler.start()
+        t_ms, count = 0.0, 0
+        while t_ms < 3000.0:
+            ms_i, _ = timed_region(thetas[W:], per)
+            t_ms += ms_i
+            count += per
+        sc = sampler.stop()
+        sustained = {"value": world * count / (t_ms * 1e-3), "unit": UNIT, "seconds": t_ms * 1e-3, "evals_per_gpu": count, "clocks": sc}
+
+    # ---- stage timing for the roofline detail (separate pass; event records perturb nothing measurable) --
     gp.set_stage_timing(True)
     stage = []
     for i in range(min(K, 5)):
         gp.lml_grad(thetas[W + i])
         stage.append(gp.last_stage_ms())
     gp.set_stage_timing(False)
-    dense_ms = float(np.mean([s["potrf"] + s["trtri"] + s["lauum"] + s["alpha"] for s in stage]))
     stage_mean = {k: float(np.mean([s[k] for s in stage])) for k in stage[0]}
-    achieved = f_eval(n, p) / (dense_ms * 1e-3) * 1e-12
     third = float(n) ** 3 / 3.0
     per_stage = {k: third / (stage_mean[k] * 1e-3) * 1e-12 for k in ("potrf", "trtri", "lauum")}
-
-    # ---- end to end through the host-buffer C-ABI entry point ------------------------------------
-    xp = torch.from_numpy(data.x).pin_memory().numpy()
-    yp = torch.from_numpy(data.y).pin_memory().numpy()
-    run_evals(0, 2, host_xy=(xp, yp))
-    barrier()
-    t0 = time.perf_counter()
-    run_evals(W, K, host_xy=(xp, yp))
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * K / float(dt.item())
-    h2d = 8 * (n * d + n * p + 2 + d)
-    d2h = 8 * (3 + d) + 4
+    peak = fp64["sustained_tflops"]
+    job_tflops = value / world * f_eval(n, p) * 1e-12
+    ncu = ncu_inputs()
+    roofline = {
+        "bound": "tensor", "achieved": job_tflops, "peak": peak, "unit": "TFLOP/s", "frac": job_tflops / peak,
+        "traffic": ncu.get("eval_dram_bytes"),
+        "what": f"job level: F_eval = N^3 + 3 N^2 P = {f_eval(n, p):.4g} FLOP per evaluation x measured evaluations/s per GPU ({C} in flight)",
+        "peak_source": "cuBLAS Dgemm 8192^3 sustained, measured in this run (MEASURED_PEAKS.json has no FP64 entry); burst "
+                       f"{fp64['burst_tflops']:.2f} TFLOP/s",
+        "algorithmic_bytes_per_eval": 16.0 * n * n + 16.0 * n * d + 8.0 * n * p,
+        "traffic_source": ncu.get("file"),
+        "detail": {
+            "one_evaluation_alone": {"ms": stage_mean["total"], "tflops": f_eval(n, p) / (stage_mean["total"] * 1e-3) * 1e-12,
+                                     "frac": f_eval(n, p) / (stage_mean["total"] * 1e-3) * 1e-12 / peak},
+            "stage_ms": stage_mean,
+            "stage_tflops_n3_over_3": per_stage,
+            "stage_frac": {k: v / peak for k, v in per_stage.items()},
+            "ncu": ncu,
+        },
+    }
 
     # ---- second headline: predicted cell-depths/s (predict + modes->cells on device, ring buffer) --
     predict = None
-    if rank == 0 or world > 1:
-        c = 200_000
-        cm = make_cell_map(p, c, seed=0)
-        e_mean, bias = fold_cell_map(cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices, cm.elevations)
-        gp.condition(thetas[0])
-        gp.set_cell_map(e_mean, bias)
-        xt = torch.from_numpy(data.x_test).cuda()
+    c_cells = 200_000
+    cm = make_cell_map(p, c_cells, seed=0)
+    e_mean, bias = fold_cell_map(cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices, cm.elevations)
+    gp.condition(thetas[0])
+    gp.set_cell_map(e_mean, bias)
+    xt = torch.from_numpy(data.x_test).cuda()
+    gp.predict_cells(xt, want_modes=False)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3 if args.quick else 12
+    p0.record(stream)
+    for _ in range(reps):
         gp.predict_cells(xt, want_modes=False)
-        barrier()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        p0.record(stream)
-        for _ in range(reps):
-            gp.predict_cells(xt, want_modes=False)
-        p1.record(stream)
-        barrier()
-        pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
-        t_events = world * reps * xt.shape[0]
-        predict = {
-            "metric": "predicted cell-depths/s", "value": t_events * c / (float(pms.item()) * 1e-3), "unit": "cell-depths/s",
-            "events_per_s": t_events / (float(pms.item()) * 1e-3), "cells": c, "events_per_rank": int(xt.shape[0]),
-            "output": "mean+variance per cell written to a device ring buffer (T*C*16 B cannot be kept)",
-        }
+    p1.record(stream)
+    barrier()
+    pms = reduce_max(p0.elapsed_time(p1))
+    t_events = world * reps * xt.shape[0]
+    ev_s = t_events / (pms * 1e-3)
+    f_evt = float(n) ** 2 + 2.0 * n * p + 4.0 * p * c_cells  # SURVEY.md section 8d (general variance map: two P x C products)
+    f_exec = float(n) ** 2 + 2.0 * n * p + 2.0 * p * c_cells  # what runs: with one theta for all modes the cell variance is rank one
+    predict = {
+        "metric": "predicted cell-depths/s", "value": ev_s * c_cells, "unit": "cell-depths/s",
+        "events_per_s": ev_s, "cells": c_cells, "events_per_rank": int(xt.shape[0]) * reps, "seconds": pms * 1e-3,
+        "output": "mean+variance per cell written to a device ring buffer (T*C*16 B cannot be kept)",
+        "roofline": {
+            "bound": "tensor", "achieved": ev_s / world * f_exec * 1e-12, "peak": peak, "unit": "TFLOP/s",
+            "frac": ev_s / world * f_exec * 1e-12 / peak,
+            "what": "executed FP64 FLOP per event, N^2 + 2 N P + 2 P C (variance product, mean, modes->cells mean; the cell variance is "
+                    "rank one under a shared theta) x events/s per GPU",
+            "with_survey_f_evt": {"flops_per_event": f_evt, "achieved": ev_s / world * f_evt * 1e-12, "frac": ev_s / world * f_evt * 1e-12 / peak,
+                                  "what": "SURVEY.md 8d's F_evt = N^2 + 2 N P + 4 P C counts a second P x C product for the variance"},
+            "hbm": {"achieved_GBps": ev_s / world * 16.0 * c_cells * 1e-9, "peak_GBps": hbm_gbs,
+                    "frac": ev_s / world * 16.0 * c_cells * 1e-9 / hbm_gbs, "what": "16 B written per cell-depth (mean + variance)",
+                    "peak_source": hbm_src},
+        },
+    }
+    if not args.quick:
         # the same sweep with the consumer fused: depth conversion + every metric of gpras/metrics.py accumulated on the fly
         # against a resident truth block, the T x C prediction never written
         from gpras_b200.metrics import MetricsAccumulator
 
-        acc = MetricsAccumulator(c, reps * int(xt.shape[0]) + 1, device=local)
+        mreps = 3
+        acc = MetricsAccumulator(c_cells, mreps * int(xt.shape[0]) + 1, device=local)
         acc.set_elevations(cm.elevations, cm.elevations)
         gtr = torch.Generator(device="cuda").manual_seed(7 + rank)
-        truth = torch.rand(int(xt.shape[0]), c, dtype=torch.float64, device="cuda", generator=gtr) * 4 + 3
+        truth = torch.rand(int(xt.shape[0]), c_cells, dtype=torch.float64, device="cuda", generator=gtr) * 4 + 3
         acc.reset(0.0)
         acc.predict_update(gp, xt, truth)
         barrier()
         p0.record(stream)
         acc.reset(0.0)
-        for _ in range(reps):
+        for _ in range(mreps):
             acc.predict_update(gp, xt, truth)
         summary = acc.finalize(0.5)
         p1.record(stream)
         barrier()
-        fms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+        fms = reduce_max(p0.elapsed_time(p1))
         predict["fused_metrics"] = {
-            "value": t_events * c / (float(fms.item()) * 1e-3), "unit": "cell-depths/s",
+            "value": world * mreps * xt.shape[0] * c_cells / (fms * 1e-3), "unit": "cell-depths/s",
             "what": "predict -> cells -> depth -> all gpras/metrics.py reductions vs a resident truth block; nothing written per cell-depth",
             "rmse_aoi_toi": summary["rmse_aoi_toi"],
         }
         acc.close()
         del truth
 
+    # ---- BASELINE config 5: the stochastic prediction sweep, 1,000,000 events x 200,000 cells, events sharded over ranks ----
+    cfg5 = None
+    if not args.quick:
+        from gpras_b200.parallel import all_gather_rows, shard_rows
+
+        t_all = 1_000_000
+        lo, hi = shard_rows(t_all, rank, world)
+        gen = torch.Generator(device="cuda").manual_seed(11)
+        x_sweep = torch.randn((t_all, d), dtype=torch.float64, device="cuda", generator=gen)[lo:hi].contiguous()
+        barrier()
+        t0 = time.perf_counter()
+        mm, mv = gp.predict_cells(x_sweep, want_modes=True)  # mode-space results come back to the host
+        both = all_gather_rows(np.concatenate([mm, mv], axis=1), 2 * p)  # the path's exchange: mode-space prediction shards
+        torch.cuda.synchronize()
+        dt5 = reduce_max(time.perf_counter() - t0)
+        cfg5 = {"workload": f"cfg5: trained N={n} surrogate predicting {t_all} events x {c_cells} cells (mean + variance), events sharded over "
+                            f"{world} rank(s); cell-space output to a device ring buffer, mode-space (T x P) results all-gathered",
+                "scaling": "strong", "wall_s": dt5, "events_per_s": t_all / dt5, "cell_depths_per_s": t_all * c_cells / dt5,
+                "mode_rows_gathered": int(both.shape[0]), "events_per_rank": hi - lo}
+        del x_sweep, mm, mv, both
+
+    # ---- BASELINE config 3 as stated: 64 optimiser restarts sharded over the GPUs (fixed total work) ----
+    strong = None
+    if not args.quick:
+        from gpras_b200 import GPRAS
+        from gpras_b200.parallel import all_gather_rows
+        from gpras_b200.synth import random_starts
+
+        for g_ in gps[1:]:
+            g_.close()
+        gps = gps[:1]
+        r_total, maxiter = 64, 15
+        st3 = random_starts(r_total, 1, seed=2)  # the reference's own ranges (gpras/gpr.py:88-90), one scalar lengthscale per start
+        starts = np.concatenate([st3[:, :2], np.repeat(st3[:, 2:3], d, axis=1)], axis=1)
+        model = GPRAS(w["kernel"])
+        barrier()
+        t0 = time.perf_counter()
+        model.fit(data.x, data.y, None, "kmeans", "L-BFGS-B", ard=True, shared_kernel=True, device=local, restarts=starts,
+                  restart_lanes=C, max_iter=maxiter)
+        torch.cuda.synchronize()
+        dts = reduce_max(time.perf_counter() - t0)
+        m0 = model.models[0]
+        stats = all_gather_rows(np.array([[float(m0.n_evals), float(getattr(m0, "restart_busy_s", 0.0))]]), 2)
+        tab = m0.restart_table
+        strong = {
+            "workload": f"cfg3 as stated: {r_total} optimiser restarts (starts log-uniform in the reference's ranges) x L-BFGS-B(maxiter {maxiter}) "
+                        f"through GPRAS.fit(restarts=...), handed out to {world} rank(s) by a ticket counter, {C} restarts in flight per GPU",
+            "scaling": "strong", "wall_s": dts, "evals": int(stats[:, 0].sum()), "evals_per_s": float(stats[:, 0].sum()) / dts,
+            "restarts_per_s": r_total / dts, "best_loss": float(np.min(tab[:, 1])), "restarts_not_positive_definite": int(np.sum(~np.isfinite(tab[:, 1]))),
+            "rank_busy_s": [float(v) for v in stats[:, 1]],
+            "imbalance": float(stats[:, 1].max() / max(stats[:, 1].mean(), 1e-12) - 1.0),
+        }
+        model._slot.release_other_threads()
+
+    # ---- BASELINE config 4: N = 16384, D = P = 64 (one GPU's worth of FP64 Cholesky near the HBM footprint of 3 N^2 doubles) ----
+    cfg4 = None
+    if not args.quick and rank == 0:
+        n4, d4 = 16384, 64
+        data4 = make_gp_data(n4, d4, d4, 0, seed=0)
+        g4 = ExactGP(w["kernel"], n4, d4, d4, device=local)
+        g4.set_data(data4.x, data4.y)
+        from gpras_b200.synth import fixed_theta
+
+        v4, s4, ls4 = fixed_theta(d4, True)
+        th4 = g4.theta_vector(v4, s4, ls4)
+        g4.lml_grad(th4)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        reps4 = 3
+        for _ in range(reps4):
+            g4.lml_grad(th4)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms4 = e0.elapsed_time(e1) / reps4
+        cfg4 = {"workload": f"cfg4: exact GP LML+grad, N={n4}, D=P={d4}, Matern52 ARD, one evaluation at a time on one GPU",
+                "ms_per_eval": ms4, "evals_per_s": 1e3 / ms4, "tflops": f_eval(n4, d4) / (ms4 * 1e-3) * 1e-12,
+                "frac_of_dgemm": f_eval(n4, d4) / (ms4 * 1e-3) * 1e-12 / peak, "device_bytes": 3 * 8 * n4 * n4}
+        g4.close()
+        del data4
+
     # ---- the cells -> modes side at BASELINE config 2 sizes: PCA fit and the forward transform ----
     preprocess = None
-    if rank == 0:
+    if rank == 0 and not args.quick:
         from gpras_b200.preprocess import PreProcessor
 
         sys.path.insert(0, str(ROOT / "tools"))
@@ -354,7 +557,7 @@ def run_ours(args) -> None:
         tr_s = (time.perf_counter() - t0) / 5
         preprocess = {"workload": f"PreProcessor: {ns} samples x {cells} cells, {modes} modes, inputs resident in HBM",
                       "fit_ms": fit_ms, "fit_iterations": pp.fit_info["iterations"], "transform_ms": tr_s * 1e3,
-                      "transform_GBps": 8.0 * ns * cells / tr_s * 1e-9, "transform_hbm_frac": 8.0 * ns * cells / tr_s * 1e-9 / 6543.7}
+                      "transform_GBps": 8.0 * ns * cells / tr_s * 1e-9, "transform_hbm_frac": 8.0 * ns * cells / tr_s * 1e-9 / hbm_gbs}
         pp.close()
         del xs_
 
@@ -368,36 +571,22 @@ def run_ours(args) -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"cfg3: exact GP LML+grad, N={n}, D={d}, P={p}, {w['kernel']} ARD + noise, shared theta; "
-                                   f"{K} restarts' evaluations per GPU, {C} in flight", "l2": "working set 1.5 GiB per eval >> 126 MB L2 (no flush needed)"},
+            "data": "synthetic", "config": config_block(),
+            "run": {"evaluations_per_gpu": K, "in_flight_per_gpu": C, "timed_region_s": ms_total * 1e-3,
+                    "exchange": "all-gather of the per-restart [LML, grad] rows inside both timed regions"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_eval * K,
             "verified": {"concurrent_equals_serial_bitwise": verified},
-            # Dominant kernel = the tile-GEMM engine (gemm_tile_kernel): ~90 % of the step.  Its largest single launch is
-            # K^-1 = W^T W (N^3/3 FLOP in ONE launch, timed live between CUDA events on its stream); `aggregate` is the same
-            # ratio over ALL dense stages of the evaluation (Cholesky chain and leaf kernels included), the harsher number.
-            "roofline": {"bound": "tensor", "achieved": per_stage["lauum"], "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
-                         "frac": per_stage["lauum"] / FP64_DGEMM_TFLOPS, "traffic": NCU["lauum_dram_bytes"],
-                         "kernel": "gemm_tile_kernel<128x128, k-major A, k-major B> (W^T W launch, N^3/3 FLOP)",
-                         "flops_per_launch": third, "ms_per_launch": stage_mean["lauum"],
-                         "algorithmic_bytes_per_launch": 8.0 * n * n, "peak_source": FP64_PEAK_SOURCE,
-                         "aggregate": {"what": "all dense stages of one evaluation: potrf + inverse + W^T W + alpha (F_eval = N^3 + 3 N^2 P)",
-                                       "achieved": achieved, "frac": achieved / FP64_DGEMM_TFLOPS, "flops_per_eval": f_eval(n, p),
-                                       "dense_ms_per_eval": dense_ms},
-                         "job": {"what": "F_eval x measured evals/s of the timed region (two evaluations in flight per GPU)",
-                                 "achieved": value / world * f_eval(n, p) * 1e-12, "frac": value / world * f_eval(n, p) * 1e-12 / FP64_DGEMM_TFLOPS},
-                         "stage_tflops": per_stage,
-                         "ncu": {"source": NCU["source"], "whole_eval_dram_bytes": NCU["eval_dram_bytes"],
-                                 "whole_eval_algorithmic_bytes": 16.0 * n * n + 16.0 * n * d + 8.0 * n * p,
-                                 "lauum_launch": {"dram_bytes": NCU["lauum_dram_bytes"], "algorithmic_bytes": 8.0 * n * n,
-                                                  "dmma_pipe_active_pct": NCU["lauum_dmma_pct"]},
-                                 "syrk_launch": {"dram_bytes": NCU["syrk_dram_bytes"], "algorithmic_bytes": 2 * 1953 * 128 * 128 * 8.0,
-                                                 "dmma_pipe_active_pct": NCU["syrk_dmma_pct"]}}},
+            "roofline": roofline,
+            "fp64_peak": fp64,
+            "sustained": sustained,
             "stage_ms": stage_mean,
             "cpu_baseline": cpu,
             "predict": predict,
+            "cfg4": cfg4,
+            "cfg5_sweep": cfg5,
+            "strong": strong,
             "preprocess": preprocess,
         }
         print(json.dumps(line), flush=True)
@@ -414,6 +603,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + predict legs only (profiling runs)")
     ap.add_argument("--concurrent", type=int, default=2, help="independent evaluations in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":

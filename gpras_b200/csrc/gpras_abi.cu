@@ -73,6 +73,11 @@ struct gpras_gp {
   int c = 0, c_pad = 0, p16 = 0;
   double *E1 = nullptr, *E2 = nullptr, *rootS = nullptr, *bias = nullptr, *zbias = nullptr, *ring_m = nullptr, *ring_v = nullptr;
   cudaEvent_t ev[8] = {};
+  // prediction pipeline: batch b's consumer (modes -> cells, or the fused metrics) runs on stream2 while batch b+1's
+  // predictor runs on `stream`; the small mode-space buffers are double-buffered, `mean / var / varm` point at the current set
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_pred[2] = {}, ev_cons[2] = {};
+  double *mean_b[2] = {nullptr, nullptr}, *var_b[2] = {nullptr, nullptr}, *varm_b[2] = {nullptr, nullptr};
   double stage_ms[7] = {};
   LookAhead la;
   // CUDA-graph replay of the evaluation (index: want_grad)
@@ -313,10 +318,16 @@ int gpras_gp_destroy(gpras_gp* h) {
   if (!h) return 0;
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  double* bufs[] = {h->Xt, h->Xts, h->Ks, h->mean, h->vpart, h->var, h->varm, h->E1, h->E2, h->bias, h->zbias, h->ring_m, h->ring_v,
-                    h->rootS};
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
+  double* bufs[] = {h->Xt, h->Xts, h->Ks, h->mean_b[0], h->mean_b[1], h->vpart, h->var_b[0], h->var_b[1], h->varm_b[0], h->varm_b[1],
+                    h->E1, h->E2, h->bias, h->zbias, h->ring_m, h->ring_v, h->rootS};
   for (double* b : bufs)
     if (b) cudaFree(b);
+  for (auto& e : h->ev_pred)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_cons)
+    if (e) cudaEventDestroy(e);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->arena) cudaFree(h->arena);
   if (h->h_arena) cudaFreeHost(h->h_arena);
   for (auto& e : h->ev)
@@ -405,14 +416,23 @@ int gpras_gp_condition(gpras_gp* h, const double* theta) {
   return 0;
 }
 
+static void use_predict_set(gpras_gp* h, int k) { h->mean = h->mean_b[k], h->var = h->var_b[k], h->varm = h->varm_b[k]; }
+
 static int ensure_predict_buffers(gpras_gp* h) {
   if (h->Xt) return 0;
   int r;
   if ((r = dalloc(&h->Xt, (size_t)PRED_TB * h->d)) || (r = dalloc(&h->Xts, (size_t)PRED_TB * h->d)) ||
-      (r = dalloc(&h->Ks, (size_t)PRED_TB * h->n_pad)) || (r = dalloc(&h->mean, (size_t)PRED_TB * h->p_pad)) ||
-      (r = dalloc(&h->vpart, (size_t)h->nt * PRED_TB)) || (r = dalloc(&h->var, PRED_TB)) ||
-      (r = dalloc(&h->varm, (size_t)PRED_TB * h->p_pad)))
+      (r = dalloc(&h->Ks, (size_t)PRED_TB * h->n_pad)) || (r = dalloc(&h->vpart, (size_t)h->nt * PRED_TB)))
     return r;
+  for (int k = 0; k < 2; k++) {
+    if ((r = dalloc(&h->mean_b[k], (size_t)PRED_TB * h->p_pad)) || (r = dalloc(&h->var_b[k], PRED_TB)) ||
+        (r = dalloc(&h->varm_b[k], (size_t)PRED_TB * h->p_pad)))
+      return r;
+    CU(cudaEventCreateWithFlags(&h->ev_pred[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_cons[k], cudaEventDisableTiming));
+  }
+  CU(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  use_predict_set(h, 0);
   return 0;
 }
 
@@ -535,11 +555,17 @@ int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_devic
     if ((r = dalloc(&h->ring_m, (size_t)CELL_TB * h->c_pad)) || (r = dalloc(&h->ring_v, (size_t)CELL_TB * h->c_pad)))
       return r;
   }
-  cudaStream_t s = h->stream;
+  cudaStream_t s = h->stream, s2 = h->stream2;
   h->launches = 0;
-  for (int t0 = 0; t0 < t; t0 += PRED_TB) {
+  // Software pipeline over batches: the predictor of batch b+1 (FP64 tensor pipe: the N^2 T variance product) overlaps the
+  // modes -> cells expansion of batch b (HBM-write bound) on a second stream.
+  int batch = 0;
+  for (int t0 = 0; t0 < t; t0 += PRED_TB, batch++) {
     const int tb = t - t0 < PRED_TB ? t - t0 : PRED_TB;
     const int tb_pad = round_up(tb, 128);
+    const int k = batch & 1;
+    if (batch >= 2) CU(cudaStreamWaitEvent(s, h->ev_cons[k], 0));  // the expansion that read this buffer set is done
+    use_predict_set(h, k);
     if ((r = stage_test_rows(h, xs, t0, tb, tb_pad, xs_on_device))) return r;
     if ((r = predict_batch(h, tb, tb_pad))) return r;
     long tot = (long)tb_pad * h->p_pad;
@@ -552,6 +578,8 @@ int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_devic
     if (mode_var)
       CU(cudaMemcpy2DAsync(mode_var + (size_t)t0 * h->p, sizeof(double) * h->p, h->varm, sizeof(double) * h->p_pad,
                            sizeof(double) * h->p, tb, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(h->ev_pred[k], s));
+    CU(cudaStreamWaitEvent(s2, h->ev_pred[k], 0));
     // modes -> cells: one streaming kernel per batch (column tile per CTA, row tiles streamed)
     {
       const bool keep = cell_mean != nullptr && cell_var != nullptr;
@@ -563,17 +591,19 @@ int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_devic
       const int per_cta = (t_tiles + 1) / 2;
       dim3 grid(h->c_pad / 128, (t_tiles + per_cta - 1) / per_cta);
       if (h->p16 == 32)
-        cells_kernel<32><<<grid, CELLS_THREADS, CellsCfg<32>::SMEM_BYTES, s>>>(h->mean, h->p_pad, h->var, h->E1, h->c_pad, h->bias,
-                                                                             h->E2, om, ov, ldo, t_tiles, per_cta, ring_rows);
+        cells_kernel<32><<<grid, CELLS_THREADS, CellsCfg<32>::SMEM_BYTES, s2>>>(h->mean, h->p_pad, h->var, h->E1, h->c_pad, h->bias,
+                                                                              h->E2, om, ov, ldo, t_tiles, per_cta, ring_rows);
       else
-        cells_kernel<64><<<grid, CELLS_THREADS, CellsCfg<64>::SMEM_BYTES, s>>>(h->mean, h->p_pad, h->var, h->E1, h->c_pad, h->bias,
-                                                                             h->E2, om, ov, ldo, t_tiles, per_cta, ring_rows);
+        cells_kernel<64><<<grid, CELLS_THREADS, CellsCfg<64>::SMEM_BYTES, s2>>>(h->mean, h->p_pad, h->var, h->E1, h->c_pad, h->bias,
+                                                                              h->E2, om, ov, ldo, t_tiles, per_cta, ring_rows);
       h->launches++;
       CU(cudaGetLastError());
     }
+    CU(cudaEventRecord(h->ev_cons[k], s2));
     if (!xs_on_device) CU(cudaStreamSynchronize(s));
   }
   CU(cudaStreamSynchronize(s));
+  CU(cudaStreamSynchronize(s2));
   return 0;
 }
 

@@ -182,13 +182,19 @@ int gpras_gp_predict_metrics(gpras_gp* h, gpras_metrics* m, const double* xs, in
   DeviceGuard guard(h->device);
   int r;
   if ((r = ensure_predict_buffers(h))) return r;
-  cudaStream_t s = h->stream;
+  cudaStream_t s = h->stream, s2 = h->stream2;
   CU(cudaStreamSynchronize(m->stream));
   h->launches = 0;
   const int l0 = m->launches;
-  for (int t0 = 0; t0 < t; t0 += PRED_TB) {
+  // Same two-stream pipeline as gpras_gp_predict_cells: the metrics consumer of batch b runs while batch b+1 is predicted.
+  const bool host_truth = truth && !truth_on_device;
+  int batch = 0;
+  for (int t0 = 0; t0 < t; t0 += PRED_TB, batch++) {
     const int tb = t - t0 < PRED_TB ? t - t0 : PRED_TB;
     const int tb_pad = round_up(tb, 128);
+    const int k = batch & 1;
+    if (batch >= 2) CU(cudaStreamWaitEvent(s, h->ev_cons[k], 0));
+    use_predict_set(h, k);
     if ((r = stage_test_rows(h, xs, t0, tb, tb_pad, xs_on_device))) return r;
     if ((r = predict_batch(h, tb, tb_pad))) return r;
     if (mode_mean)
@@ -215,10 +221,17 @@ int gpras_gp_predict_metrics(gpras_gp* h, gpras_metrics* m, const double* xs, in
         a.X = m->stage[0], a.ldx = m->c_pad;
       }
     }
-    if ((r = metrics_block(m, s, a, tb, h->p16, true))) return r;
-    if (!xs_on_device || (truth && !truth_on_device)) CU(cudaStreamSynchronize(s));
+    CU(cudaEventRecord(h->ev_pred[k], s));
+    CU(cudaStreamWaitEvent(s2, h->ev_pred[k], 0));
+    if ((r = metrics_block(m, s2, a, tb, h->p16, true))) return r;
+    CU(cudaEventRecord(h->ev_cons[k], s2));
+    if (!xs_on_device || host_truth) {  // pageable host buffers / the single truth staging buffer: keep batches ordered
+      CU(cudaStreamSynchronize(s));
+      if (host_truth) CU(cudaStreamSynchronize(s2));
+    }
   }
   CU(cudaStreamSynchronize(s));
+  CU(cudaStreamSynchronize(s2));
   h->launches += m->launches - l0;
   return 0;
 }

@@ -494,18 +494,21 @@ def _optimize_bfgs(model, max_iter: int, *, bounds=None, **scipy_options: Any) -
 
     def fun(u):
         try:
-            f, g = model.loss_and_grad(u)
+            f, g = model.loss_and_grad(u) if np.all(np.isfinite(u)) else (np.nan, None)
+            bad = not (np.isfinite(f) and np.all(np.isfinite(g)))
         except np.linalg.LinAlgError:  # NotPositiveDefiniteError is one
+            bad = True
+        if bad:
             if not good:
-                raise  # the start itself is not positive definite: nothing to back off to
-            # A line-search trial point stepped outside the positive-definite region.  Answer with the mirror image of the
-            # last good point's descent (value above it by half the predicted decrease, slope reversed): the line search's
-            # quadratic interpolation then retries at a third of the step instead of aborting the fit.
-            d = u - good["u"]
+                raise np.linalg.LinAlgError("the start itself has no finite objective (covariance matrix not positive definite)")
+            # A line-search trial point stepped outside the region where the covariance matrix factorises.  Answer with the
+            # mirror image of the last good point's descent (value above it by half the predicted decrease, slope reversed):
+            # the line search's quadratic interpolation then retries at a third of the step instead of aborting the fit.
+            d = np.nan_to_num(u - good["u"], nan=0.0, posinf=1e6, neginf=-1e6)
             slope = float(good["g"] @ d)
             nd = float(d @ d)
             if nd == 0.0 or not slope < 0.0:
-                raise
+                return good["f"] + 1.0, np.zeros_like(good["g"])
             return good["f"] - 0.5 * slope, (-slope / nd) * d
         if not good or f <= good["f"]:
             good.update(u=np.array(u, np.float64), f=float(f), g=np.array(g, np.float64))
