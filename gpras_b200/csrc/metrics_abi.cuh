@@ -25,6 +25,7 @@ template <int P16>
 int prepare_metrics_kernels() {
   int r;
   if ((r = opt_in_smem(metrics_stream_kernel<P16, true>, MetCfg<P16>::SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(metrics_plain_tma_kernel, MPT_SMEM_BYTES))) return r;
   return 0;
 }
 
@@ -50,7 +51,17 @@ int metrics_block(gpras_metrics* m, cudaStream_t s, MetricsArgs a, int t, int p1
     else
       metrics_stream_kernel<64, true><<<grid, MET_THREADS, MetCfg<64>::SMEM_BYTES, s>>>(a);
   } else {
-    metrics_stream_kernel<32, false><<<grid, MET_THREADS, MET_PLAIN_SMEM_BYTES, s>>>(a);
+    // resident arrays: streamed by the TMA unit whenever tensor maps can describe them (16-byte aligned rows)
+    CUtensorMap xm, ym, cm;
+    static const bool no_tma = getenv("GPRAS_B200_NO_TMA") != nullptr;
+    const uint64_t rows = (uint64_t)t, cols = (uint64_t)m->c;
+    bool ok = !no_tma && tma_map_2d_f64(&ym, a.Y, cols, rows, (uint64_t)a.ldy, 128, MET_ROWS);
+    if (ok) ok = a.X ? tma_map_2d_f64(&xm, a.X, cols, rows, (uint64_t)a.ldx, 128, MET_ROWS) : (xm = ym, true);
+    if (ok) ok = a.CONF ? tma_map_2d_f64(&cm, a.CONF, cols, rows, (uint64_t)a.ldconf, 128, MET_ROWS) : (cm = ym, true);
+    if (ok)
+      metrics_plain_tma_kernel<<<grid, MET_THREADS, MPT_SMEM_BYTES, s>>>(xm, ym, cm, a);
+    else
+      metrics_stream_kernel<32, false><<<grid, MET_THREADS, MET_PLAIN_SMEM_BYTES, s>>>(a);
   }
   CU(cudaGetLastError());
   metrics_fold_cells_kernel<<<(unsigned)((m->c_pad + 255) / 256), 256, 0, s>>>(m->cell_part, splits, m->c_pad, m->state, m->first ? 1 : 0);

@@ -14,6 +14,7 @@
 // elevation vectors are supplied.  Reductions have a fixed shape (no atomics): results are bitwise repeatable.
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace gpras {
 
@@ -311,6 +312,163 @@ __global__ void __launch_bounds__(MET_THREADS, FUSED ? 2 : 1) metrics_stream_ker
   __syncthreads();
   if (tid < 2) {
     const double* r = sMisc + 8 * tid;
+    a.cta_part[((long)blockIdx.y * a.n_ctile + tj) * MET_CTAQ + tid] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  }
+}
+
+// ---- resident (T x C) arrays, streamed by the TMA unit ------------------------------------------------------------------
+// The !FUSED case above reads truth, prediction and confidence with per-thread loads and no prefetch across row tiles
+// (measured: 3.3 TB/s, half of HBM).  Here one thread keeps MPT_STAGES stages of three 32 x 128 boxes in flight
+// (cp.async.bulk.tensor -> shared memory, completion on an mbarrier) and the arithmetic runs out of shared memory.  Warp w owns
+// rows w, w + 8, w + 16, w + 24 of a row tile and all 128 columns of the CTA's slab (lane l: columns 2l, 2l+1, 64+2l, 65+2l), so
+// a row sum is one warp reduction and the per-cell partials stay in registers until the CTA ends.  Same outputs, same
+// fixed-shape reductions (bitwise repeatable) as metrics_stream_kernel<.., false>.
+constexpr int MPT_STAGES = 2;
+constexpr int MPT_BOX_DOUBLES = MET_ROWS * 128;
+constexpr int MPT_SMEM_BYTES = MPT_STAGES * 3 * MPT_BOX_DOUBLES * (int)sizeof(double) + 128;
+
+static __global__ void __launch_bounds__(MET_THREADS, 1)
+metrics_plain_tma_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
+                         const __grid_constant__ CUtensorMap cmap, const MetricsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[MPT_STAGES];
+  double* tiles = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tj = blockIdx.x;
+  const int t_begin = blockIdx.y * a.tiles_per_cta;
+  int t_end = t_begin + a.tiles_per_cta;
+  if (t_end > a.t_tiles) t_end = a.t_tiles;
+  const int n_it = t_end > t_begin ? t_end - t_begin : 0;
+  const bool has_x = a.X != nullptr, has_cf = a.CONF != nullptr;
+  const bool has_ex = a.elev_x != nullptr, has_ey = a.elev_y != nullptr;
+  const uint32_t stage_bytes = (uint32_t)((1 + (has_x ? 1 : 0) + (has_cf ? 1 : 0)) * MPT_BOX_DOUBLES * sizeof(double));
+  if (tid == 0) {
+    for (int s = 0; s < MPT_STAGES; s++) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int s, int tt) {
+    double* base = tiles + s * 3 * MPT_BOX_DOUBLES;
+    mbar_expect_tx(&full[s], stage_bytes);
+    tma_load_2d(base, &ymap, tj * 128, tt * MET_ROWS, &full[s]);
+    if (has_x) tma_load_2d(base + MPT_BOX_DOUBLES, &xmap, tj * 128, tt * MET_ROWS, &full[s]);
+    if (has_cf) tma_load_2d(base + 2 * MPT_BOX_DOUBLES, &cmap, tj * 128, tt * MET_ROWS, &full[s]);
+  };
+  if (tid == 0)
+    for (int s = 0; s < MPT_STAGES && s < n_it; s++) issue(s, t_begin + s);
+
+  // this lane's four columns: 2l, 2l+1, 64+2l, 65+2l of the slab
+  long col[4];
+  bool cok[4];
+  double ex[4], ey[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    col[j] = (long)tj * 128 + 64 * (j >> 1) + 2 * lane + (j & 1);
+    cok[j] = col[j] < a.c;
+    ex[j] = (has_ex && cok[j]) ? a.elev_x[col[j]] : 0.0;
+    ey[j] = (has_ey && cok[j]) ? a.elev_y[col[j]] : 0.0;
+  }
+  double c_e[4], c_e2[4], c_cf[4], c_mx[4], c_my[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) c_e[j] = c_e2[j] = c_cf[j] = 0.0, c_mx[j] = c_my[j] = -INFINITY;
+  double s_ab = 0.0, s_ct = 0.0;
+
+  for (int it = 0; it < n_it; it++) {
+    const int s = it % MPT_STAGES, tt = t_begin + it;
+    const int row_base = tt * MET_ROWS;
+    mbar_wait(&full[s], (it / MPT_STAGES) & 1);
+    const double* ty = tiles + s * 3 * MPT_BOX_DOUBLES;
+    const double* tx = ty + MPT_BOX_DOUBLES;
+    const double* tc = ty + 2 * MPT_BOX_DOUBLES;
+#pragma unroll
+    for (int rr = 0; rr < MET_ROWS / 8; rr++) {
+      const int rl = warp + 8 * rr;
+      const bool rok = row_base + rl < a.t_rows;
+      double xv[4], yv[4], cv[4];
+#pragma unroll
+      for (int hlf = 0; hlf < 2; hlf++) {
+        const int o = rl * 128 + 64 * hlf + 2 * lane;
+        const double2 y2 = *reinterpret_cast<const double2*>(ty + o);
+        yv[2 * hlf] = y2.x, yv[2 * hlf + 1] = y2.y;
+        if (has_x) {
+          const double2 x2 = *reinterpret_cast<const double2*>(tx + o);
+          xv[2 * hlf] = x2.x, xv[2 * hlf + 1] = x2.y;
+        } else {
+          xv[2 * hlf] = xv[2 * hlf + 1] = 0.0;
+        }
+        if (has_cf) {
+          const double2 c2 = *reinterpret_cast<const double2*>(tc + o);
+          cv[2 * hlf] = c2.x, cv[2 * hlf + 1] = c2.y;
+        } else {
+          cv[2 * hlf] = cv[2 * hlf + 1] = 0.0;
+        }
+      }
+      double r_e = 0.0, r_e2 = 0.0, r_cf = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool ok = rok && cok[j];
+        double x = xv[j], y = yv[j] - ey[j];
+        if (has_ex) x = fmax(x - ex[j], 0.0);
+        if (has_ey) y = fmax(y, 0.0);
+        const double e = ok ? x - y : 0.0;
+        const double cf = ok ? cv[j] : 0.0;
+        if (ok) {
+          c_mx[j] = fmax(c_mx[j], x);
+          c_my[j] = fmax(c_my[j], y);
+          s_ct += fabs(e) <= a.v_tol ? 1.0 : 0.0;
+        }
+        c_e[j] += e;
+        c_e2[j] = fma(e, e, c_e2[j]);
+        c_cf[j] += cf;
+        r_e += e;
+        r_e2 = fma(e, e, r_e2);
+        r_cf += cf;
+        s_ab += fabs(e);
+      }
+      r_e = warp_sum(r_e), r_e2 = warp_sum(r_e2), r_cf = warp_sum(r_cf);
+      if (lane == 0) {
+        const long rix = (long)row_base + rl;
+        a.row_part[((long)0 * a.t_tiles * MET_ROWS + rix) * a.n_ctile + tj] = r_e;
+        a.row_part[((long)1 * a.t_tiles * MET_ROWS + rix) * a.n_ctile + tj] = r_e2;
+        a.row_part[((long)2 * a.t_tiles * MET_ROWS + rix) * a.n_ctile + tj] = r_cf;
+      }
+    }
+    __syncthreads();  // every warp is done with this stage: refill it
+    if (tid == 0 && it + MPT_STAGES < n_it) issue(s, tt + MPT_STAGES);
+  }
+
+  // ---- per-cell partials: combine the eight warps (fixed order) through shared memory ----
+  double* red = tiles;  // [8 warps][MET_CELLQ][128]
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int cl = 64 * (j >> 1) + 2 * lane + (j & 1);
+    red[(warp * MET_CELLQ + 0) * 128 + cl] = c_e[j];
+    red[(warp * MET_CELLQ + 1) * 128 + cl] = c_e2[j];
+    red[(warp * MET_CELLQ + 2) * 128 + cl] = c_cf[j];
+    red[(warp * MET_CELLQ + 3) * 128 + cl] = c_mx[j];
+    red[(warp * MET_CELLQ + 4) * 128 + cl] = c_my[j];
+  }
+  s_ab = warp_sum(s_ab);
+  s_ct = warp_sum(s_ct);
+  double* misc = tiles + 8 * MET_CELLQ * 128;
+  if (lane == 0) misc[warp] = s_ab, misc[8 + warp] = s_ct;
+  __syncthreads();
+  if (tid < 128) {
+    double v[MET_CELLQ] = {0.0, 0.0, 0.0, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      v[0] += red[(w * MET_CELLQ + 0) * 128 + tid];
+      v[1] += red[(w * MET_CELLQ + 1) * 128 + tid];
+      v[2] += red[(w * MET_CELLQ + 2) * 128 + tid];
+      v[3] = fmax(v[3], red[(w * MET_CELLQ + 3) * 128 + tid]);
+      v[4] = fmax(v[4], red[(w * MET_CELLQ + 4) * 128 + tid]);
+    }
+    double* o = a.cell_part + (long)blockIdx.y * MET_CELLQ * a.c_pad + (long)tj * 128 + tid;
+#pragma unroll
+    for (int qq = 0; qq < MET_CELLQ; qq++) o[(long)qq * a.c_pad] = v[qq];
+  }
+  if (tid < 2) {
+    const double* r = misc + 8 * tid;
     a.cta_part[((long)blockIdx.y * a.n_ctile + tj) * MET_CTAQ + tid] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
   }
 }

@@ -63,13 +63,30 @@ int launch_project(cudaStream_t s, const double* X, long ldx, int n, int c, cons
   const int n_pad = round_up(n, 128);
   const int row_tiles = n_pad / 128;
   const int k_stages = (int)(c_pad / PROJ_BK);
-  int nz = (8 * 148 + row_tiles - 1) / row_tiles;  // ~4 waves of 2 CTAs per SM: the tail stays below ~10%
+  // Split the cells so that the grid is a whole number of waves of 2 CTAs per SM (a partial last wave costs a full CTA time:
+  // measured 4.4 -> 5.0 TB/s at 8192 x 200 000, 16 modes, from fixing this alone), as many waves as keep >= 40 stages per CTA.
+  static const int waves_env = getenv("GPRAS_B200_PROJ_WAVES") ? atoi(getenv("GPRAS_B200_PROJ_WAVES")) : 0;
+  int nz = 1;
+  for (int w = 1; w <= 8; w++) {
+    const int cand = (2 * 148 * w) / row_tiles;
+    if (cand < 1) continue;
+    if (waves_env ? w == waves_env : (k_stages / cand >= 40 || nz == 1)) nz = cand;
+  }
   if (nz > (k_stages + 31) / 32) nz = (k_stages + 31) / 32;
   if (nz < 1) nz = 1;
   const int per = (k_stages + nz - 1) / nz;
   nz = (k_stages + per - 1) / per;
-  project_kernel<PN><<<dim3(row_tiles, nz), PROJ_THREADS, ProjCfg<PN>::SMEM_BYTES, s>>>(X, ldx, n, c, elev, clamp, mean, wfull, E,
-                                                                                      c_pad, k_stages, per, part, n_pad);
+  // The x stream goes through the TMA unit whenever a tensor map can describe it (16-byte aligned rows); otherwise the
+  // cp.async variant of the same kernel runs.  GPRAS_B200_NO_TMA=1 forces the latter (development comparisons).
+  CUtensorMap xmap;
+  static const bool no_tma = getenv("GPRAS_B200_NO_TMA") != nullptr;
+  if (!no_tma && tma_map_2d_f64(&xmap, X, (uint64_t)c, (uint64_t)n, (uint64_t)ldx, PROJ_BK, 128, true)) {
+    project_tma_kernel<PN><<<dim3(row_tiles, nz), PROJ_THREADS, ProjTmaCfg<PN>::SMEM_BYTES, s>>>(xmap, n, c, elev, clamp, mean, wfull, E,
+                                                                                               c_pad, k_stages, per, part, n_pad);
+  } else {
+    project_kernel<PN><<<dim3(row_tiles, nz), PROJ_THREADS, ProjCfg<PN>::SMEM_BYTES, s>>>(X, ldx, n, c, elev, clamp, mean, wfull, E,
+                                                                                        c_pad, k_stages, per, part, n_pad);
+  }
   CU(cudaGetLastError());
   *nz_out = nz;
   return 0;
@@ -78,7 +95,7 @@ int launch_project(cudaStream_t s, const double* X, long ldx, int n, int c, cons
 int project_splits_max(int n, long c_pad) {
   const int row_tiles = round_up(n, 128) / 128;
   const int k_stages = (int)(c_pad / PROJ_BK);
-  int nz = (8 * 148 + row_tiles - 1) / row_tiles;
+  int nz = (2 * 16 * 148 + row_tiles - 1) / row_tiles;  // upper bound over every GPRAS_B200_PROJ_WAVES setting
   if (nz > (k_stages + 31) / 32) nz = (k_stages + 31) / 32;
   return nz < 1 ? 1 : nz;
 }
@@ -341,7 +358,9 @@ int gpras_pre_create(gpras_pre** out, int device, int c, int hydraulic, double w
   if (device < 64 && !attr_done[device]) {
     if ((r = opt_in_smem(project_kernel<8>, ProjCfg<8>::SMEM_BYTES)) || (r = opt_in_smem(project_kernel<16>, ProjCfg<16>::SMEM_BYTES)) ||
         (r = opt_in_smem(project_kernel<32>, ProjCfg<32>::SMEM_BYTES)) || (r = opt_in_smem(project_kernel<64>, ProjCfg<64>::SMEM_BYTES)) ||
-        (r = opt_in_smem(jacobi_eig128_kernel, EIG_SMEM_BYTES)))
+        (r = opt_in_smem(project_tma_kernel<8>, ProjTmaCfg<8>::SMEM_BYTES)) || (r = opt_in_smem(project_tma_kernel<16>, ProjTmaCfg<16>::SMEM_BYTES)) ||
+        (r = opt_in_smem(project_tma_kernel<32>, ProjTmaCfg<32>::SMEM_BYTES)) || (r = opt_in_smem(project_tma_kernel<64>, ProjTmaCfg<64>::SMEM_BYTES)) ||
+        (r = opt_in_smem(colstats_tma_kernel, CS_SMEM_BYTES)) || (r = opt_in_smem(jacobi_eig128_kernel, EIG_SMEM_BYTES)))
       return r;
     attr_done[device] = true;
   }
@@ -429,7 +448,12 @@ int gpras_pre_fit(gpras_pre* h, const double* x, long ldx, int n, int on_device,
     const int rows_per = (n + splits - 1) / splits;
     splits = (n + rows_per - 1) / rows_per;
     PRE_TRY(palloc(h, &part, (size_t)splits * 3 * c_pad));
-    colstats_kernel<<<dim3(gx, splits), 128, 0, s>>>(xd, ldd, n, c, h->elev, clamp, rows_per, part, c_pad);
+    CUtensorMap xmap;
+    static const bool no_tma = getenv("GPRAS_B200_NO_TMA") != nullptr;
+    if (!no_tma && tma_map_2d_f64(&xmap, xd, (uint64_t)c, (uint64_t)n, (uint64_t)ldd, CS_COLS, CS_ROWS))
+      colstats_tma_kernel<<<dim3(gx, splits), 128, CS_SMEM_BYTES, s>>>(xmap, n, c, h->elev, clamp, rows_per, part, c_pad);
+    else
+      colstats_kernel<<<dim3(gx, splits), 128, 0, s>>>(xd, ldd, n, c, h->elev, clamp, rows_per, part, c_pad);
     PRE_CU(cudaGetLastError());
     colstats_finish_kernel<<<(unsigned)((c_pad + 255) / 256), 256, 0, s>>>(part, splits, c_pad, c, n, h->hp, h->elev, h->weights_in,
                                                                           h->wet_threshold, h->mean, h->wfull, h->cls);

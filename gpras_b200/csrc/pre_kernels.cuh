@@ -12,6 +12,7 @@
 // compaction is needed on the device (the host compacts when it hands eofs / input_mean back to Python).
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace gpras {
 
@@ -39,6 +40,66 @@ static __global__ void __launch_bounds__(128) colstats_kernel(const double* __re
     mx0 = fmax(mx0, v0), mn0 = fmin(mn0, v0), s0 += v0;
     mx1 = fmax(mx1, v1), mn1 = fmin(mn1, v1), s1 += v1;
   }
+  double* o = part + (long)blockIdx.y * 3 * c_pad;
+  o[c0] = mx0, o[c_pad + c0] = mn0, o[2 * c_pad + c0] = s0;
+  if (two) o[c0 + 1] = mx1, o[c_pad + c0 + 1] = mn1, o[2 * c_pad + c0 + 1] = s1;
+}
+
+// The same statistics with the matrix streamed by the TMA unit: a CTA owns a slab of 256 columns and a row range, one thread
+// keeps CS_STAGES boxes of CS_ROWS x 256 values in flight (cp.async.bulk.tensor -> shared memory, completion on an mbarrier),
+// all 128 threads reduce their two columns out of shared memory.  Measured on B200 (tools/microbench/read_bw.cu, 8192 x
+// 200 000): LDG slabs 4.2-5.3 TB/s, TMA boxes 7.4-7.5 TB/s (contiguous reads: 7.15 TB/s).  Out-of-range rows / columns of a
+// box read as zero and are masked here (rows by the loop bound, columns by `c`).
+constexpr int CS_ROWS = 16, CS_COLS = 256, CS_STAGES = 4;
+constexpr int CS_SMEM_BYTES = CS_STAGES * CS_ROWS * CS_COLS * (int)sizeof(double) + 128;
+static __global__ void __launch_bounds__(128) colstats_tma_kernel(const __grid_constant__ CUtensorMap map, int n, int c,
+                                                                  const double* __restrict__ elev, int clamp, int rows_per_split,
+                                                                  double* __restrict__ part, long c_pad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[CS_STAGES];
+  double* tile = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  constexpr int STAGE_DOUBLES = CS_ROWS * CS_COLS;
+  constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * sizeof(double);
+  const int tid = threadIdx.x;
+  const int slab0 = blockIdx.x * CS_COLS;
+  const int c0 = slab0 + 2 * tid;
+  const int r0 = blockIdx.y * rows_per_split;
+  int r1 = r0 + rows_per_split;
+  if (r1 > n) r1 = n;
+  const int n_it = r1 > r0 ? (r1 - r0 + CS_ROWS - 1) / CS_ROWS : 0;
+  if (tid == 0) {
+    for (int s = 0; s < CS_STAGES; s++) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int s = 0; s < CS_STAGES && s < n_it; s++) {
+      mbar_expect_tx(&full[s], STAGE_BYTES);
+      tma_load_2d(tile + s * STAGE_DOUBLES, &map, slab0, r0 + s * CS_ROWS, &full[s]);
+    }
+  const bool live0 = c0 < c, two = c0 + 1 < c;
+  const double e0 = (clamp && live0) ? elev[c0] : 0.0, e1 = (clamp && two) ? elev[c0 + 1] : 0.0;
+  double mx0 = -INFINITY, mx1 = -INFINITY, mn0 = INFINITY, mn1 = INFINITY, s0 = 0.0, s1 = 0.0;
+  for (int it = 0; it < n_it; it++) {
+    const int s = it % CS_STAGES;
+    mbar_wait(&full[s], (it / CS_STAGES) & 1);
+    const double* t = tile + s * STAGE_DOUBLES + 2 * tid;
+    const int rows = r1 - (r0 + it * CS_ROWS) < CS_ROWS ? r1 - (r0 + it * CS_ROWS) : CS_ROWS;
+#pragma unroll 4
+    for (int r = 0; r < rows; r++) {
+      const double2 v = *reinterpret_cast<const double2*>(t + r * CS_COLS);
+      double v0 = v.x, v1 = v.y;
+      if (clamp) v0 = fmax(v0 - e0, 0.0), v1 = fmax(v1 - e1, 0.0);
+      mx0 = fmax(mx0, v0), mn0 = fmin(mn0, v0), s0 += v0;
+      mx1 = fmax(mx1, v1), mn1 = fmin(mn1, v1), s1 += v1;
+    }
+    __syncthreads();  // every thread is done with this stage: refill it
+    if (tid == 0 && it + CS_STAGES < n_it) {
+      mbar_expect_tx(&full[s], STAGE_BYTES);
+      tma_load_2d(tile + s * STAGE_DOUBLES, &map, slab0, r0 + (it + CS_STAGES) * CS_ROWS, &full[s]);
+    }
+  }
+  if (!live0) return;
   double* o = part + (long)blockIdx.y * 3 * c_pad;
   o[c0] = mx0, o[c_pad + c0] = mn0, o[2 * c_pad + c0] = s0;
   if (two) o[c0 + 1] = mx1, o[c_pad + c0 + 1] = mn1, o[2 * c_pad + c0 + 1] = s1;
@@ -178,6 +239,118 @@ project_kernel(const double* __restrict__ X, long ldx, int n, int c, const doubl
 #pragma unroll
       for (int f = 0; f < 2; f++) {
         double v = sA[(wm + 8 * f + g) * LD + kk];
+        if (clamp) v = fmax(v - sV[2 * PROJ_BK + kk], 0.0);
+        av[f] = live ? (v - mu) * wt : 0.0;
+      }
+#pragma unroll
+      for (int h = 0; h < NF; h++) bv[h] = sB[(8 * h + g) * LD + kk];
+#pragma unroll
+      for (int f = 0; f < 2; f++)
+#pragma unroll
+        for (int h = 0; h < NF; h++) dmma(acc[f][h][0], acc[f][h][1], av[f], bv[h]);
+    }
+  }
+  cp_async_wait<0>();
+  double* o = part + ((long)blockIdx.y * n_pad + (long)ti * 128 + wm) * PN;
+#pragma unroll
+  for (int f = 0; f < 2; f++)
+#pragma unroll
+    for (int h = 0; h < NF; h++)
+      *reinterpret_cast<double2*>(o + (long)(8 * f + g) * PN + 8 * h + 2 * q) = make_double2(acc[f][h][0], acc[f][h][1]);
+}
+
+// The projection with its HBM stream (the 128 x 16 tile of x per stage) moved by the TMA unit: one cp.async.bulk.tensor box per
+// stage issued by one thread, landing with the 128-byte swizzle (chunk ^= row & 7) in an unpadded 1 KB-aligned tile; the DMMA
+// fragments take their four k values in the order k(q, ks) = 2 ks + (q & 1) + 8 (q >> 1), for which the eight rows x four
+// lanes of a fragment read hit sixteen different banks per half-warp (any k order is valid as long as A, B and the per-cell
+// vectors use the same one).  The small operands (E tile, mean / weight / elevation slices) stay on cp.async in their padded
+// layout.  Rows past n and cells past c read as zero.
+template <int PN>
+struct ProjTmaCfg {
+  static constexpr int LD = PROJ_BK + 4;
+  static constexpr int A_DOUBLES = 128 * PROJ_BK, B_DOUBLES = PN * LD, V_DOUBLES = 3 * PROJ_BK;
+  static constexpr int SMALL_DOUBLES = B_DOUBLES + V_DOUBLES;
+  static constexpr int STAGES = 4;
+  static constexpr int SMEM_BYTES = STAGES * (A_DOUBLES + SMALL_DOUBLES) * (int)sizeof(double) + 1024;
+};
+
+template <int PN>
+__global__ void __launch_bounds__(PROJ_THREADS, 2)
+project_tma_kernel(const __grid_constant__ CUtensorMap xmap, int n, int c, const double* __restrict__ elev, int clamp,
+                   const double* __restrict__ mean, const double* __restrict__ wfull, const double* __restrict__ E, long lde,
+                   int k_stages_total, int stages_per_split, double* __restrict__ part, long n_pad) {
+  using Cfg = ProjTmaCfg<PN>;
+  constexpr int NF = PN / 8, LD = Cfg::LD, STAGES = Cfg::STAGES;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[STAGES];
+  double* sAall = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  double* sSmall = sAall + STAGES * Cfg::A_DOUBLES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = warp * 16;
+  const int ti = blockIdx.x;
+  const int s_begin = blockIdx.y * stages_per_split;
+  int s_end = s_begin + stages_per_split;
+  if (s_end > k_stages_total) s_end = k_stages_total;
+  const int nk = s_end - s_begin;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto load_stage = [&](int slot, int ks) {
+    const long c0 = (long)ks * PROJ_BK;
+    if (tid == 0) {
+      mbar_expect_tx(&full[slot], Cfg::A_DOUBLES * (uint32_t)sizeof(double));
+      tma_load_2d(sAall + slot * Cfg::A_DOUBLES, &xmap, (int)c0, ti * 128, &full[slot]);
+    }
+    double* sB = sSmall + slot * Cfg::SMALL_DOUBLES;
+    double* sV = sB + Cfg::B_DOUBLES;
+    constexpr int CPK = PROJ_BK / 2;
+    for (int ch = tid; ch < PN * CPK; ch += PROJ_THREADS) {
+      const int row = ch / CPK, kc = ch - row * CPK;
+      cp_async16(sB + row * LD + 2 * kc, E + (long)row * lde + c0 + 2 * kc);
+    }
+    if (tid < 3 * CPK) {
+      const int which = tid / CPK, kc = tid - which * CPK;
+      const double* src = which == 0 ? mean : (which == 1 ? wfull : elev);
+      if (which < 2 || clamp) cp_async16(sV + which * PROJ_BK + 2 * kc, src + c0 + 2 * kc);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nk) load_stage(s, s_begin + s);
+    cp_async_commit();
+  }
+  double acc[2][NF][2];
+#pragma unroll
+  for (int f = 0; f < 2; f++)
+#pragma unroll
+    for (int h = 0; h < NF; h++) acc[f][h][0] = acc[f][h][1] = 0.0;
+
+  for (int kt = 0; kt < nk; kt++) {
+    const int slot = kt % STAGES;
+    cp_async_wait<STAGES - 2>();
+    mbar_wait(&full[slot], (kt / STAGES) & 1);
+    __syncthreads();
+    const int nx = kt + STAGES - 1;
+    if (nx < nk) load_stage(nx % STAGES, s_begin + nx);
+    cp_async_commit();
+    const double* sA = sAall + slot * Cfg::A_DOUBLES;
+    const double* sB = sSmall + slot * Cfg::SMALL_DOUBLES;
+    const double* sV = sB + Cfg::B_DOUBLES;
+    const long cbase = (long)(s_begin + kt) * PROJ_BK;
+#pragma unroll
+    for (int ks = 0; ks < PROJ_BK / 4; ks++) {
+      const int kk = 2 * ks + (q & 1) + 8 * (q >> 1);                 // this lane's k of the step (see above)
+      const int sw = (((ks + 4 * (q >> 1)) ^ g) << 1) + (q & 1);       // its swizzled position in a row whose index is g mod 8
+      const double mu = sV[kk], wt = sV[PROJ_BK + kk];
+      const bool live = cbase + kk < c;
+      double av[2], bv[NF];
+#pragma unroll
+      for (int f = 0; f < 2; f++) {
+        double v = sA[(wm + 8 * f + g) * PROJ_BK + sw];
         if (clamp) v = fmax(v - sV[2 * PROJ_BK + kk], 0.0);
         av[f] = live ? (v - mu) * wt : 0.0;
       }

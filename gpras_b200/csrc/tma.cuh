@@ -68,16 +68,21 @@ inline TmaEncodeTiledFn tma_encoder() {
 // Row-major FP64 matrix `rows x cols` with pitch `ld` elements (base 16-byte aligned, ld even), boxes of
 // `box_rows x box_cols` (each <= 256, box_cols * 8 a multiple of 16).  Out-of-range elements of a box read as 0.
 // Returns false when the map cannot be built (unaligned input, driver too old): the caller takes its non-TMA CUDA path.
+// swizzle128: boxes of exactly 16 columns (128 B) land with their 16-byte chunks XOR-ed by (row & 7) (CU_TENSOR_MAP_SWIZZLE_128B),
+// which, together with a matching k order of the DMMA fragments, makes 8-row x 4-column fragment reads bank-conflict free
+// without padding (TMA cannot pad rows).  The shared-memory destination must then be 1024-byte aligned.
 inline bool tma_map_2d_f64(CUtensorMap* map, const double* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
-                           uint32_t box_rows) {
+                           uint32_t box_rows, bool swizzle128 = false) {
   TmaEncodeTiledFn enc = tma_encoder();
   if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (ld & 1) || box_cols > 256 || box_rows > 256 || (box_cols & 1)) return false;
+  if (swizzle128 && box_cols != 16) return false;
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {ld * sizeof(double)};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace gpras

@@ -142,7 +142,13 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--transform-only", action="store_true", help="PreProcessor legs only, plus 16 modes at config-3 size")
     args = ap.parse_args()
+    if args.transform_only:
+        bench_preprocess(torch, 2048, 50_000, 16, "cfg2")
+        bench_preprocess(torch, 8192, 200_000, 16, "cfg3 size, 16 modes")
+        bench_preprocess(torch, 8192, 200_000, 32, "cfg3")
+        return
     bench_preprocess(torch, 2048, 50_000, 16, "cfg2")
     if not args.quick:
         bench_preprocess(torch, 8192, 200_000, 32, "cfg3")
