@@ -75,6 +75,7 @@ SYMBOLS = {
     "gpras_pre_last_launches": (C.c_int, [vp]),
     "gpras_pre_last_stage_ms": (C.c_int, [vp, vp]),
     "gpras_dsyev128": (C.c_int, [vp, vp, vp, vp]),
+    "gpras_kmeans_lloyd": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_double, vp, vp, vp]),
     "gpras_dgemm_tiles": (
         C.c_int,
         [vp, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double],

@@ -14,7 +14,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libgpras_b200.so"
-SOURCES = ["gpras_abi.cu", "sgpr.cu", "pre.cu"]
+SOURCES = ["gpras_abi.cu", "sgpr.cu", "pre.cu", "kmeans.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",

@@ -259,3 +259,23 @@ class SparseGP:
 
     def last_launches(self) -> int:
         return int(self.lib.gpras_sgpr_last_launches(self._h))
+
+
+def kmeans_lloyd(x, centers0, max_iter: int = 300, tol: float = 1e-4, device: int = 0):
+    """Lloyd iterations of ``sklearn.cluster.KMeans`` from the initial centres ``centers0`` on the GPU
+    (``gpras_kmeans_lloyd``; the reference's inducing-input initialiser, ``gpras/gpr.py:313-315``).  ``tol`` is scikit-learn's
+    RELATIVE tolerance (scaled by the mean feature variance, ``_tolerance``).  Returns (centres, labels, inertia, n_iter)."""
+    lib = _lib.load()
+    if lib.gpras_device_count() <= 0:
+        raise _lib.GprasError("no CUDA device visible: gpras_b200 has no CPU fallback")
+    x = _f64(x)
+    c = _f64(centers0).copy()
+    if x.ndim != 2 or c.ndim != 2 or c.shape[1] != x.shape[1]:
+        raise ValueError("x must be (N, D) and centers0 (M, D)")
+    n, d = x.shape
+    labels = np.empty(n, np.int32)
+    inertia, n_iter = C.c_double(), C.c_int()
+    tol_abs = float(np.mean(np.var(x, axis=0)) * tol)
+    check(lib.gpras_kmeans_lloyd(int(device), ptr(x), n, d, ptr(c), c.shape[0], int(max_iter), tol_abs, labels.ctypes.data, C.byref(inertia),
+                                 C.byref(n_iter)))
+    return c, labels, inertia.value, n_iter.value

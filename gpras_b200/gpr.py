@@ -400,10 +400,25 @@ class ExactModel:
         return self.training_loss()
 
     # -- prediction --
-    def predict_y(self, xs):
-        gp = self._slot.acquire(self)
+    def predict_y(self, xs, keep_handle: bool = False):
+        """``predict_y`` of the reference's models (``gpr.py:337``).  ``keep_handle``: give this model a device handle of its
+        own for prediction, so that its factor stays resident while the other per-column models are predicted and across
+        calls (the reference's second caller predicts once per plan with unchanged models, ``gpras/preprocess.py:601-606``)."""
+        if keep_handle:
+            if getattr(self, "_pred_gp", None) is None:
+                self._pred_gp = ExactGP(self.kernel.name, self.x.shape[0], self.x.shape[1], self.y.shape[1], device=self.device)
+                self._pred_gp.set_data(self.x, self.y)
+            gp = self._pred_gp
+        else:
+            gp = self._slot.acquire(self)
         gp.condition(self.theta())  # free when the handle already holds this model's factor at this theta
         return gp.predict(np.asarray(xs, np.float64))
+
+    def release(self) -> None:
+        gp = getattr(self, "_pred_gp", None)
+        if gp is not None:
+            gp.close()
+            self._pred_gp = None
 
     def parameter_dict(self) -> dict:
         """Plain-ndarray version of ``gpflow.utilities.parameter_dict`` (same keys)."""
@@ -708,6 +723,7 @@ class GPRAS:
         initial_theta: NDArray[Any] | None = None,
         restarts: NDArray[Any] | None = None,
         restart_lanes: int | None = None,
+        kmeans_on_device: bool = False,
         n_jobs: int = 1,
         lockstep_models: bool = True,
         **opt_kwargs: Any,
@@ -723,7 +739,8 @@ class GPRAS:
         ([variance, noise, lengthscale(s)]) overrides the initial values; ``restarts`` ((R, 2 + n_ls) constrained
         start points, column order [variance, noise, lengthscale(s)]) runs the recipe from every start and keeps
         the lowest final loss (handed out to ranks by a ticket counter when ``torch.distributed`` is initialised;
-        ``restart_lanes`` restarts in flight per GPU, default 2 for exact models above 4096 rows, else 1); ``n_jobs > 1``
+        ``restart_lanes`` restarts in flight per GPU, default 2 for exact models above 4096 rows, else 1);
+        ``kmeans_on_device`` runs the Lloyd iterations of the "kmeans" initialiser on the GPU; ``n_jobs > 1``
         optimises that many per-column models concurrently on the GPU (host threads, one device handle each; the
         reference loops sequentially, ``gpr.py:273-274``, and so does the default).  Under ``torch.distributed`` (one
         process per GPU) per-column models are sharded round-robin over ranks and their parameters all-gathered.
@@ -737,7 +754,7 @@ class GPRAS:
         if device is None:
             device = _default_device()
         self._opts = dict(exact=exact, ard=ard, shared_kernel=shared_kernel, priors=priors, device=device,
-                          parameterisation=parameterisation)
+                          parameterisation=parameterisation, kmeans_on_device=bool(kmeans_on_device))
         self._init_models(self.x, self.y, n_inducing, inducing_initializer)
         opt = OPTIMIZERS[optimization_method]  # KeyError on an unknown method, as the reference (gpr.py:272)
         unique = self.models[:1] if (shared_kernel and exact) else self.models
@@ -795,6 +812,7 @@ class GPRAS:
             )
         ini_length = float(np.mean(np.abs(x)))
         ls0 = np.full(x.shape[1], ini_length) if o["ard"] else ini_length
+        self.release()
         self.models = []
         if o["exact"]:
             if o["shared_kernel"]:
@@ -813,7 +831,24 @@ class GPRAS:
                                            o["device"], o["priors"], o["parameterisation"]))
 
     def _create_inducing(self, x, n_inducing: int, method: InductionInitializerType) -> NDArray[Any]:
-        """Inducing-input initialisation (``gpr.py:310-320``): KMeans centres or a per-feature linspace diagonal."""
+        """Inducing-input initialisation (``gpr.py:310-320``): KMeans centres or a per-feature linspace diagonal.
+
+        ``"kmeans"`` is the reference's own call, ``KMeans(n_clusters=M, random_state=0, n_init="auto")``.  With
+        ``fit(..., kmeans_on_device=True)`` the same k-means++ seeding (scikit-learn's ``kmeans_plusplus`` with the same random
+        state, on the mean-centred inputs like ``KMeans.fit``) is followed by Lloyd iterations on the GPU
+        (``gpras_kmeans_lloyd``: same stopping rules, fixed-order sums)."""
+        if method == "kmeans" and self._opts.get("kmeans_on_device"):
+            from sklearn.cluster import kmeans_plusplus
+
+            from .engine import kmeans_lloyd
+
+            x = np.asarray(x, np.float64)
+            mu = x.mean(axis=0)
+            xc = x - mu
+            seeds, _ = kmeans_plusplus(xc, int(n_inducing), random_state=0)
+            centres, _, inertia, n_iter = kmeans_lloyd(xc, seeds, device=self._opts.get("device", 0))
+            self.kmeans_info = {"inertia": inertia, "n_iter": n_iter}
+            return centres + mu
         if method == "kmeans":
             from sklearn.cluster import KMeans
 
@@ -831,12 +866,36 @@ class GPRAS:
         x = np.asarray(x).astype(np.float64)
         if self._opts.get("shared_kernel") and self._opts.get("exact") and self.models:
             return self.models[0].predict_y(x)
+        # Per-column models: each keeps its conditioned factor on a handle of its own while they fit in the budget, so a
+        # second predict() costs only the predictor (the reference loops over the models, gpr.py:336-339).
+        keep = self._predict_handles_fit()
         means, variances = [], []
         for m in self.models:
-            mu, var = m.predict_y(x)
+            mu, var = m.predict_y(x, keep_handle=keep)
             means.append(mu)
             variances.append(var)
         return np.concatenate(means, axis=1), np.concatenate(variances, axis=1)
+
+    PREDICT_HANDLE_BUDGET_BYTES = 32 << 30
+
+    def _predict_handles_fit(self) -> bool:
+        if not self.models:
+            return False
+        n = self.x.shape[0]
+        n_pad = (n + 127) // 128 * 128
+        if self._opts.get("exact"):
+            per = 3 * 8 * n_pad * n_pad
+        else:
+            m_ind = int(np.asarray(self.models[0].inducing_variable.Z).shape[0])
+            per = 8 * (4 * n_pad * ((m_ind + 127) // 128 * 128) + 8 * 512 * 512)
+        return len(self.models) * per <= self.PREDICT_HANDLE_BUDGET_BYTES
+
+    def release(self) -> None:
+        """Give the per-model prediction handles back (device memory)."""
+        for m in self.models:
+            rel = getattr(m, "release", None)
+            if rel is not None:
+                rel()
 
     def predict_std(self, x: NDArray[Any]) -> tuple[NDArray[Any], NDArray[Any]]:
         """Explicit extra: (mean, std); callers of the reference take ``np.sqrt`` themselves (pipeline.py:262-263)."""

@@ -144,10 +144,25 @@ class SparseModel:
         return -(elbo + self._log_prior()), (np.concatenate(parts) if parts else np.zeros(0))
 
     # -- prediction --
-    def predict_y(self, xs):
-        gp = self._gp()
+    def predict_y(self, xs, keep_handle: bool = False):
+        """``keep_handle``: a device handle of the model's own for prediction, whose conditioned state survives while the other
+        per-column models are predicted and across calls (``gpras/preprocess.py:601-606`` predicts once per plan)."""
+        if keep_handle:
+            if getattr(self, "_pred_gp", None) is None:
+                n, d = self.x.shape
+                self._pred_gp = SparseGP(self.kernel.name, n, d, self.inducing_variable.Z.shape[0], self.y.shape[1], device=self.device)
+                self._pred_gp.set_data(self.x, self.y)
+            gp = self._pred_gp
+        else:
+            gp = self._gp()
         gp.condition(self.theta(), np.asarray(self.inducing_variable.Z, np.float64), JITTER)
         return gp.predict(np.asarray(xs, np.float64))
+
+    def release(self) -> None:
+        gp = getattr(self, "_pred_gp", None)
+        if gp is not None:
+            gp.close()
+            self._pred_gp = None
 
     def parameter_dict(self) -> dict:
         return {

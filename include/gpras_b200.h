@@ -182,6 +182,15 @@ int gpras_pre_last_stage_ms(gpras_pre* h, double* ms7);
  * lambda descending, eigenvectors as columns of V.  Building block of the PCA fit, exported for tests. */
 int gpras_dsyev128(void* cuda_stream, const double* H, double* lambda, double* V);
 
+/* ---- inducing-input initialiser ------------------------------------------------------------ */
+/* Lloyd iterations of sklearn.cluster.KMeans(n_clusters=m, random_state=0, n_init="auto") (gpr.py:313-315) from the given
+ * initial centres (the k-means++ seeding stays on the host): x (n x d) and centers (m x d, in: seeds, out: final) are host
+ * arrays, tol is the ABSOLUTE tolerance on the total squared centre shift (scikit-learn: 1e-4 * mean(var(x, axis=0))),
+ * labels_out (n, may be NULL), inertia_out / n_iter_out (may be NULL).  Stopping rules, empty-cluster relocation and the
+ * final label pass follow sklearn/cluster/_kmeans.py:_kmeans_single_lloyd; sums run in a fixed order (bitwise repeatable). */
+int gpras_kmeans_lloyd(int device, const double* x, int n, int d, double* centers, int m, int max_iter, double tol,
+                       int* labels_out, double* inertia_out, int* n_iter_out);
+
 /* ---- stand-alone building blocks on device pointers (tests, composition) ------------------ */
 /* C = alpha * A(.)B(.) + beta * C on the DMMA tile engine.  shape: 0 = 128x128 CTA tile (all four layouts),
  * 1 = 128x64 (row-major A, n-major B only), 2 = 128x32 (k-major B only).  m % 128 == 0, n % tile == 0, k % 32 == 0;
