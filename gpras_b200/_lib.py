@@ -71,6 +71,8 @@ SYMBOLS = {
     "gpras_pre_iterations": (C.c_int, [vp]),
     "gpras_pre_transform": (C.c_int, [vp, vp, C.c_long, C.c_int, C.c_int, vp]),
     "gpras_pre_reverse": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    "gpras_pre_reverse_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_long]),
+    "gpras_pre_cell_pitch": (C.c_long, [vp]),
     "gpras_pre_trim": (C.c_int, [vp]),
     "gpras_pre_last_launches": (C.c_int, [vp]),
     "gpras_pre_last_stage_ms": (C.c_int, [vp, vp]),

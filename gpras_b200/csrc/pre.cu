@@ -7,6 +7,7 @@
 #include "host_common.cuh"
 #include "eig_kernels.cuh"
 #include "pre_kernels.cuh"
+#include "cells_kernel.cuh"
 
 namespace {
 
@@ -694,6 +695,70 @@ int gpras_pre_reverse(gpras_pre* h, const double* mean, const double* var, int t
                         cudaMemcpyDeviceToHost, s);
     }
     if (cudaStreamSynchronize(s) != cudaSuccess) r = fail(GPRAS_E_CUDA, "reverse transform", cudaGetLastError());
+  }
+  cleanup();
+  return r;
+}
+
+long gpras_pre_cell_pitch(gpras_pre* h) { return h ? h->c_pad : 0; }
+
+// reverse_transform with the (T x C) results left ON THE DEVICE (or streamed through a ring buffer when the caller keeps
+// nothing): one fused kernel per block of events, general variance map (one hyperparameter set per mode).
+int gpras_pre_reverse_device(gpras_pre* h, const double* mean, const double* var, int t, int on_device, double* cell_mean,
+                             double* cell_var, long ldc) {
+  if (!h || !mean || !var || t <= 0) return fail(GPRAS_E_ARG, "bad argument");
+  if ((cell_mean != nullptr) != (cell_var != nullptr)) return fail(GPRAS_E_ARG, "pass both cell_mean and cell_var, or neither");
+  if (!h->fitted || h->p <= 0) return fail(GPRAS_E_STATE, "fit() / set_state() has not been called");
+  if (cell_mean && ldc < h->c_pad) return fail(GPRAS_E_ARG, "ldc smaller than gpras_pre_cell_pitch()");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = h->stream;
+  h->launches = 0;
+  int r;
+  if (!h->map_ready && (r = build_map(h))) return r;
+  static std::atomic<bool> attr_done[64] = {};
+  if (h->device < 64 && !attr_done[h->device]) {
+    if ((r = opt_in_smem(cells_general_kernel<32>, CellsGenCfg<32>::SMEM_BYTES)) ||
+        (r = opt_in_smem(cells_general_kernel<64>, CellsGenCfg<64>::SMEM_BYTES)))
+      return r;
+    attr_done[h->device] = true;
+  }
+  const int p = h->p, pk = round_up(p, 32);
+  const long c_pad = h->c_pad;
+  constexpr int RING_ROWS = 256;
+  const bool keep = cell_mean != nullptr;
+  double *M = nullptr, *V = nullptr, *ring_m = nullptr, *ring_v = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(s);
+    pfree(h, M), pfree(h, V), pfree(h, ring_m), pfree(h, ring_v);
+  };
+  if ((r = palloc(h, &M, (size_t)PRE_REV_TB * pk)) || (r = palloc(h, &V, (size_t)PRE_REV_TB * pk)) ||
+      (!keep && ((r = palloc(h, &ring_m, (size_t)RING_ROWS * c_pad)) || (r = palloc(h, &ring_v, (size_t)RING_ROWS * c_pad))))) {
+    cleanup();
+    return r;
+  }
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (int t0 = 0; t0 < t && !r; t0 += PRE_REV_TB) {
+    const int tb = t - t0 < PRE_REV_TB ? t - t0 : PRE_REV_TB;
+    const int tb_pad = round_up(tb, 128);
+    cudaMemsetAsync(M, 0, sizeof(double) * (size_t)tb_pad * pk, s);
+    cudaMemsetAsync(V, 0, sizeof(double) * (size_t)tb_pad * pk, s);
+    cudaMemcpy2DAsync(M, sizeof(double) * pk, mean + (size_t)t0 * p, sizeof(double) * p, sizeof(double) * p, tb, kind, s);
+    cudaMemcpy2DAsync(V, sizeof(double) * pk, var + (size_t)t0 * p, sizeof(double) * p, sizeof(double) * p, tb, kind, s);
+    double* om = keep ? cell_mean + (size_t)t0 * ldc : ring_m;
+    double* ov = keep ? cell_var + (size_t)t0 * ldc : ring_v;
+    const long ldo = keep ? ldc : c_pad;
+    const int t_tiles = (keep ? round_up(tb, CELLS_ROWS) : tb_pad) / CELLS_ROWS;  // kept output: only whole 64-row tiles that exist
+    const int per_cta = (t_tiles + 1) / 2;
+    dim3 grid((unsigned)(c_pad / 128), (unsigned)((t_tiles + per_cta - 1) / per_cta));
+    if (pk == 32)
+      cells_general_kernel<32><<<grid, CELLS_THREADS, CellsGenCfg<32>::SMEM_BYTES, s>>>(M, V, pk, h->Ef, c_pad, h->bias, om, ov, ldo, t_tiles,
+                                                                                      per_cta, keep ? (1 << 30) : RING_ROWS);
+    else
+      cells_general_kernel<64><<<grid, CELLS_THREADS, CellsGenCfg<64>::SMEM_BYTES, s>>>(M, V, pk, h->Ef, c_pad, h->bias, om, ov, ldo, t_tiles,
+                                                                                      per_cta, keep ? (1 << 30) : RING_ROWS);
+    h->launches++;
+    if (cudaGetLastError() != cudaSuccess) r = fail(GPRAS_E_CUDA, "cells_general_kernel");
+    if (!on_device && cudaStreamSynchronize(s) != cudaSuccess) r = fail(GPRAS_E_CUDA, "reverse transform", cudaGetLastError());
   }
   cleanup();
   return r;

@@ -235,6 +235,34 @@ class PreProcessor:
                                     ptr(out_v) if var is not None else None))
         return out_m if var is None else (out_m, out_v)
 
+    def cell_pitch(self) -> int:
+        lib = self._ensure_state()
+        return int(lib.gpras_pre_cell_pitch(self._h))
+
+    def reverse_transform_device(self, mean, var, cell_mean=None, cell_var=None) -> None:
+        """``reverse_transform`` with the (T x cells) mean and variance left on the GPU: ``cell_mean`` / ``cell_var`` are CUDA
+        float64 torch tensors of shape (>= round_up(T, 64), cell_pitch()), or both None (the tiles stream through an internal
+        ring buffer -- throughput runs of sweeps whose output cannot be kept).  ``mean`` / ``var`` (T x modes): NumPy arrays or
+        CUDA tensors; ``var`` holds one variance PER MODE (the reference's per-column models, ``gpras/gpr.py:293-308``), mapped
+        by ``var @ (diag(x_std) eofs / w)^2`` (``gpras/preprocess.py:1081-1094``) in the same fused kernel as the mean."""
+        lib = self._ensure_state()
+        dev = not isinstance(mean, np.ndarray) and hasattr(mean, "data_ptr")
+        if not dev:
+            mean, var = _f64(mean), _f64(var)
+        t, p = int(mean.shape[0]), int(mean.shape[1])
+        if p != int(self.spatial_mode_count) or tuple(var.shape) != (t, p):
+            raise ValueError(f"expected (T, {self.spatial_mode_count}) means and variances")
+        if dev and (not mean.is_contiguous() or not var.is_contiguous()):
+            raise ValueError("device inputs must be contiguous")
+        ldc = 0
+        if cell_mean is not None:
+            rows = (t + 63) // 64 * 64
+            if cell_var is None or tuple(cell_mean.shape) != tuple(cell_var.shape) or cell_mean.shape[0] < rows:
+                raise ValueError(f"cell_mean / cell_var must both be given with at least {rows} rows")
+            ldc = int(cell_mean.stride(0))
+        check(lib.gpras_pre_reverse_device(self._h, ptr(mean), ptr(var), t, int(dev), ptr(cell_mean) if cell_mean is not None else None,
+                                           ptr(cell_var) if cell_var is not None else None, ldc))
+
     # ---- wetness helpers (host-side restatements used by callers on small arrays) ------------------------------------
     def classify_wetness_wse(self, x, elevations):
         return self._classify_depths(x.max(axis=0) - elevations, x.min(axis=0) - elevations)

@@ -173,6 +173,14 @@ int gpras_pre_transform(gpras_pre* h, const double* x, long ldx, int n, int on_d
 /* PreProcessor.reverse_transform (preprocess.py:1052-1084): mean (t x p) [and var (t x p), may be NULL] -> cell space
  * (t x c) host arrays; depth semantics follow the handle's hydraulic parameter. */
 int gpras_pre_reverse(gpras_pre* h, const double* mean, const double* var, int t, double* cell_mean, double* cell_var);
+/* The same map with the (t x cells) results left on the DEVICE: cell_mean / cell_var are device pointers with pitch
+ * ldc >= gpras_pre_cell_pitch() and at least round_up(t, 64) rows, or both NULL (tiles go to an internal ring buffer: the
+ * 3.2 TB of BASELINE config 5 cannot be kept).  mean / var (t x modes): host (on_device == 0) or device pointers.  One fused
+ * kernel per block of events with the GENERAL variance map var @ (diag(x_std) eofs / w)^2 (preprocess.py:1081-1094), i.e.
+ * the reference's default model family with one hyperparameter set per mode (gpr.py:293-308). */
+int gpras_pre_reverse_device(gpras_pre* h, const double* mean, const double* var, int t, int on_device, double* cell_mean,
+                             double* cell_var, long ldc);
+long gpras_pre_cell_pitch(gpras_pre* h);
 /* Workspaces (staged input, centred samples, Gram matrix ...) are recycled across calls; trim returns them to the driver. */
 int gpras_pre_trim(gpras_pre* h);
 int gpras_pre_last_launches(gpras_pre* h);

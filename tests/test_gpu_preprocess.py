@@ -196,3 +196,64 @@ def test_edge_shapes_and_errors(cuda):
     with pytest.raises(ValueError):
         pp.reverse_transform(np.zeros((2, 3)))  # wrong number of modes
     pp.close()
+
+
+@pytest.mark.parametrize("name", PRE_CASES)
+def test_reverse_transform_device_general_variance_matches_reference(cuda, pre_golden, name):
+    """The fused device-resident reverse transform (one variance per mode -- the reference's per-column model family) against
+    the reference's own ``reverse_transform`` outputs for free per-mode variances (golden ``reverse_var_free``)."""
+    torch = cuda
+    from gpras_b200.preprocess import PreProcessor
+
+    c = sub(pre_golden, name)
+    pp = PreProcessor(spatial_mode_count=int(c["spatial_mode_count"]), input_mean=c["input_mean"], elevations=c["elevations"],
+                      hydraulic_parameter=str(c["hydraulic_parameter"]), wetness_classes=c["wetness_classes"], weights=c["fit_weights"],
+                      eofs=c["eofs"], eigenvalues=c["eigenvalues"], n_samples_fit=int(c["n_samples_fit"]), x_mean=c["x_mean"], x_std=c["x_std"])
+    t, cells = c["reverse_mean"].shape
+    pitch = pp.cell_pitch()
+    rows = (t + 63) // 64 * 64
+    cm = torch.full((rows, pitch), float("nan"), dtype=torch.float64, device="cuda")
+    cv = torch.full((rows, pitch), float("nan"), dtype=torch.float64, device="cuda")
+    pp.reverse_transform_device(c["mode_mean"], c["mode_var_free"], cm, cv)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(cm[:t, :cells].cpu().numpy(), c["reverse_mean"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(cv[:t, :cells].cpu().numpy(), c["reverse_var_free"], rtol=1e-12, atol=1e-14)
+    # device inputs, and the ring-buffer mode (nothing kept) runs the same kernel
+    cm2, cv2 = torch.empty_like(cm), torch.empty_like(cv)
+    pp.reverse_transform_device(torch.from_numpy(c["mode_mean"]).cuda(), torch.from_numpy(c["mode_var_free"]).cuda(), cm2, cv2)
+    torch.cuda.synchronize()
+    assert torch.equal(cm2[:t, :cells], cm[:t, :cells]) and torch.equal(cv2[:t, :cells], cv[:t, :cells])
+    pp.reverse_transform_device(c["mode_mean"], c["mode_var_free"])
+    # and it agrees with the host-output path
+    hm, hv = pp.reverse_transform(c["mode_mean"], c["mode_var_free"])
+    np.testing.assert_allclose(cm[:t, :cells].cpu().numpy(), hm, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(cv[:t, :cells].cpu().numpy(), hv, rtol=1e-13, atol=1e-15)
+    pp.close()
+
+
+def test_reverse_transform_device_many_events_and_64_modes(cuda):
+    """Several 1024-event blocks, a row count that is no tile multiple, 40 modes (the 64-wide kernel) against the oracle."""
+    torch = cuda
+    from gpras_b200.preprocess import PreProcessor
+    from gpras_b200.synth import make_cell_map
+    from oracle.cells import reverse_transform
+
+    for p, cells, t in ((40, 1500, 2300), (7, 333, 70)):
+        cm = make_cell_map(p, cells, seed=p)
+        rng = np.random.default_rng(p)
+        mean, var = rng.standard_normal((t, p)), rng.uniform(0.01, 2.0, (t, p))
+        classes = np.where(cm.dry_indices, "AD", "TF")
+        eofs_wet = cm.eofs
+        pp = PreProcessor(spatial_mode_count=p, input_mean=cm.input_mean, elevations=cm.elevations, hydraulic_parameter="wse",
+                          wetness_classes=classes, weights=cm.weights, eofs=eofs_wet, eigenvalues=np.ones(p), n_samples_fit=100,
+                          x_mean=cm.x_mean, x_std=cm.x_std)
+        pitch = pp.cell_pitch()
+        rows = (t + 63) // 64 * 64
+        om = torch.empty((rows, pitch), dtype=torch.float64, device="cuda")
+        ov = torch.empty((rows, pitch), dtype=torch.float64, device="cuda")
+        pp.reverse_transform_device(mean, var, om, ov)
+        torch.cuda.synchronize()
+        rm, rv = reverse_transform(mean, var, cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices, cm.elevations)
+        np.testing.assert_allclose(om[:t, :cells].cpu().numpy(), rm, rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(ov[:t, :cells].cpu().numpy(), rv, rtol=1e-11, atol=1e-13)
+        pp.close()
