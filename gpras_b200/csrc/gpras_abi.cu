@@ -574,10 +574,10 @@ int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_devic
     CU(cudaGetLastError());
     if (mode_mean)
       CU(cudaMemcpy2DAsync(mode_mean + (size_t)t0 * h->p, sizeof(double) * h->p, h->mean, sizeof(double) * h->p_pad,
-                           sizeof(double) * h->p, tb, cudaMemcpyDeviceToHost, s));
+                           sizeof(double) * h->p, tb, cudaMemcpyDefault, s));
     if (mode_var)
       CU(cudaMemcpy2DAsync(mode_var + (size_t)t0 * h->p, sizeof(double) * h->p, h->varm, sizeof(double) * h->p_pad,
-                           sizeof(double) * h->p, tb, cudaMemcpyDeviceToHost, s));
+                           sizeof(double) * h->p, tb, cudaMemcpyDefault, s));
     CU(cudaEventRecord(h->ev_pred[k], s));
     CU(cudaStreamWaitEvent(s2, h->ev_pred[k], 0));
     // modes -> cells: one streaming kernel per batch (column tile per CTA, row tiles streamed)

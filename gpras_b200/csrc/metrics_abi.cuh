@@ -210,14 +210,14 @@ int gpras_gp_predict_metrics(gpras_gp* h, gpras_metrics* m, const double* xs, in
     if ((r = predict_batch(h, tb, tb_pad))) return r;
     if (mode_mean)
       CU(cudaMemcpy2DAsync(mode_mean + (size_t)t0 * h->p, sizeof(double) * h->p, h->mean, sizeof(double) * h->p_pad,
-                           sizeof(double) * h->p, tb, cudaMemcpyDeviceToHost, s));
+                           sizeof(double) * h->p, tb, cudaMemcpyDefault, s));
     if (mode_var) {
       long tot = (long)tb_pad * h->p_pad;
       broadcast_var_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h->var, h->varm, tb_pad, h->p, h->p_pad);
       h->launches++;
       CU(cudaGetLastError());
       CU(cudaMemcpy2DAsync(mode_var + (size_t)t0 * h->p, sizeof(double) * h->p, h->varm, sizeof(double) * h->p_pad,
-                           sizeof(double) * h->p, tb, cudaMemcpyDeviceToHost, s));
+                           sizeof(double) * h->p, tb, cudaMemcpyDefault, s));
     }
     MetricsArgs a;
     memset(&a, 0, sizeof a);

@@ -131,15 +131,23 @@ class ExactGP:
     def cell_pitch(self) -> int:
         return int(self.lib.gpras_gp_cell_pitch(self._h))
 
-    def predict_cells(self, xs, cell_mean=None, cell_var=None, want_modes: bool = True):
+    def predict_cells(self, xs, cell_mean=None, cell_var=None, want_modes: bool = True, modes_out=None):
         """Predict and expand to mesh cells on the device.  ``cell_mean`` / ``cell_var`` are CUDA float64
-        torch tensors of shape (T, cell_pitch()) or None (tiles go to an internal ring buffer)."""
+        torch tensors of shape (T, cell_pitch()) or None (tiles go to an internal ring buffer).  ``modes_out``: a pair of
+        contiguous (T, P) CUDA tensors that receive the mode-space mean / variance instead of host arrays (sharded sweeps
+        all-gather them over NCCL without a host round trip)."""
         on_device = not isinstance(xs, np.ndarray) and hasattr(xs, "data_ptr")
         if not on_device:
             xs = _f64(xs)
         t = int(xs.shape[0])
-        mm = np.empty((t, self.p)) if want_modes else None
-        mv = np.empty((t, self.p)) if want_modes else None
+        if modes_out is not None:
+            mm, mv = modes_out
+            if tuple(mm.shape) != (t, self.p) or tuple(mv.shape) != (t, self.p) or not (mm.is_contiguous() and mv.is_contiguous()):
+                raise ValueError(f"modes_out must be two contiguous ({t}, {self.p}) tensors")
+            want_modes = True
+        else:
+            mm = np.empty((t, self.p)) if want_modes else None
+            mv = np.empty((t, self.p)) if want_modes else None
         ldc = int(cell_mean.shape[1]) if cell_mean is not None else (int(cell_var.shape[1]) if cell_var is not None else 0)
         check(
             self.lib.gpras_gp_predict_cells(

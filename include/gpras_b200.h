@@ -73,7 +73,7 @@ int gpras_gp_predict(gpras_gp* h, const double* xs, int t, double* mean, double*
 int gpras_gp_set_cell_map(gpras_gp* h, const double* e_mean, const double* bias, int c);
 /* Predict and expand to cells on the device: cell_mean, cell_var are DEVICE buffers (t x ldc doubles, ldc >=
  * padded cells, see gpras_gp_cell_pitch) or NULL to run without keeping the cell-space output (the tiles are
- * written to an internal ring buffer).  mode_mean / mode_var (t*p, host) may be NULL. */
+ * written to an internal ring buffer).  mode_mean / mode_var (t*p, host OR device memory) may be NULL. */
 int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_device, double* mode_mean,
                            double* mode_var, double* cell_mean, double* cell_var, long ldc);
 long gpras_gp_cell_pitch(gpras_gp* h);
