@@ -267,7 +267,10 @@ project_kernel(const double* __restrict__ X, long ldx, int n, int c, const doubl
 // layout.  Rows past n and cells past c read as zero.
 template <int PN>
 struct ProjTmaCfg {
-  static constexpr int LD = PROJ_BK + 4;
+  // pitch of the padded E tile: == 2 mod 16, so that with the k order above (k in {2ks, 2ks+1, 2ks+8, 2ks+9}) the four rows x
+  // four k values of a half-warp's B-fragment read fall in sixteen different banks (+4, right for the plain k order, gave a
+  // two-way conflict here: 1.0e8 conflict cycles in the first ncu capture)
+  static constexpr int LD = PROJ_BK + 2;
   static constexpr int A_DOUBLES = 128 * PROJ_BK, B_DOUBLES = PN * LD, V_DOUBLES = 3 * PROJ_BK;
   static constexpr int SMALL_DOUBLES = B_DOUBLES + V_DOUBLES;
   static constexpr int STAGES = 4;

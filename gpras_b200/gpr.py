@@ -129,14 +129,16 @@ class Parameter:
     def log_prior(self) -> float:
         if self.prior is None:
             return 0.0
-        lv = np.log(self.value())
-        return float(np.sum(-lv - 0.5 * LOG_2PI - 0.5 * lv * lv))
+        with np.errstate(all="ignore"):  # a line-search trial point may underflow a value to 0: the loss is then non-finite, handled by the caller
+            lv = np.log(self.value())
+            return float(np.sum(-lv - 0.5 * LOG_2PI - 0.5 * lv * lv))
 
     def dlog_prior_dvalue(self):
         if self.prior is None:
             return np.zeros_like(self.unconstrained)
         v = self.value()
-        return -(1.0 + np.log(v)) / v
+        with np.errstate(all="ignore"):
+            return -(1.0 + np.log(v)) / v
 
     def __repr__(self) -> str:
         return f"Parameter({self.numpy()!r}, trainable={self.trainable})"

@@ -12,9 +12,10 @@ REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
             "data", "config", "clocks", "e2e", "gpu_launches", "roofline"]
 
 
-@pytest.mark.parametrize("name", ["bench_1gpu_final.json", "bench_2gpu_final.json", "bench_8gpu_final.json"])
+@pytest.mark.parametrize("name", ["r01/bench_1gpu_final.json", "r01/bench_2gpu_final.json", "r01/bench_8gpu_final.json",
+                                  "r02/bench_1gpu_final.json", "r02/bench_2gpu_dev.json"])
 def test_committed_bench_lines_follow_the_contract(name):
-    d = json.loads((ROOT / "profiles" / "r01" / name).read_text())
+    d = json.loads((ROOT / "profiles" / name).read_text().strip().splitlines()[-1])
     for k in REQUIRED:
         assert k in d, k
     assert d["metric"] == "LML+grad evals/s at N=8192" and d["unit"] == "evals/s" and d["dtype"] == "f64"
@@ -33,11 +34,35 @@ def test_committed_bench_lines_follow_the_contract(name):
         assert set(c) >= {"value", "unit", "cores", "kind", "sample"} and c["kind"] in ("reference", "port")
 
 
-def test_reference_arm_line_follows_the_contract():
-    d = json.loads((ROOT / "profiles" / "r01" / "bench_reference_final.json").read_text())
+@pytest.mark.parametrize("rnd", ["r01", "r02"])
+def test_reference_arm_line_follows_the_contract(rnd):
+    d = json.loads((ROOT / "profiles" / rnd / "bench_reference_final.json").read_text().strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["metric"] == "LML+grad evals/s at N=8192" and d["unit"] == "evals/s"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
+
+
+def test_round2_bench_line_is_job_level_and_both_arms_share_the_config():
+    ours = json.loads((ROOT / "profiles" / "r02" / "bench_1gpu_final.json").read_text().strip().splitlines()[-1])
+    ref = json.loads((ROOT / "profiles" / "r02" / "bench_reference_final.json").read_text().strip().splitlines()[-1])
+    assert ours["config"] == ref["config"]  # the driver compares them
+    r = ours["roofline"]
+    # top-level fraction = F_eval x evals/s per GPU over the DGEMM rate measured in the run, not a single launch
+    f_eval = 8192.0**3 + 3 * 8192.0**2 * 32
+    assert abs(r["achieved"] - ours["value"] / ours["n_gpus"] * f_eval * 1e-12) < 1e-9 * r["achieved"]
+    assert abs(r["peak"] - ours["fp64_peak"]["sustained_tflops"]) < 1e-12 and "detail" in r
+    assert ours["sustained"]["seconds"] >= 3.0 and ours["predict"]["roofline"]["frac"] < 1.0
+    for k in ("cfg4", "cfg5_sweep", "strong"):
+        assert ours[k] is not None, k
+    assert ours["strong"]["scaling"] == "strong" and ours["cfg5_sweep"]["scaling"] == "strong"
+    assert ref["steps"] <= 3 and ref["steps_requested"] >= ref["steps"]
+
+
+def test_bench_ncu_figures_come_from_profiles():
+    src = (ROOT / "bench.py").read_text()
+    assert "bench_ncu_inputs.json" in src and "lauum_dram_bytes" not in src  # no ncu constants typed into bench.py
+    d = json.loads(sorted((ROOT / "profiles").glob("r*/bench_ncu_inputs.json"))[-1].read_text())
+    assert d["eval_dram_bytes"] > 0 and d["eval_launches"] > 0
 
 
 def test_bench_cli_surface():
