@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 LIB_PATH = Path(__file__).resolve().parent / "libgpras_b200.so"
-ABI_VERSION = 2  # == GPRAS_B200_ABI_VERSION in include/gpras_b200.h
+ABI_VERSION = 3  # == GPRAS_B200_ABI_VERSION in include/gpras_b200.h
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

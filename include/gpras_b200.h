@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GPRAS_B200_ABI_VERSION 2
+#define GPRAS_B200_ABI_VERSION 3
 
 /* kernel ids == KERNEL_FACTORY keys that are constructible in the reference (gpr.py:21-29, 298) */
 #define GPRAS_KERNEL_RBF 0
