@@ -245,6 +245,10 @@ def run_ours(args) -> None:
     thetas = make_thetas(W + K, d, seed=2 + rank)  # every rank = its own shard of restarts / candidates
     stream = torch.cuda.current_stream()
     hbm_gbs, hbm_src = hbm_peak()
+    legs = None if args.legs == "all" else set(args.legs.split(","))
+
+    def leg(name: str) -> bool:
+        return not args.quick and (legs is None or name in legs)
 
     def barrier():
         if world > 1:
@@ -344,7 +348,7 @@ def run_ours(args) -> None:
 
     # ---- sustained: the same loop for >= 3 s (power / clock behaviour of a long run) -------------------
     sustained = None
-    if not args.quick:
+    if leg("sustained"):
         per = max(K, 10)
         sampler = ClockSampler(local)
         sampler.start()
@@ -425,7 +429,7 @@ def run_ours(args) -> None:
                     "peak_source": hbm_src},
         },
     }
-    if not args.quick:
+    if leg("predict"):
         # the same sweep with the consumer fused: depth conversion + every metric of gpras/metrics.py accumulated on the fly
         # against a resident truth block, the T x C prediction never written
         from gpras_b200.metrics import MetricsAccumulator
@@ -456,7 +460,7 @@ def run_ours(args) -> None:
 
     # ---- BASELINE config 5: the stochastic prediction sweep, 1,000,000 events x 200,000 cells, events sharded over ranks ----
     cfg5 = None
-    if not args.quick:
+    if leg("cfg5"):
         from gpras_b200.parallel import all_gather_rows, shard_rows
 
         t_all = 1_000_000
@@ -496,7 +500,7 @@ def run_ours(args) -> None:
 
     # ---- BASELINE config 3 as stated: 64 optimiser restarts sharded over the GPUs (fixed total work) ----
     strong = None
-    if not args.quick:
+    if leg("strong"):
         from gpras_b200 import GPRAS
         from gpras_b200.parallel import all_gather_rows
         from gpras_b200.synth import random_starts
@@ -508,28 +512,33 @@ def run_ours(args) -> None:
         st3 = random_starts(r_total, 1, seed=2)  # the reference's own ranges (gpras/gpr.py:88-90), one scalar lengthscale per start
         starts = np.concatenate([st3[:, :2], np.repeat(st3[:, 2:3], d, axis=1)], axis=1)
         model = GPRAS(w["kernel"])
+        lanes = int(os.environ.get("BENCH_RESTART_LANES", C))
+        # warm-up: a one-iteration restart per lane creates the lanes' device handles (1.6 GB each) before the timed region,
+        # like the handles of the weak leg
+        model.fit(data.x, data.y, None, "kmeans", "L-BFGS-B", ard=True, shared_kernel=True, device=local, restarts=starts[: lanes * world],
+                  restart_lanes=lanes, max_iter=1)
         barrier()
         t0 = time.perf_counter()
         model.fit(data.x, data.y, None, "kmeans", "L-BFGS-B", ard=True, shared_kernel=True, device=local, restarts=starts,
-                  restart_lanes=C, max_iter=maxiter)
+                  restart_lanes=lanes, max_iter=maxiter)
         torch.cuda.synchronize()
         dts = reduce_max(time.perf_counter() - t0)
         m0 = model.models[0]
-        stats = all_gather_rows(np.array([[float(m0.n_evals), float(getattr(m0, "restart_busy_s", 0.0))]]), 2)
+        stats = all_gather_rows(np.array([[float(m0.n_evals), float(getattr(m0, "restart_busy_s", 0.0))]]), 2)  # (evaluations of the timed fit only: fit() builds new models)
         tab = m0.restart_table
         strong = {
             "workload": f"cfg3 as stated: {r_total} optimiser restarts (starts log-uniform in the reference's ranges) x L-BFGS-B(maxiter {maxiter}) "
                         f"through GPRAS.fit(restarts=...), handed out to {world} rank(s) by a ticket counter, {C} restarts in flight per GPU",
             "scaling": "strong", "wall_s": dts, "evals": int(stats[:, 0].sum()), "evals_per_s": float(stats[:, 0].sum()) / dts,
             "restarts_per_s": r_total / dts, "best_loss": float(np.min(tab[:, 1])), "restarts_not_positive_definite": int(np.sum(~np.isfinite(tab[:, 1]))),
-            "rank_busy_s": [float(v) for v in stats[:, 1]],
+            "rank_busy_s": [float(v) for v in stats[:, 1]], "host_cores": os.cpu_count(), "host_threads_per_rank": lanes,
             "imbalance": float(stats[:, 1].max() / max(stats[:, 1].mean(), 1e-12) - 1.0),
         }
         model._slot.release_other_threads()
 
     # ---- BASELINE config 4: N = 16384, D = P = 64 (one GPU's worth of FP64 Cholesky near the HBM footprint of 3 N^2 doubles) ----
     cfg4 = None
-    if not args.quick and rank == 0:
+    if leg("cfg4") and rank == 0:
         n4, d4 = 16384, 64
         data4 = make_gp_data(n4, d4, d4, 0, seed=0)
         g4 = ExactGP(w["kernel"], n4, d4, d4, device=local)
@@ -555,7 +564,7 @@ def run_ours(args) -> None:
 
     # ---- the cells -> modes side at BASELINE config 2 sizes: PCA fit and the forward transform ----
     preprocess = None
-    if rank == 0 and not args.quick:
+    if rank == 0 and leg("preprocess"):
         from gpras_b200.preprocess import PreProcessor
 
         sys.path.insert(0, str(ROOT / "tools"))
@@ -591,7 +600,7 @@ def run_ours(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_block(),
-            "run": {"evaluations_per_gpu": K, "in_flight_per_gpu": C, "timed_region_s": ms_total * 1e-3,
+            "run": {"evaluations_per_gpu": K, "in_flight_per_gpu": C, "timed_region_s": ms_total * 1e-3, "host_cores": os.cpu_count(),
                     "exchange": "all-gather of the per-restart [LML, grad] rows inside both timed regions"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -624,6 +633,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline + predict legs only (profiling runs)")
     ap.add_argument("--concurrent", type=int, default=2, help="independent evaluations in flight per GPU")
+    ap.add_argument("--legs", default="all", help="comma list of extra legs to run (sustained,predict,cfg5,strong,cfg4,preprocess) or 'all'")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

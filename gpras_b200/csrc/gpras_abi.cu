@@ -73,6 +73,11 @@ struct gpras_gp {
   int c = 0, c_pad = 0, p16 = 0;
   double *E1 = nullptr, *E2 = nullptr, *rootS = nullptr, *bias = nullptr, *zbias = nullptr, *ring_m = nullptr, *ring_v = nullptr;
   cudaEvent_t ev[8] = {};
+  // Host wait of an evaluation: large problems sleep on a blocking event instead of spinning in cudaStreamSynchronize -- with
+  // several restart lanes per rank and 8 ranks per box, spinning host threads outnumber the cores and slow each other down
+  // (measured: 64 restarts on 8 GPUs at 31 instead of 54 evaluations/s per rank); small problems keep the low-latency spin.
+  cudaEvent_t ev_done = nullptr;
+  bool blocking_wait = false;
   // prediction pipeline: batch b's consumer (modes -> cells, or the fused metrics) runs on stream2 while batch b+1's
   // predictor runs on `stream`; the small mode-space buffers are double-buffered, `mean / var / varm` point at the current set
   cudaStream_t stream2 = nullptr;
@@ -208,6 +213,7 @@ int enqueue_eval(gpras_gp* h, const double* theta, int want_grad) {
     if ((r = record_eval(h, want_grad))) return r;
     h->eager_done[g] = true;
   }
+  if (h->blocking_wait) CU(cudaEventRecord(h->ev_done, s));
   h->pending = true;
   h->pending_grad = want_grad != 0;
   return 0;
@@ -215,7 +221,10 @@ int enqueue_eval(gpras_gp* h, const double* theta, int want_grad) {
 
 int fetch_eval(gpras_gp* h, double* lml, double* grad) {
   if (!h->pending) return fail(GPRAS_E_STATE, "no evaluation enqueued");
-  CU(cudaStreamSynchronize(h->stream));
+  if (h->blocking_wait)
+    CU(cudaEventSynchronize(h->ev_done));
+  else
+    CU(cudaStreamSynchronize(h->stream));
   h->pending = false;
   if (h->stage_timing) {
     for (int i = 0; i < 6; i++) {
@@ -267,7 +276,7 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
   h->own_stream = true;
   // graph replay pays off while the evaluation is launch/latency bound (measured: +6..10% for N <= 4096, -3% at
   // N = 8192 with two evaluations in flight, where eager launches interleave better across handles)
-  h->use_graphs = h->n_pad <= 4096 && !getenv("GPRAS_B200_NO_GRAPHS");
+  h->use_graphs = (h->n_pad <= 4096 || getenv("GPRAS_B200_GRAPHS_ALL")) && !getenv("GPRAS_B200_NO_GRAPHS");
   const size_t nn = (size_t)h->n_pad * h->n_pad, np = (size_t)h->n_pad * h->p_pad;
   const int ntile = h->nt * (h->nt + 1) / 2;
   // One device allocation and one pinned allocation per handle, carved below: a handle costs ~1 ms to create instead of
@@ -310,6 +319,8 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
   CU(cudaMemsetAsync(h->W, 0, sizeof(double) * nn, h->stream));  // the leaves never write above the diagonal
   CU(cudaStreamSynchronize(h->stream));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
+  h->blocking_wait = h->n_pad >= 2048 && !getenv("GPRAS_B200_SPIN_WAIT");
+  CU(cudaEventCreateWithFlags(&h->ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -332,6 +343,7 @@ int gpras_gp_destroy(gpras_gp* h) {
   if (h->h_arena) cudaFreeHost(h->h_arena);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
   for (auto& g : h->graph)
     if (g) cudaGraphExecDestroy(g);
   h->la.destroy();

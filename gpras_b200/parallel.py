@@ -125,7 +125,7 @@ def run_restarts(model, opt, starts: np.ndarray, opt_kwargs: dict, lanes: int = 
     width = 2 + n_theta + z0.size
     tickets = _Tickets(starts.shape[0], rank, world, dynamic)
     lanes = max(1, min(int(lanes), starts.shape[0]))
-    if lanes > 1 and not hasattr(model, "clone"):
+    if lanes > 1 and not hasattr(model, "lane_models"):
         lanes = 1
 
     def reset(mdl, theta):
@@ -159,13 +159,10 @@ def run_restarts(model, opt, starts: np.ndarray, opt_kwargs: dict, lanes: int = 
     else:
         from concurrent.futures import ThreadPoolExecutor
 
-        clones = [model] + [model.clone() for _ in range(lanes - 1)]
+        clones = model.lane_models(lanes)  # one device handle per lane, kept by the model's slot between calls
         with ThreadPoolExecutor(max_workers=lanes) as ex:
             results = list(ex.map(lane, clones))
-        model.n_evals = sum(r[2] for r in results)
-        release = getattr(model, "release_other_threads", None)
-        if release is not None:
-            release()
+        model.n_evals = getattr(model, "n_evals", 0) + sum(r[2] for r in results)
     rows = [row for res in results for row in res[0]]
     model.restart_busy_s = max((res[1] for res in results), default=0.0)
     table = all_gather_rows(np.array(rows).reshape(-1, width), width)

@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+run() { # tag, env...
+  tag=$1; shift
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus 8 --steps 10 --warmup 3 --legs strong --no-cpu-baseline > gpurun_out/s8_$tag.json 2> gpurun_out/s8_$tag.err
+}
+run lanes1 BENCH_RESTART_LANES=1
+run graphs GPRAS_B200_GRAPHS_ALL=1
+run lanes3 BENCH_RESTART_LANES=3
