@@ -38,6 +38,7 @@ SYMBOLS = {
     "gpras_gp_predict_cells": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_long]),
     "gpras_gp_cell_pitch": (C.c_long, [vp]),
     "gpras_gp_get_matrix": (C.c_int, [vp, C.c_int, vp]),
+    "gpras_gp_set_blocking_wait": (C.c_int, [vp, C.c_int]),
     "gpras_gp_last_launches": (C.c_int, [vp]),
     "gpras_gp_last_stage_ms": (C.c_int, [vp, vp]),
     "gpras_gp_set_stage_timing": (C.c_int, [vp, C.c_int]),

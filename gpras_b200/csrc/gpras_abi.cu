@@ -73,9 +73,9 @@ struct gpras_gp {
   int c = 0, c_pad = 0, p16 = 0;
   double *E1 = nullptr, *E2 = nullptr, *rootS = nullptr, *bias = nullptr, *zbias = nullptr, *ring_m = nullptr, *ring_v = nullptr;
   cudaEvent_t ev[8] = {};
-  // Host wait of an evaluation: large problems sleep on a blocking event instead of spinning in cudaStreamSynchronize -- with
-  // several restart lanes per rank and 8 ranks per box, spinning host threads outnumber the cores and slow each other down
-  // (measured: 64 restarts on 8 GPUs at 31 instead of 54 evaluations/s per rank); small problems keep the low-latency spin.
+  // Host wait of an evaluation: cudaStreamSynchronize (spins: lowest latency, the default) or a blocking event (the thread
+  // sleeps: for several host threads per GPU, e.g. restart lanes, where spinning threads can outnumber the cores; it costs
+  // ~1 % at N = 8192 with one host thread, measured).  gpras_gp_set_blocking_wait selects it per handle.
   cudaEvent_t ev_done = nullptr;
   bool blocking_wait = false;
   // prediction pipeline: batch b's consumer (modes -> cells, or the fused metrics) runs on stream2 while batch b+1's
@@ -319,7 +319,7 @@ int gpras_gp_create(gpras_gp** out, int device, int kernel_id, int n, int d, int
   CU(cudaMemsetAsync(h->W, 0, sizeof(double) * nn, h->stream));  // the leaves never write above the diagonal
   CU(cudaStreamSynchronize(h->stream));
   for (auto& e : h->ev) CU(cudaEventCreate(&e));
-  h->blocking_wait = h->n_pad >= 2048 && !getenv("GPRAS_B200_SPIN_WAIT");
+  h->blocking_wait = getenv("GPRAS_B200_BLOCKING_WAIT") != nullptr;  // see gpras_gp_set_blocking_wait
   CU(cudaEventCreateWithFlags(&h->ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
   *out = h;
   return 0;
@@ -637,6 +637,13 @@ int gpras_gp_get_matrix(gpras_gp* h, int which, double* out) {
   }
   CU(cudaMemcpy2D(out, sizeof(double) * h->n, src, sizeof(double) * h->n_pad, sizeof(double) * h->n, h->n,
                   cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gpras_gp_set_blocking_wait(gpras_gp* h, int enabled) {
+  if (!h) return fail(GPRAS_E_ARG, "null handle");
+  if (h->pending) return fail(GPRAS_E_STATE, "an evaluation is in flight on this handle");
+  h->blocking_wait = enabled != 0;
   return 0;
 }
 

@@ -43,6 +43,10 @@ class ExactGP:
         except Exception:
             pass
 
+    def set_blocking_wait(self, enabled: bool) -> None:
+        """Sleep instead of spinning while waiting for an evaluation (several host threads per GPU)."""
+        check(self.lib.gpras_gp_set_blocking_wait(self._h, int(enabled)))
+
     # ---- data -----------------------------------------------------------------------------
     def set_stream(self, cuda_stream: int | None) -> None:
         check(self.lib.gpras_gp_set_stream(self._h, cuda_stream or None))

@@ -287,7 +287,10 @@ class ExactModel:
         workspace per lane and call costs ~0.3 s each next to other live allocations and stalls the evaluations in flight."""
         if not hasattr(self._slot, "pool"):  # e.g. the oracle-backed test double: evaluations are pure functions
             return [self.clone() for _ in range(count)]
-        return [self.clone(_FixedSlot(gp)) for gp in self._slot.pool(self, count)]
+        gps = self._slot.pool(self, count)
+        for gp in gps:  # one host thread per lane: let them sleep while they wait
+            gp.set_blocking_wait(count > 1)
+        return [self.clone(_FixedSlot(gp)) for gp in gps]
 
     def release_other_threads(self) -> None:
         release = getattr(self._slot, "release_other_threads", None)

@@ -160,8 +160,14 @@ def run_restarts(model, opt, starts: np.ndarray, opt_kwargs: dict, lanes: int = 
         from concurrent.futures import ThreadPoolExecutor
 
         clones = model.lane_models(lanes)  # one device handle per lane, kept by the model's slot between calls
-        with ThreadPoolExecutor(max_workers=lanes) as ex:
-            results = list(ex.map(lane, clones))
+        try:
+            with ThreadPoolExecutor(max_workers=lanes) as ex:
+                results = list(ex.map(lane, clones))
+        finally:
+            for c in clones:  # the lanes' handles go back to the spinning (lowest-latency) host wait
+                gp = getattr(getattr(c, "_slot", None), "gp", None)
+                if gp is not None:
+                    gp.set_blocking_wait(False)
         model.n_evals = getattr(model, "n_evals", 0) + sum(r[2] for r in results)
     rows = [row for res in results for row in res[0]]
     model.restart_busy_s = max((res[1] for res in results), default=0.0)

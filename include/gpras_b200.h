@@ -78,6 +78,10 @@ int gpras_gp_predict_cells(gpras_gp* h, const double* xs, int t, int xs_on_devic
                            double* mode_var, double* cell_mean, double* cell_var, long ldc);
 long gpras_gp_cell_pitch(gpras_gp* h);
 
+/* How the host waits for an evaluation: 0 (default) cudaStreamSynchronize, which spins; 1 a blocking event, which lets the
+ * thread sleep (several host threads per GPU, e.g. the restart lanes of gpras_b200/parallel.py). */
+int gpras_gp_set_blocking_wait(gpras_gp* h, int enabled);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 /* Copy internal matrices to host (n x n, row-major, lower triangle meaningful): which = 0 K~ as built,
  * 1 L, 2 W = L^-1, 3 K~^-1;  4 alpha (n x p). For tests. */
