@@ -57,6 +57,7 @@ SYMBOLS = {
     "gpras_metrics_reset": (C.c_int, [vp, C.c_double]),
     "gpras_metrics_update": (C.c_int, [vp, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int, C.c_int]),
     "gpras_gp_predict_metrics": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, C.c_long, C.c_int, vp, vp]),
+    "gpras_metrics_update_modes": (C.c_int, [vp, vp, vp, C.c_long, C.c_int, vp, C.c_long, vp, vp, C.c_long, C.c_int]),
     "gpras_metrics_finalize": (C.c_int, [vp, C.c_double, vp, vp, vp]),
     "gpras_metrics_timesteps": (C.c_long, [vp]),
     "gpras_metrics_last_launches": (C.c_int, [vp]),
@@ -74,6 +75,7 @@ SYMBOLS = {
     "gpras_pre_reverse": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "gpras_pre_reverse_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_long]),
     "gpras_pre_cell_pitch": (C.c_long, [vp]),
+    "gpras_pre_reverse_metrics": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_long, C.c_int]),
     "gpras_pre_trim": (C.c_int, [vp]),
     "gpras_pre_last_launches": (C.c_int, [vp]),
     "gpras_pre_last_stage_ms": (C.c_int, [vp, vp]),

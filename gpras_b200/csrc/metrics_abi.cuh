@@ -26,11 +26,12 @@ int prepare_metrics_kernels() {
   int r;
   if ((r = opt_in_smem(metrics_stream_kernel<P16, true>, MetCfg<P16>::SMEM_BYTES))) return r;
   if ((r = opt_in_smem(metrics_plain_tma_kernel, MPT_SMEM_BYTES))) return r;
+  if ((r = opt_in_smem(metrics_general_kernel<P16>, MetGenCfg<P16>::SMEM_BYTES))) return r;
   return 0;
 }
 
 // One block of t <= MET_TB rows; every pointer is a device pointer.  fused: (M, var, E, bias, rootS) describe the prediction.
-int metrics_block(gpras_metrics* m, cudaStream_t s, MetricsArgs a, int t, int p16, bool fused) {
+int metrics_block(gpras_metrics* m, cudaStream_t s, MetricsArgs a, int t, int p16, bool fused, bool general = false) {
   if (m->t_seen + t > m->t_cap) return fail(GPRAS_E_ARG, "more timesteps than the accumulator's capacity");
   const int t_tiles = (t + MET_ROWS - 1) / MET_ROWS;
   int splits = (2 * 148 + m->n_ctile - 1) / m->n_ctile;
@@ -45,7 +46,12 @@ int metrics_block(gpras_metrics* m, cudaStream_t s, MetricsArgs a, int t, int p1
   a.elev_x = m->has_ex ? m->elev_x : nullptr;
   a.elev_y = m->has_ey ? m->elev_y : nullptr;
   dim3 grid(m->n_ctile, splits);
-  if (fused) {
+  if (general) {  // prediction from mode-space means and PER-MODE variances
+    if (p16 == 32)
+      metrics_general_kernel<32><<<grid, MET_THREADS, MetGenCfg<32>::SMEM_BYTES, s>>>(a);
+    else
+      metrics_general_kernel<64><<<grid, MET_THREADS, MetGenCfg<64>::SMEM_BYTES, s>>>(a);
+  } else if (fused) {
     if (p16 == 32)
       metrics_stream_kernel<32, true><<<grid, MET_THREADS, MetCfg<32>::SMEM_BYTES, s>>>(a);
     else
@@ -244,6 +250,27 @@ int gpras_gp_predict_metrics(gpras_gp* h, gpras_metrics* m, const double* xs, in
   CU(cudaStreamSynchronize(s));
   CU(cudaStreamSynchronize(s2));
   h->launches += m->launches - l0;
+  return 0;
+}
+
+// Accumulate t <= 2048 timesteps predicted in MODE space with one variance per mode (the reference's per-column models):
+// y = max(M E + bias - elev, 0), conf = sqrt(V E^2), consumed tile by tile against the truth -- the (t x cells) prediction is
+// never written.  Every pointer is a DEVICE pointer: M, V (round_up(t, 32) x ldm, zero padded, ldm = p16 = 32 or 64),
+// E (p16 x lde folded EOF map, zero on dry cells), bias (lde), truth (t x ldx) or NULL.  Runs on the accumulator's stream
+// and returns when the block has been consumed.  Called by gpras_pre_reverse_metrics, which owns the map.
+int gpras_metrics_update_modes(gpras_metrics* m, const double* M, const double* V, long ldm, int p16, const double* E, long lde,
+                               const double* bias, const double* truth, long ldx, int t) {
+  if (!m || !M || !V || !E || !bias || t <= 0 || t > MET_TB) return fail(GPRAS_E_ARG, "bad argument");
+  if ((p16 != 32 && p16 != 64) || ldm != p16 || lde < m->c_pad) return fail(GPRAS_E_ARG, "mode tiles must be padded to 32 or 64 columns");
+  if (truth && ldx < m->c) return fail(GPRAS_E_ARG, "row pitch smaller than the cell count");
+  DeviceGuard guard(m->device);
+  MetricsArgs a;
+  memset(&a, 0, sizeof a);
+  a.M = M, a.Vm = V, a.ldm = ldm, a.E = E, a.lde = lde, a.bias = bias;
+  a.X = truth, a.ldx = ldx;
+  int r = metrics_block(m, m->stream, a, t, p16, true, true);
+  if (r) return r;
+  CU(cudaStreamSynchronize(m->stream));
   return 0;
 }
 

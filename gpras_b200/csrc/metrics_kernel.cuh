@@ -30,6 +30,7 @@ struct MetricsArgs {
   const double* M;      // (t_pad x ldm) mode-space means
   long ldm;
   const double* var;    // (t_pad) mode-space variance (noise included), shared by all modes
+  const double* Vm;     // general-variance kernel: (t_pad x ldm) mode-space variances, one per mode
   const double* E;      // (P16 x lde) folded EOF map, zero on dry / padded cells
   long lde;
   const double* bias;   // (c_pad)
@@ -305,6 +306,216 @@ __global__ void __launch_bounds__(MET_THREADS, FUSED ? 2 : 1) metrics_stream_ker
       }
     }
   // ---- CTA scalars: sum |e| and the match count ----
+  s_ab = warp_sum(s_ab);
+  s_ct = warp_sum(s_ct);
+  __syncthreads();
+  if (lane == 0) sMisc[warp] = s_ab, sMisc[8 + warp] = s_ct;
+  __syncthreads();
+  if (tid < 2) {
+    const double* r = sMisc + 8 * tid;
+    a.cta_part[((long)blockIdx.y * a.n_ctile + tj) * MET_CTAQ + tid] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  }
+}
+
+// ---- fused consumer with ONE VARIANCE PER MODE (the reference's default per-column models) ---------------------------------
+// As metrics_stream_kernel<P16, true>, but the confidence is conf[t][c] = sqrt(sum_p V[t][p] E[p][c]^2)
+// (gpras/preprocess.py:1081-1094 followed by pipeline.py:262-263's sqrt): a second DMMA product over the same E tile, squared
+// as the B fragments are read.  It is no longer separable in (t, c), so its row and cell sums are accumulated per element
+// like the error's.  Same outputs and fixed-shape reductions as the other variants.
+template <int P16>
+struct MetGenCfg {
+  static constexpr int LDE = 128 + 4;
+  static constexpr int LDA = P16 + 4;
+  static constexpr int RED_DOUBLES = 3 * 32 * MET_RED_LD + 16;
+  static constexpr int SMEM_DOUBLES = P16 * LDE + 4 * MET_ROWS * LDA + RED_DOUBLES;
+  static constexpr int SMEM_BYTES = SMEM_DOUBLES * (int)sizeof(double);
+};
+
+template <int P16>
+__global__ void __launch_bounds__(MET_THREADS, 1) metrics_general_kernel(const MetricsArgs a) {
+  using Cfg = MetGenCfg<P16>;
+  extern __shared__ __align__(16) double smem[];
+  double* sE = smem;
+  double* sA = sE + P16 * Cfg::LDE;                 // [2][MET_ROWS][LDA] means
+  double* sW = sA + 2 * MET_ROWS * Cfg::LDA;        // [2][MET_ROWS][LDA] variances
+  double* sRed = sW + 2 * MET_ROWS * Cfg::LDA;      // [3][32 slots][MET_RED_LD]
+  double* sMisc = sRed + 3 * 32 * MET_RED_LD;       // [16]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int wn = warp * 16;
+  const int tj = blockIdx.x;
+  const int t_begin = blockIdx.y * a.tiles_per_cta;
+  int t_end = t_begin + a.tiles_per_cta;
+  if (t_end > a.t_tiles) t_end = a.t_tiles;
+  const long col0 = (long)tj * 128 + wn + 2 * q;
+  const bool cols_full = (long)tj * 128 + 128 <= a.c;
+  const bool has_ex = a.elev_x != nullptr, has_ey = a.elev_y != nullptr;
+
+  double ex[2][2], b0[2][2];
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      const long c = col0 + 8 * h + w;
+      const bool ok = c < a.c;
+      ex[h][w] = (has_ex && ok) ? a.elev_x[c] : 0.0;
+      b0[h][w] = a.bias[c] - ((has_ey && ok) ? a.elev_y[c] : 0.0);
+    }
+  double c_e[2][2], c_e2[2][2], c_cf[2][2], c_mx[2][2], c_my[2][2];
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      c_e[h][w] = c_e2[h][w] = c_cf[h][w] = 0.0;
+      c_mx[h][w] = c_my[h][w] = -INFINITY;
+    }
+  double s_ab = 0.0, s_ct = 0.0;
+
+  auto load_rows = [&](int buf, int tt) {
+    constexpr int CPR = P16 / 2;
+    for (int c = tid; c < MET_ROWS * CPR; c += MET_THREADS) {
+      const int row = c / CPR, kc = c - row * CPR;
+      const long src = (long)(tt * MET_ROWS + row) * a.ldm + 2 * kc;
+      cp_async16(sA + (buf * MET_ROWS + row) * Cfg::LDA + 2 * kc, a.M + src);
+      cp_async16(sW + (buf * MET_ROWS + row) * Cfg::LDA + 2 * kc, a.Vm + src);
+    }
+  };
+  if (t_begin < t_end) {
+    for (int c = tid; c < P16 * 64; c += MET_THREADS) {
+      const int kr = c >> 6, mc = c & 63;
+      cp_async16(sE + kr * Cfg::LDE + 2 * mc, a.E + (long)kr * a.lde + (long)tj * 128 + 2 * mc);
+    }
+    load_rows(0, t_begin);
+    cp_async_commit();
+  }
+
+  for (int tt = t_begin; tt < t_end; tt++) {
+    const int buf = (tt - t_begin) & 1;
+    const int row_base = tt * MET_ROWS;
+    const bool full = cols_full && row_base + MET_ROWS <= a.t_rows;
+    double xv[4][2][2];
+    if (a.X == nullptr) {
+#pragma unroll
+      for (int f = 0; f < 4; f++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) xv[f][h][0] = xv[f][h][1] = 0.0;
+    } else if (full && a.x_vec) {
+#pragma unroll
+      for (int f = 0; f < 4; f++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const double2 v = __ldg(reinterpret_cast<const double2*>(a.X + (long)(row_base + 8 * f + g) * a.ldx + col0 + 8 * h));
+          xv[f][h][0] = v.x, xv[f][h][1] = v.y;
+        }
+    } else {
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        const int row = row_base + 8 * f + g;
+        const bool rok = row < a.t_rows;
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+          for (int w = 0; w < 2; w++) {
+            const long c = col0 + 8 * h + w;
+            xv[f][h][w] = (rok && c < a.c) ? __ldg(a.X + (long)row * a.ldx + c) : 0.0;
+          }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (tt + 1 < t_end) load_rows(buf ^ 1, tt + 1);
+    cp_async_commit();
+    double acc[4][2][2], vac[4][2][2];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        acc[f][h][0] = b0[h][0], acc[f][h][1] = b0[h][1];
+        vac[f][h][0] = vac[f][h][1] = 0.0;
+      }
+    const double* a0 = sA + buf * MET_ROWS * Cfg::LDA;
+    const double* w0 = sW + buf * MET_ROWS * Cfg::LDA;
+#pragma unroll
+    for (int ks = 0; ks < P16 / 4; ks++) {
+      double av[4], wv[4], bv[2];
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        av[f] = a0[(8 * f + g) * Cfg::LDA + 4 * ks + q];
+        wv[f] = w0[(8 * f + g) * Cfg::LDA + 4 * ks + q];
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) bv[h] = sE[(4 * ks + q) * Cfg::LDE + wn + 8 * h + g];
+#pragma unroll
+      for (int f = 0; f < 4; f++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          dmma(acc[f][h][0], acc[f][h][1], av[f], bv[h]);
+          dmma(vac[f][h][0], vac[f][h][1], wv[f], bv[h] * bv[h]);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const int rl = 8 * f + g;
+      const bool rok = full || row_base + rl < a.t_rows;
+      double r_e = 0.0, r_e2 = 0.0, r_cf = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+          double x = xv[f][h][w], y = acc[f][h][w];
+          if (has_ex) x = fmax(x - ex[h][w], 0.0);
+          if (has_ey) y = fmax(y, 0.0);
+          const bool ok = full || (rok && (col0 + 8 * h + w < a.c));
+          const double e = ok ? x - y : 0.0;
+          const double cf = ok ? sqrt(fmax(vac[f][h][w], 0.0)) : 0.0;
+          if (ok) {
+            c_mx[h][w] = fmax(c_mx[h][w], x);
+            c_my[h][w] = fmax(c_my[h][w], y);
+            s_ct += fabs(e) <= a.v_tol ? 1.0 : 0.0;
+          }
+          c_e[h][w] += e;
+          c_e2[h][w] = fma(e, e, c_e2[h][w]);
+          c_cf[h][w] += cf;
+          r_e += e;
+          r_e2 = fma(e, e, r_e2);
+          r_cf += cf;
+          s_ab += fabs(e);
+        }
+      const int slot = warp * 4 + q;
+      sRed[(0 * 32 + slot) * MET_RED_LD + rl] = r_e;
+      sRed[(1 * 32 + slot) * MET_RED_LD + rl] = r_e2;
+      sRed[(2 * 32 + slot) * MET_RED_LD + rl] = r_cf;
+    }
+    __syncthreads();
+    if (tid < 3 * MET_ROWS) {
+      const int qq = tid / MET_ROWS, row = tid - qq * MET_ROWS;
+      const double* r = sRed + (long)qq * 32 * MET_RED_LD + row;
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; k++) s += r[k * MET_RED_LD];
+      a.row_part[((long)qq * a.t_tiles * MET_ROWS + row_base + row) * a.n_ctile + tj] = s;
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      double v0 = c_e[h][w], v1 = c_e2[h][w], v2 = c_cf[h][w], v3 = c_mx[h][w], v4 = c_my[h][w];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        v3 = fmax(v3, __shfl_xor_sync(0xffffffffu, v3, o));
+        v4 = fmax(v4, __shfl_xor_sync(0xffffffffu, v4, o));
+      }
+      if (g == 0) {
+        double* o = a.cell_part + (long)blockIdx.y * MET_CELLQ * a.c_pad + col0 + 8 * h + w;
+        o[0] = v0, o[a.c_pad] = v1, o[2 * a.c_pad] = v2, o[3 * a.c_pad] = v3, o[4 * a.c_pad] = v4;
+      }
+    }
   s_ab = warp_sum(s_ab);
   s_ct = warp_sum(s_ct);
   __syncthreads();

@@ -764,6 +764,57 @@ int gpras_pre_reverse_device(gpras_pre* h, const double* mean, const double* var
   return r;
 }
 
+// reverse_transform fused with the metrics: per-mode variances, truth streamed, nothing written per cell-depth
+// (gpr.predict of per-column models -> reverse_transform -> wse_2_depth -> export_metric_summary, pipeline.py:260-286).
+int gpras_pre_reverse_metrics(gpras_pre* h, gpras_metrics* m, const double* mean, const double* var, int t, int on_device,
+                              const double* truth, long ldx, int truth_on_device) {
+  if (!h || !m || !mean || !var || t <= 0) return fail(GPRAS_E_ARG, "bad argument");
+  if (!h->fitted || h->p <= 0) return fail(GPRAS_E_STATE, "fit() / set_state() has not been called");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = h->stream;
+  int r;
+  if (!h->map_ready && (r = build_map(h))) return r;
+  const int p = h->p, pk = round_up(p, 32);
+  const long c_pad = h->c_pad;
+  double *M = nullptr, *V = nullptr, *X = nullptr;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(s);
+    pfree(h, M), pfree(h, V), pfree(h, X);
+  };
+  if ((r = palloc(h, &M, (size_t)PRE_REV_TB * pk)) || (r = palloc(h, &V, (size_t)PRE_REV_TB * pk)) ||
+      (truth && !truth_on_device && (r = palloc(h, &X, (size_t)PRE_REV_TB * c_pad)))) {
+    cleanup();
+    return r;
+  }
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (int t0 = 0; t0 < t && !r; t0 += PRE_REV_TB) {
+    const int tb = t - t0 < PRE_REV_TB ? t - t0 : PRE_REV_TB;
+    const int tb_pad = round_up(tb, 128);
+    cudaMemsetAsync(M, 0, sizeof(double) * (size_t)tb_pad * pk, s);
+    cudaMemsetAsync(V, 0, sizeof(double) * (size_t)tb_pad * pk, s);
+    cudaMemcpy2DAsync(M, sizeof(double) * pk, mean + (size_t)t0 * p, sizeof(double) * p, sizeof(double) * p, tb, kind, s);
+    cudaMemcpy2DAsync(V, sizeof(double) * pk, var + (size_t)t0 * p, sizeof(double) * p, sizeof(double) * p, tb, kind, s);
+    const double* xd = nullptr;
+    long ldd = 0;
+    if (truth) {
+      if (truth_on_device) {
+        xd = truth + (size_t)t0 * ldx, ldd = ldx;
+      } else {
+        cudaMemcpy2DAsync(X, sizeof(double) * c_pad, truth + (size_t)t0 * ldx, sizeof(double) * ldx, sizeof(double) * h->c, tb,
+                          cudaMemcpyHostToDevice, s);
+        xd = X, ldd = c_pad;
+      }
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      r = fail(GPRAS_E_CUDA, "staging the mode-space block", cudaGetLastError());
+      break;
+    }
+    r = gpras_metrics_update_modes(m, M, V, pk, pk, h->Ef, c_pad, h->bias, xd, ldd, tb);
+  }
+  cleanup();
+  return r;
+}
+
 int gpras_dsyev128(void* cuda_stream, const double* H, double* lambda, double* V) {
   if (!H || !lambda || !V) return fail(GPRAS_E_ARG, "null argument");
   if (gpras_device_count() <= 0) return fail(GPRAS_E_CUDA, "no CUDA device (no CPU fallback)");

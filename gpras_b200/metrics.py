@@ -112,6 +112,28 @@ class MetricsAccumulator:
             ptr(mm) if want_modes else None, ptr(mv) if want_modes else None))
         return mm, mv
 
+    def reverse_update(self, pp, mean, var, truth=None) -> None:
+        """Accumulate events predicted in MODE space by per-column models (one variance per mode, ``gpras/gpr.py:293-308``):
+        ``pp`` is the fitted / loaded ``PreProcessor`` mirror whose ``reverse_transform`` maps modes to cells; the cell-space
+        prediction ``max(mean E + bias - elev, 0)`` and its confidence ``sqrt(var E^2)`` are formed tile by tile and consumed
+        against ``truth`` (``(t, cells)``, host array, CUDA tensor or None) without ever being written
+        (``pipeline.py:260-286`` fused; ``gpras_pre_reverse_metrics``)."""
+        lib = pp._ensure_state()
+        dev = _is_device(mean)
+        if not dev:
+            mean, var = _f64(mean), _f64(var)
+        t, p = int(mean.shape[0]), int(mean.shape[1])
+        if tuple(var.shape) != (t, p) or p != int(pp.spatial_mode_count):
+            raise ValueError(f"expected (T, {pp.spatial_mode_count}) means and variances")
+        tr_dev = _is_device(truth)
+        if truth is not None and not tr_dev:
+            truth = _f64(truth)
+        if truth is not None and (truth.shape[0] != t or truth.shape[1] != self.c):
+            raise ValueError(f"expected truth of shape ({t}, {self.c})")
+        ldx = 0 if truth is None else (int(truth.stride(0)) if tr_dev else truth.shape[1])
+        check(lib.gpras_pre_reverse_metrics(pp._h, self._h, ptr(mean), ptr(var), t, int(dev), ptr(truth) if truth is not None else None,
+                                            ldx, int(tr_dev)))
+
     def timesteps(self) -> int:
         return int(self.lib.gpras_metrics_timesteps(self._h))
 

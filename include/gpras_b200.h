@@ -136,6 +136,12 @@ int gpras_gp_predict_metrics(gpras_gp* h, gpras_metrics* m, const double* xs, in
 /* scalars: 15 doubles = [sum e, sum e^2, sum conf, sum |e|, count(|e|<=v_tol), sum d, sum d^2, sum xm, sum (xm-mean xm)^2,
  * hits, misses, false alarms at depth_threshold, the same three at threshold 0] with d = max_t x - max_t y, xm = max_t x;
  * cells (5 x c) and rows (3 x timesteps) receive the raw per-cell / per-timestep reductions (host, may be NULL). */
+/* One block (t <= 2048) of mode-space predictions with ONE VARIANCE PER MODE, consumed against the truth without writing the
+ * (t x cells) prediction: y = max(M E + bias - elev, 0), conf = sqrt(V E^2).  All pointers are device pointers (M, V zero
+ * padded to ldm = p16 = 32 or 64 columns and round_up(t, 32) rows; E, bias: the folded map of a gpras_pre handle).  The
+ * caller-facing entry is gpras_pre_reverse_metrics. */
+int gpras_metrics_update_modes(gpras_metrics* m, const double* M, const double* V, long ldm, int p16, const double* E, long lde,
+                               const double* bias, const double* truth, long ldx, int t);
 int gpras_metrics_finalize(gpras_metrics* m, double depth_threshold, double* scalars, double* cells, double* rows);
 long gpras_metrics_timesteps(gpras_metrics* m);
 int gpras_metrics_last_launches(gpras_metrics* m);
@@ -185,6 +191,11 @@ int gpras_pre_reverse(gpras_pre* h, const double* mean, const double* var, int t
 int gpras_pre_reverse_device(gpras_pre* h, const double* mean, const double* var, int t, int on_device, double* cell_mean,
                              double* cell_var, long ldc);
 long gpras_pre_cell_pitch(gpras_pre* h);
+/* gpr.predict (per-column models: mean and variance per mode) -> reverse_transform -> wse_2_depth -> every metric of
+ * gpras/metrics.py, pipeline.py:260-286, fused: the truth (t x ldx, host or device, may be NULL) is streamed, the (t x cells)
+ * prediction and its confidence are never materialised.  m: an accumulator created for the same device and cell count. */
+int gpras_pre_reverse_metrics(gpras_pre* h, gpras_metrics* m, const double* mean, const double* var, int t, int on_device,
+                              const double* truth, long ldx, int truth_on_device);
 /* Workspaces (staged input, centred samples, Gram matrix ...) are recycled across calls; trim returns them to the driver. */
 int gpras_pre_trim(gpras_pre* h);
 int gpras_pre_last_launches(gpras_pre* h);

@@ -274,3 +274,43 @@ def test_metrics_misuse_raises(cuda):
     s = acc.finalize(0.5)
     assert s["rmse_aoi_toi"] == 1.0 and s["err_aoi_toi"] == -1.0 and acc.timesteps() == 6
     acc.close()
+
+
+@pytest.mark.parametrize("p,cells,t,with_truth", [(7, 333, 70, True), (40, 1500, 2300, True), (16, 900, 300, False)])
+def test_reverse_metrics_with_per_mode_variances_match_materialised_path(cuda, p, cells, t, with_truth):
+    """Per-column models give one variance per mode; the fused reverse-transform + metrics consumer (nothing written per
+    cell-depth) must equal the metrics of the materialised prediction: oracle reverse transform -> depth -> oracle metrics."""
+    torch = cuda
+    from gpras_b200.metrics import MetricsAccumulator
+    from gpras_b200.preprocess import PreProcessor
+    from gpras_b200.synth import make_cell_map
+    from oracle import metrics as om
+    from oracle.cells import reverse_transform
+
+    cm = make_cell_map(p, cells, seed=p)
+    rng = np.random.default_rng(p + t)
+    mean, var = rng.standard_normal((t, p)), rng.uniform(0.01, 2.0, (t, p))
+    pp = PreProcessor(spatial_mode_count=p, input_mean=cm.input_mean, elevations=cm.elevations, hydraulic_parameter="wse",
+                      wetness_classes=np.where(cm.dry_indices, "AD", "TF"), weights=cm.weights, eofs=cm.eofs, eigenvalues=np.ones(p),
+                      n_samples_fit=100, x_mean=cm.x_mean, x_std=cm.x_std)
+    rm, rv = reverse_transform(mean, var, cm.eofs, cm.x_mean, cm.x_std, cm.weights, cm.input_mean, cm.dry_indices, cm.elevations)
+    truth = rm + 0.3 * rng.standard_normal(rm.shape) if with_truth else None
+    acc = MetricsAccumulator(cells, t)
+    acc.set_elevations(cm.elevations if with_truth else None, cm.elevations)
+    acc.reset(0.1)
+    half = t // 2
+    acc.reverse_update(pp, mean[:half], var[:half], None if truth is None else truth[:half])
+    acc.reverse_update(pp, torch.from_numpy(mean[half:]).cuda(), torch.from_numpy(var[half:]).cuda(),
+                       None if truth is None else torch.from_numpy(truth[half:]).cuda())
+    got = acc.finalize(0.5)
+    y = np.maximum(rm - cm.elevations, 0)
+    x = np.maximum(truth - cm.elevations, 0) if with_truth else np.zeros_like(y)
+    ref = om.summarise(x, y, np.sqrt(rv), 0.5, 0.1)
+    for k in VEC:
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-11, err_msg=k)
+    for k in SCA + ("fi_aoi_toi",):
+        if np.isfinite(ref[k]):
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-11, err_msg=k)
+    assert acc.timesteps() == t
+    acc.close()
+    pp.close()
