@@ -42,6 +42,16 @@ def _worker(rank, world, port, out_dir):
     np.save(os.path.join(out_dir, f"table{rank}.npy"), table)
     np.save(os.path.join(out_dir, f"theta{rank}.npy"), m.theta())
 
+    # sparse model whose recipe trains Z: the winner's inducing inputs travel with its hyperparameters, on every rank
+    from test_host_cpu import OracleBackedSparseModel
+
+    ds = make_gp_data(50, 2, 1, seed=4)
+    sm = OracleBackedSparseModel("RBF", ds.x, ds.y, ds.x[:5].copy(), 1.0)
+    stab = parallel.run_restarts(sm, gpr.OPTIMIZERS["two-stage"], np.array([[1.0, 0.1, 1.0], [0.4, 0.3, 2.0], [2.0, 0.05, 0.6]]), dict(max_iter=3))
+    np.save(os.path.join(out_dir, f"sparse_table{rank}.npy"), stab)
+    np.save(os.path.join(out_dir, f"sparse_state{rank}.npy"), np.concatenate([sm.theta(), np.asarray(sm.inducing_variable.Z).ravel(),
+                                                                              [sm.training_loss()]]))
+
     # target columns sharded over ranks: LML and gradient are sums over column blocks (oracle as the local evaluator)
     from oracle import metrics as om
     from oracle.exact_gp import Theta, lml_and_grad
@@ -91,6 +101,19 @@ def test_restart_sharding_world2_matches_serial(tmp_path):
     np.testing.assert_allclose(ts, t0, rtol=1e-12)
     best = int(np.argmin(ts[:, 1]))
     np.testing.assert_allclose(m.theta()[:3], ts[best, 2:5], rtol=1e-12)
+
+
+def test_sparse_restarts_world2_keep_z_with_theta(tmp_path):
+    """ADVICE (round 1): with Z-training recipes every rank must end with the winner's theta AND its inducing inputs."""
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    t0, t1 = np.load(tmp_path / "sparse_table0.npy"), np.load(tmp_path / "sparse_table1.npy")
+    np.testing.assert_array_equal(t0, t1)
+    s0, s1 = np.load(tmp_path / "sparse_state0.npy"), np.load(tmp_path / "sparse_state1.npy")
+    np.testing.assert_array_equal(s0, s1)  # same theta, same Z, same loss on both ranks
+    best = int(np.argmin(t0[:, 1]))
+    np.testing.assert_allclose(s0[:3], t0[best, 2:5], rtol=1e-14)
+    np.testing.assert_allclose(s0[-1], t0[best, 1], rtol=1e-10)  # the model every rank holds is the one whose loss is reported
 
 
 def test_column_and_event_sharding_world2(tmp_path):
