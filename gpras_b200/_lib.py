@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 LIB_PATH = Path(__file__).resolve().parent / "libgpras_b200.so"
-ABI_VERSION = 3  # == GPRAS_B200_ABI_VERSION in include/gpras_b200.h
+ABI_VERSION = 4  # == GPRAS_B200_ABI_VERSION in include/gpras_b200.h
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -51,6 +51,15 @@ SYMBOLS = {
     "gpras_sgpr_condition": (C.c_int, [vp, vp, vp, C.c_double]),
     "gpras_sgpr_predict": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "gpras_sgpr_last_launches": (C.c_int, [vp]),
+    "gpras_sgpr_batch_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gpras_sgpr_batch_destroy": (C.c_int, [vp]),
+    "gpras_sgpr_batch_set_data": (C.c_int, [vp, vp, vp]),
+    "gpras_sgpr_batch_elbo_grad": (C.c_int, [vp, vp, vp, C.c_double, vp, vp, vp, vp]),
+    "gpras_sgpr_batch_adam": (
+        C.c_int,
+        [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, vp, vp, vp],
+    ),
+    "gpras_sgpr_batch_last_launches": (C.c_int, [vp]),
     "gpras_metrics_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_long]),
     "gpras_metrics_destroy": (C.c_int, [vp]),
     "gpras_metrics_set_elevations": (C.c_int, [vp, vp, vp]),

@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_tile_kernel(cons
 
 // out[e] = sum_z part[z * stride + e]  (fixed order -> deterministic), e < count
 static __global__ void splitk_reduce_kernel(const double* __restrict__ part, long stride, int nz, long count,
-                                     double* __restrict__ out) {
+                                     double* __restrict__ out, long bs = 0) {
+  part += blockIdx.y * bs, out += blockIdx.y * bs;
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;
   double s = 0.0;

@@ -18,8 +18,11 @@ constexpr int CT_LD = CT + 2;     // shared pitch of the transposed feature tile
 constexpr int PT_THREADS = 256;   // 16 x 16 threads; each owns 4 x 4 entries in each 64 x 64 quadrant
 
 // Xs[i][d] = X[i][d] / l_d for i < n, 0 for padding rows.
+// (bs: element stride between the models of a batch, blockIdx.y = model; 0 for a single model.  Same convention in every
+// kernel of the sparse model's evaluation: all per-model buffers live at one fixed offset from each other.)
 static __global__ void scale_features_kernel(const double* __restrict__ X, double* __restrict__ Xs, int n, int n_pad, int D,
-                                      const double* __restrict__ theta) {
+                                      const double* __restrict__ theta, long bs = 0) {
+  X += blockIdx.y * bs, Xs += blockIdx.y * bs, theta += blockIdx.y * bs;
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long)n_pad * D) return;
   int i = (int)(e / D), dd = (int)(e - (long)i * D);
@@ -58,8 +61,9 @@ template <int KID>
 __global__ void __launch_bounds__(PT_THREADS) cov_kernel(const double* __restrict__ Xs1, int n1, const double* __restrict__ Xs2,
                                                          int n2, int D, const double* __restrict__ theta,
                                                          double* __restrict__ out, long ldo, int n_tiles_x, int tri,
-                                                         int square, double jitter) {
+                                                         int square, double jitter, long bs = 0) {
   extern __shared__ __align__(16) double smem[];
+  Xs1 += blockIdx.y * bs, Xs2 += blockIdx.y * bs, theta += blockIdx.y * bs, out += blockIdx.y * bs;
   double* s1 = smem;
   double* s2 = smem + (long)D * CT_LD;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;

@@ -350,7 +350,13 @@ __device__ __forceinline__ void leaf_body(const double* In, long ldin, double* A
 // Factor + invert one diagonal block (single-block matrices: M <= 128 of the sparse model, and the microbenchmark).
 static __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_inv_kernel(const double* In, long ldin, double* A, long lda, double* __restrict__ W,
-                      long ldw, double* __restrict__ logdet_part, int* __restrict__ info, int jb) {
+                      long ldw, double* __restrict__ logdet_part, int* __restrict__ info, int jb, long bs = 0) {
+  // batch of independent single-block matrices (sparse models trained together): blockIdx.y = model, bs doubles apart
+  if (bs) {
+    const bool same = In == A;
+    A += blockIdx.y * bs, W += blockIdx.y * bs, logdet_part += blockIdx.y * bs, info += blockIdx.y * bs * 2;
+    In = same ? A : In + blockIdx.y * bs;
+  }
   // In points at the 128 x 128 block to factor (pitch ldin): the diagonal block of A itself, or a scratch block;
   // L goes to the diagonal block jb of A, W = L^-1 to that of W.
   if (In == A) In += (long)jb * LEAF_N * lda + (long)jb * LEAF_N;

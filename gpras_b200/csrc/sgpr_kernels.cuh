@@ -14,7 +14,8 @@ namespace gpras {
 
 // AATs = sum_z part[z] / s2 ;  B = AATs + I   (m_pad x m_pad, full)
 static __global__ void sgpr_finish_b_kernel(const double* __restrict__ part, long slab, int nz, const double* __restrict__ theta,
-                                     int m_pad, double* __restrict__ AATs, double* __restrict__ B) {
+                                     int m_pad, double* __restrict__ AATs, double* __restrict__ B, long bs = 0) {
+  part += blockIdx.y * bs, theta += blockIdx.y * bs, AATs += blockIdx.y * bs, B += blockIdx.y * bs;
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long)m_pad * m_pad) return;
   double s = 0.0;
@@ -26,7 +27,8 @@ static __global__ void sgpr_finish_b_kernel(const double* __restrict__ part, lon
 }
 
 // mirror the lower triangle into the upper one (n x n, pitch ld)
-static __global__ void mirror_lower_kernel(double* __restrict__ A, int n, long ld) {
+static __global__ void mirror_lower_kernel(double* __restrict__ A, int n, long ld, long bs = 0) {
+  A += blockIdx.y * bs;
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long)n * n) return;
   const int i = (int)(e / n), j = (int)(e - (long)i * n);
@@ -34,7 +36,9 @@ static __global__ void mirror_lower_kernel(double* __restrict__ A, int n, long l
 }
 
 // v[i][q] *= 1 / s2
-static __global__ void sgpr_scale_noise_kernel(double* __restrict__ v, long count, const double* __restrict__ theta) {
+static __global__ void sgpr_scale_noise_kernel(double* __restrict__ v, long count, const double* __restrict__ theta,
+                                        long bs = 0) {
+  v += blockIdx.y * bs, theta += blockIdx.y * bs;
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < count) v[e] /= theta[1];
 }
@@ -42,7 +46,8 @@ static __global__ void sgpr_scale_noise_kernel(double* __restrict__ v, long coun
 // Rm = R (I - Binv) - chat chat^T ;  RA = Rm - R AATs     (full, m_pad x m_pad; chat is m_pad x ldc, R columns)
 static __global__ void sgpr_build_r_kernel(const double* __restrict__ Binv, const double* __restrict__ AATs,
                                     const double* __restrict__ chat, long ldc, int R, int m_pad, double* __restrict__ Rm,
-                                    double* __restrict__ RA) {
+                                    double* __restrict__ RA, long bs = 0) {
+  Binv += blockIdx.y * bs, AATs += blockIdx.y * bs, chat += blockIdx.y * bs, Rm += blockIdx.y * bs, RA += blockIdx.y * bs;
   long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long)m_pad * m_pad) return;
   const int i = (int)(e / m_pad), j = (int)(e - (long)i * m_pad);
@@ -58,7 +63,9 @@ static __global__ void sgpr_build_r_kernel(const double* __restrict__ Binv, cons
 static __global__ void sgpr_scalars_kernel(const double* __restrict__ AATs, const double* __restrict__ Binv,
                                     const double* __restrict__ c, const double* __restrict__ chat, long ldc, int R,
                                     const double* __restrict__ Y, long ldy, int n, int m, int m_pad,
-                                    double* __restrict__ scal) {
+                                    double* __restrict__ scal, long bs = 0) {
+  AATs += blockIdx.y * bs, Binv += blockIdx.y * bs, c += blockIdx.y * bs, chat += blockIdx.y * bs, Y += blockIdx.y * bs,
+      scal += blockIdx.y * bs;
   __shared__ double red[5][256];
   const int tid = threadIdx.x;
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
@@ -106,8 +113,10 @@ __global__ void __launch_bounds__(PT_THREADS) sgpr_chain_kernel(const bool UU, c
                                                                 const double* __restrict__ Y, long ldy, int R,
                                                                 const double* __restrict__ theta, int n_tiles_x,
                                                                 double* __restrict__ part, int npart_cols,
-                                                                double* __restrict__ zpart, int m_pad) {
+                                                                double* __restrict__ zpart, int m_pad, long bs = 0) {
   extern __shared__ __align__(16) double smem[];
+  Zs += blockIdx.y * bs, Xs += blockIdx.y * bs, G1 += blockIdx.y * bs, u += blockIdx.y * bs, Y += blockIdx.y * bs,
+      theta += blockIdx.y * bs, part += blockIdx.y * bs, zpart += blockIdx.y * bs;
   double* s1 = smem;                    // [D][CT_LD]  rows (Zs)
   double* s2 = s1 + (long)D * CT_LD;    // [D][CT_LD]  cols (Xs or Zs)
   double* zacc = s2 + (long)D * CT_LD;  // [128][D]
@@ -234,7 +243,9 @@ static __global__ void sgpr_finalize_kernel(const double* __restrict__ scal, con
                                      const double* __restrict__ pa, int na, const double* __restrict__ pb, int nb,
                                      int npart_cols, const double* __restrict__ za, int nza, const double* __restrict__ zb,
                                      int nzb, const double* __restrict__ theta, int n, int m, int m_pad, int D, int R,
-                                     double* __restrict__ result) {
+                                     double* __restrict__ result, long bs = 0) {
+  scal += blockIdx.y * bs, logdet_lb += blockIdx.y * bs, pa += blockIdx.y * bs, pb += blockIdx.y * bs, za += blockIdx.y * bs,
+      zb += blockIdx.y * bs, theta += blockIdx.y * bs, result += blockIdx.y * bs;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const double variance = theta[0], s2 = theta[1];
   if (tid == 0) {

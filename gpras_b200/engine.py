@@ -273,6 +273,73 @@ class SparseGP:
         return int(self.lib.gpras_sgpr_last_launches(self._h))
 
 
+class SparseBatch:
+    """The per-column sparse models of one fit on one GPU, evaluated together and trained on the device
+    (``gpras_sgpr_batch_*``): ``p`` independent SGPR models over the same inputs with ``m <= 128`` inducing points each."""
+
+    MAX_INDUCING = 128
+
+    def __init__(self, kernel: str, n: int, d: int, m: int, p: int, device: int = 0):
+        self.lib = _lib.load()
+        if self.lib.gpras_device_count() <= 0:
+            raise _lib.GprasError("no CUDA device visible: gpras_b200 has no CPU fallback")
+        self.kernel, self.n, self.d, self.m, self.p, self.device = kernel, int(n), int(d), int(m), int(p), int(device)
+        h = C.c_void_p()
+        check(self.lib.gpras_sgpr_batch_create(C.byref(h), device, KERNEL_IDS[kernel], self.n, self.d, self.m, self.p))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.gpras_sgpr_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_data(self, x, y) -> None:
+        x, y = _f64(x), _f64(y)
+        if x.shape != (self.n, self.d) or y.shape != (self.n, self.p):
+            raise ValueError(f"expected x {(self.n, self.d)} and y {(self.n, self.p)}, got {x.shape}, {y.shape}")
+        check(self.lib.gpras_sgpr_batch_set_data(self._h, ptr(x), ptr(y)))
+
+    def elbo_grad(self, theta, z, jitter: float = 1e-6):
+        """(ELBO [p], d/dlog theta [p, 2 + D], d/dZ [p, M, D], info [p]) of all models in one pass."""
+        theta, z = _f64(theta), _f64(z)
+        if theta.shape != (self.p, 2 + self.d) or z.shape != (self.p, self.m, self.d):
+            raise ValueError(f"expected theta {(self.p, 2 + self.d)} and z {(self.p, self.m, self.d)}, got {theta.shape}, {z.shape}")
+        elbo, gt, gz = np.empty(self.p), np.empty((self.p, 2 + self.d)), np.empty((self.p, self.m, self.d))
+        info = np.zeros(self.p, np.int32)
+        check(self.lib.gpras_sgpr_batch_elbo_grad(self._h, ptr(theta), ptr(z), float(jitter), ptr(elbo), ptr(gt), ptr(gz),
+                                                  info.ctypes.data))
+        return elbo, gt, gz, info
+
+    def adam(self, u, n_ls: int, train_hypers: bool, train_z: bool, max_iter: int, learning_rate: float = 0.001,
+             jitter: float = 1e-6, transform: str = "softplus", priors: bool = True, noise_floor: float = 1e-6):
+        """One Adam stage of all models on the device (``gpras/gpr.py:147-173``).  ``u`` (p, 2 + n_ls + M D): unconstrained
+        [variance, noise, lengthscale(s), Z] per model.  Returns (u, losses [max_iter, p], steps [p])."""
+        u = _f64(u).copy()
+        nu = 2 + int(n_ls) + self.m * self.d
+        if u.shape != (self.p, nu):
+            raise ValueError(f"expected u of shape {(self.p, nu)}, got {u.shape}")
+        losses = np.empty((int(max_iter), self.p))
+        iters, info = np.zeros(self.p, np.int32), np.zeros(self.p, np.int32)
+        check(self.lib.gpras_sgpr_batch_adam(self._h, ptr(u), int(n_ls), int(train_hypers), int(train_z), int(max_iter),
+                                             float(learning_rate), float(jitter), 1 if transform == "log" else 0, int(priors),
+                                             float(noise_floor), ptr(losses) if max_iter > 0 else None, iters.ctypes.data,
+                                             info.ctypes.data))
+        bad = np.flatnonzero(info)
+        if bad.size:
+            raise _lib.NotPositiveDefiniteError(
+                f"Kuu or B lost positive definiteness in model {int(bad[0])} (first failing pivot {int(info[bad[0]])})")
+        return u, losses, iters
+
+    def last_launches(self) -> int:
+        return int(self.lib.gpras_sgpr_batch_last_launches(self._h))
+
+
 def kmeans_lloyd(x, centers0, max_iter: int = 300, tol: float = 1e-4, device: int = 0):
     """Lloyd iterations of ``sklearn.cluster.KMeans`` from the initial centres ``centers0`` on the GPU
     (``gpras_kmeans_lloyd``; the reference's inducing-input initialiser, ``gpras/gpr.py:313-315``).  ``tol`` is scikit-learn's

@@ -749,6 +749,7 @@ class GPRAS:
         kmeans_on_device: bool = False,
         n_jobs: int = 1,
         lockstep_models: bool = True,
+        device_trainer: bool = True,
         **opt_kwargs: Any,
     ) -> None:
         """Fit the surrogate (``gpr.py:237-275``).  Positional arguments and ``**opt_kwargs`` are the reference's.
@@ -768,7 +769,11 @@ class GPRAS:
         reference loops sequentially, ``gpr.py:273-274``, and so does the default).  Under ``torch.distributed`` (one
         process per GPU) per-column models are sharded round-robin over ranks and their parameters all-gathered.
         ``lockstep_models`` (default on) trains the per-column sparse models of the Adam-based recipes together, one round of
-        evaluations in flight at a time; the result is the one of the sequential loop.
+        evaluations in flight at a time; the result is the one of the sequential loop.  ``device_trainer`` (default on): sparse
+        models with at most 128 inducing points are evaluated in ONE batched pass (model index in the grid) and their Adam
+        steps -- transforms, priors, chain rule, update and early-stopping rule -- run on the device as a replayed CUDA graph
+        (``gpras_sgpr_batch_adam``), the host reading the variables back once per stage; same trajectories as the host loop up
+        to the rounding of ``exp`` / ``log`` / ``pow`` (measured 1e-13 relative on the fitted parameters).
         """
         self.x = np.asarray(x).astype(np.float64)
         self.y = np.asarray(y).astype(np.float64)
@@ -795,7 +800,8 @@ class GPRAS:
 
         from .parallel import dist_info
 
-        if (lockstep_models and n_jobs == 1 and restarts is None and dist_info()[1] == 1 and len(unique) > 1
+        if (lockstep_models and n_jobs == 1 and restarts is None and dist_info()[1] == 1
+                and (len(unique) > 1 or (not exact and device_trainer))
                 and optimization_method in ("adam", "two-stage") and set(opt_kwargs) <= {"max_iter"}
                 and (not exact or self.x.shape[0] <= 4096)):
             # the reference's default path: independent per-column models trained by Adam -- all of them advance together,
@@ -805,7 +811,7 @@ class GPRAS:
             if initial_theta is not None:
                 for model in unique:
                     _assign_theta(model, initial_theta)
-            fit_lockstep(unique, optimization_method, **opt_kwargs)
+            fit_lockstep(unique, optimization_method, device_trainer=device_trainer, **opt_kwargs)
         elif dist_info()[1] > 1 and len(unique) > 1 and restarts is None:
             # one process per GPU: per-column models go round-robin to ranks, parameters are all-gathered at the end
             from .parallel import run_models_sharded

@@ -244,15 +244,103 @@ def adam_lockstep(models, max_iter: int, learning_rate: float = 0.001) -> None:
         active = still
 
 
-def fit_lockstep(models, method: str, max_iter: int = 100) -> bool:
+_BATCH_POOL: dict = {}
+
+
+def _device_batch(models):
+    """A ``SparseBatch`` holding all of ``models`` when they qualify for the device-resident trainer (one target column each over
+    the same inputs, the same kernel / transform / prior configuration, at most 128 inducing points), else None."""
+    from .engine import SparseBatch
+
+    m0 = models[0]
+    if not all(isinstance(mdl, SparseModel) for mdl in models):
+        return None
+    m, d = m0.inducing_variable.Z.shape
+    cfg0 = _trainer_config(m0)
+    for mdl in models:
+        if (mdl.y.shape[1] != 1 or mdl.inducing_variable.Z.shape != (m, d) or mdl.device != m0.device or _trainer_config(mdl) != cfg0
+                or not (mdl.x is m0.x or np.array_equal(mdl.x, m0.x))):
+            return None
+    if m > SparseBatch.MAX_INDUCING or cfg0 is None:
+        return None
+    n = m0.x.shape[0]
+    key = (threading.get_ident(), m0.kernel.name, n, d, m, len(models), m0.device)
+    if key not in _BATCH_POOL:
+        for old in [k for k in _BATCH_POOL if k[0] == key[0]]:  # one batch per thread: a new shape replaces the old arena
+            _BATCH_POOL.pop(old).close()
+        _BATCH_POOL[key] = SparseBatch(m0.kernel.name, n, d, m, len(models), device=m0.device)
+    batch = _BATCH_POOL[key]
+    batch.set_data(m0.x, np.concatenate([mdl.y for mdl in models], axis=1))
+    return batch
+
+
+def _trainer_config(mdl):
+    """(kernel, transform, priors, noise floor, number of lengthscales) of a model, or None if its three hyperparameters are not
+    configured alike (the device trainer applies one transform and one prior setting to all of them)."""
+    ps = mdl.parameters
+    tr = {p.transform for p in ps}
+    pr = {p.prior for p in ps}
+    if len(tr) != 1 or len(pr) != 1 or mdl.kernel.variance.lower != 0.0 or mdl.kernel.lengthscales.lower != 0.0:
+        return None
+    if mdl.kernel.variance.size != 1 or mdl.likelihood.variance.size != 1:
+        return None
+    return (mdl.kernel.name, tr.pop(), pr.pop(), mdl.likelihood.variance.lower, mdl.kernel.lengthscales.size)
+
+
+def adam_device(models, batch, max_iter: int, learning_rate: float = 0.001) -> bool:
+    """``_optimize_adam`` (``gpr.py:147-173``) of all ``models`` as ONE device-resident loop (``gpras_sgpr_batch_adam``): no
+    host round trip per step.  Returns False when the models' trainable flags are not one of the recipes' stages."""
+    m0 = models[0]
+    flags = [[p.trainable for p in mdl.parameters] + [mdl.inducing_variable.trainable] for mdl in models]
+    if any(f != flags[0] for f in flags) or len(set(flags[0][:3])) != 1:
+        return False
+    train_h, train_z = flags[0][0], flags[0][3]
+    if not (train_h or train_z):
+        return True  # nothing trainable: _optimize_adam returns at once
+    _, transform, prior, floor, n_ls = _trainer_config(m0)
+    u0 = np.stack([np.concatenate([mdl.kernel.variance.unconstrained, mdl.likelihood.variance.unconstrained,
+                                   mdl.kernel.lengthscales.unconstrained, np.asarray(mdl.inducing_variable.Z, np.float64).ravel()])
+                   for mdl in models])
+    u, losses, iters = batch.adam(u0, n_ls, train_h, train_z, int(max_iter), learning_rate, JITTER, transform, prior is not None, floor)
+    for b, mdl in enumerate(models):
+        if train_h:
+            mdl.kernel.variance.unconstrained = u[b, 0:1].copy()
+            mdl.likelihood.variance.unconstrained = u[b, 1:2].copy()
+            mdl.kernel.lengthscales.unconstrained = u[b, 2:2 + n_ls].copy()
+        if train_z:
+            z = mdl.inducing_variable.Z
+            mdl.inducing_variable.Z = u[b, 2 + n_ls:].reshape(z.shape).copy()
+        mdl.n_evals += int(iters[b])
+        mdl.adam_losses = losses[: int(iters[b]), b].copy()
+    return True
+
+
+def fit_lockstep(models, method: str, max_iter: int = 100, device_trainer: bool = True) -> bool:
     """Train all per-column sparse models together with the Adam-based recipes (``"adam"``, ``"two-stage"``).  Returns False
-    (nothing done) for other recipes."""
+    (nothing done) for other recipes.  ``device_trainer`` (default): models that qualify (``_device_batch``) are evaluated in one
+    batched pass and their Adam steps run on the device; otherwise every round enqueues one evaluation per model and the
+    update rule runs on the host (``adam_lockstep``)."""
     from .gpr import _set_stage
 
     if method not in ("adam", "two-stage") or not models:
         return False
     m0 = models[0]
     n, d = m0.x.shape
+    batch = _device_batch(models) if device_trainer else None
+    if batch is not None:
+        if method == "adam":
+            if adam_device(models, batch, max_iter):
+                return True
+        else:
+            for mdl in models:
+                _set_stage(mdl, hypers=False, z=True)
+            adam_device(models, batch, max_iter)
+            for mdl in models:
+                _set_stage(mdl, hypers=True, z=False)
+            adam_device(models, batch, max_iter)
+            for mdl in models:
+                _set_stage(mdl, hypers=True, z=True)
+            return True
     if isinstance(m0, SparseModel):
         pool = _model_pool(m0.kernel.name, n, d, m0.inducing_variable.Z.shape[0], m0.y.shape[1], m0.device, len(models))
     else:  # per-column exact models: one exact-GP handle each

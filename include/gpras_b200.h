@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GPRAS_B200_ABI_VERSION 3
+#define GPRAS_B200_ABI_VERSION 4
 
 /* kernel ids == KERNEL_FACTORY keys that are constructible in the reference (gpr.py:21-29, 298) */
 #define GPRAS_KERNEL_RBF 0
@@ -111,6 +111,30 @@ int gpras_sgpr_elbo_grad_fetch(gpras_sgpr* h, double* elbo, double* grad_theta, 
 int gpras_sgpr_condition(gpras_sgpr* h, const double* theta, const double* z, double jitter);
 int gpras_sgpr_predict(gpras_sgpr* h, const double* xs, int t, double* mean, double* var);
 int gpras_sgpr_last_launches(gpras_sgpr* h);
+
+/* ---- the per-column sparse models of ONE fit, batched and trained on the device ----------------------------------
+ * Replaces the loop `for model in self.models: opt(model)` (gpr.py:273-274) for the Adam-based recipes (gpr.py:112-127,
+ * 147-173): p independent SGPR models (one target column each, r = 1) over the same inputs, m <= 128 inducing points.
+ * Every kernel of the evaluation runs once for all models (model index in blockIdx.y: bitwise the single-model results of
+ * gpras_sgpr_elbo_grad), and one Adam step of all models -- transforms, LogNormal(0, 1) priors, chain rule, Keras' update,
+ * the reference's early-stopping rule -- is one CUDA graph with no host round trip. */
+typedef struct gpras_sgpr_batch gpras_sgpr_batch;
+int gpras_sgpr_batch_create(gpras_sgpr_batch** out, int device, int kernel_id, int n, int d, int m, int p);
+int gpras_sgpr_batch_destroy(gpras_sgpr_batch* h);
+/* x: n x d (shared), y: n x p row-major (column b = model b's targets); host arrays. */
+int gpras_sgpr_batch_set_data(gpras_sgpr_batch* h, const double* x, const double* y);
+/* Bound + gradient of every model: theta p x (2 + d), z p x m x d -> elbo p, grad_theta p x (2 + d) (d/dlog theta),
+ * grad_z p x m x d, info p (0, or the failing pivot of a model whose Kuu / B lost positive definiteness). */
+int gpras_sgpr_batch_elbo_grad(gpras_sgpr_batch* h, const double* theta, const double* z, double jitter, double* elbo,
+                               double* grad_theta, double* grad_z, int* info);
+/* One Adam stage (_optimize_adam, gpr.py:147-173) of all models, device resident.
+ * u: p x (2 + n_ls + m d) in/out, the UNCONSTRAINED variables [variance, noise, lengthscale(s), Z] of each model;
+ * n_ls: 1 (one lengthscale, the reference) or d; train_hypers / train_z: the gpflow.set_trainable stage;
+ * transform: 0 = GPflow softplus (noise: + noise_floor), 1 = exp; priors: LogNormal(0, 1) on the hyperparameters;
+ * losses: max_iter x p out (NaN where a model had stopped; may be NULL); iters: p out, steps taken; info: p out. */
+int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hypers, int train_z, int max_iter, double lr,
+                          double jitter, int transform, int priors, double noise_floor, double* losses, int* iters, int* info);
+int gpras_sgpr_batch_last_launches(gpras_sgpr_batch* h);
 
 /* ---- streaming accuracy metrics: replaces gpras/metrics.py:85-324 (called from production/analysis/pipeline.py:281-286) -- */
 /* One accumulator = one event of up to t_capacity timesteps over c cells.  It keeps, per cell, sum(x-y), sum((x-y)^2),

@@ -178,7 +178,7 @@ def test_header_symbols_are_exported_and_bound(lib):
     out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     assert declared <= exported, declared - exported
-    assert lib.gpras_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.gpras_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_library_contains_dmma_and_no_cpu_fallback(lib):
