@@ -13,6 +13,7 @@
 // Restricted to M <= 128 inducing points (one 128-tile: the factorisations are single leaf launches).
 #pragma once
 #include "sgpr_abi.cuh"
+#include "sgpr_fused.cuh"
 
 struct SgprAdamCfg {
   int n_ls, train_hypers, train_z, transform, priors;
@@ -46,6 +47,10 @@ struct gpras_sgpr_batch {
   int losses_cap = 0;
   double* h_pinned = nullptr;  // p x (nu + 8) staging
   std::vector<std::pair<SgprAdamCfg, cudaGraphExec_t>> graphs;
+  // fused evaluation (sgpr_fused.cuh) for m <= 64, d <= 32: four kernels per evaluation, inputs shared by the models
+  bool fused = false;
+  gpras::SfArgs fa = {};
+  double *Xsh = nullptr, *yv = nullptr, *yy = nullptr;
 };
 
 namespace gpras {
@@ -342,6 +347,69 @@ int sb_record_eval(gpras_sgpr_batch* h, double jitter) {
   return 0;
 }
 
+// |y|^2 per model, summed like sgpr_scalars_kernel does (256 strided partial sums, then a fixed tree)
+__global__ void sf_yy_kernel(const double* __restrict__ yv, int n, long n_pad, double* __restrict__ yy) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  const double* y = yv + blockIdx.x * n_pad;
+  double s = 0.0;
+  for (int e = tid; e < n; e += 256) s = fma(y[e], y[e], s);
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) yy[blockIdx.x] = red[0];
+}
+
+template <int KID>
+int sf_launch_t(gpras_sgpr_batch* h, const SfArgs& a) {
+  cudaStream_t s = h->stream;
+  const int P = h->p;
+  static std::atomic<bool> attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    int r;
+    if ((r = opt_in_smem(sf_prep_kernel<KID>, 220 * 1024)) || (r = opt_in_smem(sf_forward_kernel<KID>, 220 * 1024)) ||
+        (r = opt_in_smem(sf_mid_kernel<KID>, 220 * 1024)) || (r = opt_in_smem(sf_backward_kernel<KID>, 220 * 1024)))
+      return r;
+    attr_done[dev] = true;
+  }
+  const int tile_smem = sf_tile_doubles(a.D, a.mp) * (int)sizeof(double);
+  sf_prep_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a);
+  sf_forward_kernel<KID><<<dim3(a.nct, P), SF_THREADS, tile_smem, s>>>(a);
+  sf_mid_kernel<KID><<<dim3(1, P), SF_THREADS, sf_mid_smem(a.D), s>>>(a);
+  sf_backward_kernel<KID><<<dim3(a.nct, P), SF_THREADS, tile_smem, s>>>(a);
+  h->launches += 4;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// the fused evaluation: theta / Z in device memory -> result
+int sf_record_eval(gpras_sgpr_batch* h, double jitter) {
+  SfArgs a = h->fa;
+  a.jitter = jitter;
+  int r = 0;
+  switch (h->kid) {
+    case K_RBF: r = sf_launch_t<K_RBF>(h, a); break;
+    case K_MATERN12: r = sf_launch_t<K_MATERN12>(h, a); break;
+    case K_MATERN32: r = sf_launch_t<K_MATERN32>(h, a); break;
+    case K_MATERN52: r = sf_launch_t<K_MATERN52>(h, a); break;
+    case K_EXPONENTIAL: r = sf_launch_t<K_EXPONENTIAL>(h, a); break;
+    default: return fail(GPRAS_E_ARG, "unknown kernel id");
+  }
+  if (r) return r;
+  sgpr_finalize_kernel<<<dim3(8, h->p), 256, 0, h->stream>>>(a.scal, a.logdetB, 1, a.partA, a.nct, a.partB, 1, 1 + a.D, a.zpA, a.nct,
+                                                           a.zpB, 1, a.theta, a.n, a.m, SF_MP, a.D, 1, h->result, h->bs);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int sb_eval(gpras_sgpr_batch* h, double jitter) { return h->fused ? sf_record_eval(h, jitter) : sb_record_eval(h, jitter); }
+
 }  // namespace
 
 extern "C" {
@@ -371,7 +439,25 @@ int gpras_sgpr_batch_create(gpras_sgpr_batch** out, int device, int kernel_id, i
     double** ptr;
     size_t count;
   };
-  const Carve parts[] = {
+  h->fused = m <= SF_MP && d <= SF_MAX_D && !getenv("GPRAS_B200_SGPR_UNFUSED");
+  std::vector<Carve> parts;
+  SfArgs& fa = h->fa;
+  if (h->fused) {
+    // tiles of 128 training rows, grouped so that the grid is about 1.5 waves of the 148 SMs and a model has at most 32 groups
+    // (each group leaves one partial M x M matrix for the model's mid kernel to add up)
+    fa.n = n, fa.n_pad = h->n_pad, fa.D = d, fa.m = m, fa.mp = round_up(m, 8), fa.ntn = h->ntn;
+    int tpc = (int)(((long)p * h->ntn + 111) / 222);
+    if (tpc < (h->ntn + 31) / 32) tpc = (h->ntn + 31) / 32;
+    if (tpc < 1) tpc = 1;
+    fa.tpc = tpc, fa.nct = (h->ntn + tpc - 1) / tpc;
+    parts = {{&h->theta, (size_t)2 + d}, {&h->Z, (size_t)m * d}, {&fa.Zs, (size_t)SF_MP * d}, {&fa.W, (size_t)SF_MP * SF_MP},
+             {&fa.Ap, (size_t)fa.mp * h->n_pad}, {&fa.slabs, (size_t)fa.nct * SF_MP * SF_MP}, {&fa.aep, (size_t)fa.nct * SF_MP},
+             {&fa.RW, (size_t)SF_MP * SF_MP}, {&fa.uvec, (size_t)SF_MP}, {&fa.scal, 8}, {&fa.logdetB, 1},
+             {&fa.partA, (size_t)fa.nct * (1 + d)}, {&fa.zpA, (size_t)fa.nct * SF_MP * d}, {&fa.partB, (size_t)1 + d},
+             {&fa.zpB, (size_t)SF_MP * d}, {&h->result, 3 + d + (size_t)m * d}, {&h->au, (size_t)h->nu}, {&h->amom, (size_t)h->nu},
+             {&h->avel, (size_t)h->nu}, {&h->ast, (size_t)gpras::AST}};
+  } else {
+    parts = {
       {&h->X, (size_t)h->n_pad * d}, {&h->Xs, (size_t)h->n_pad * d}, {&h->Z, (size_t)h->m_pad * d}, {&h->Zs, (size_t)h->m_pad * d},
       {&h->Y, (size_t)h->n_pad * h->r_pad}, {&h->Kuf, mn}, {&h->Kuu, mm}, {&h->WL, mm}, {&h->Ap, mn}, {&h->slabs, mm * h->nz_aat},
       {&h->AATs, mm}, {&h->B, mm}, {&h->WB, mm}, {&h->Binv, mm}, {&h->Rm, mm}, {&h->RA, mm}, {&h->RW, mm}, {&h->T1, mm}, {&h->Guu, mm},
@@ -380,8 +466,10 @@ int gpras_sgpr_batch_create(gpras_sgpr_batch** out, int device, int kernel_id, i
       {&h->partB, (size_t)1 + d}, {&h->zpA, (size_t)h->ntn * h->m_pad * d}, {&h->zpB, (size_t)h->m_pad * d},
       {&h->result, 3 + d + (size_t)m * d}, {&h->au, (size_t)h->nu}, {&h->amom, (size_t)h->nu}, {&h->avel, (size_t)h->nu},
       {&h->ast, (size_t)gpras::AST}};
+  }
   size_t per_model = 64;
   for (const Carve& c : parts) per_model += (c.count * sizeof(double) + 255) / 256 * 256;
+  // (fused layout: the SfArgs pointers were carved through references into h->fa)
   h->bs = (long)(per_model / sizeof(double));
   {
     cudaError_t e = cudaMalloc(&h->arena, per_model * p);
@@ -399,6 +487,15 @@ int gpras_sgpr_batch_create(gpras_sgpr_batch** out, int device, int kernel_id, i
   }
   // zero everything once: padding rows of X / Z / Y and the never-written upper triangles of WL / WB must be zero
   CU(cudaMemsetAsync(h->arena, 0, per_model * p, h->stream));
+  if (h->fused) {
+    if ((rc = dalloc(&h->Xsh, (size_t)h->n_pad * d)) || (rc = dalloc(&h->yv, (size_t)p * h->n_pad)) || (rc = dalloc(&h->yy, p))) {
+      gpras_sgpr_batch_destroy(h);
+      return rc;
+    }
+    CU(cudaMemsetAsync(h->Xsh, 0, sizeof(double) * h->n_pad * d, h->stream));
+    CU(cudaMemsetAsync(h->yv, 0, sizeof(double) * (size_t)p * h->n_pad, h->stream));
+    fa.X = h->Xsh, fa.yv = h->yv, fa.yy = h->yy, fa.theta = h->theta, fa.Z = h->Z, fa.info = h->info, fa.bs = h->bs;
+  }
   CU(cudaMallocHost(&h->h_pinned, sizeof(double) * (size_t)p * (h->nu + gpras::AST)));
   CU(cudaStreamSynchronize(h->stream));
   *out = h;
@@ -412,6 +509,9 @@ int gpras_sgpr_batch_destroy(gpras_sgpr_batch* h) {
   for (auto& g : h->graphs)
     if (g.second) cudaGraphExecDestroy(g.second);
   if (h->arena) cudaFree(h->arena);
+  if (h->Xsh) cudaFree(h->Xsh);
+  if (h->yv) cudaFree(h->yv);
+  if (h->yy) cudaFree(h->yy);
   if (h->losses) cudaFree(h->losses);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -423,6 +523,18 @@ int gpras_sgpr_batch_destroy(gpras_sgpr_batch* h) {
 int gpras_sgpr_batch_set_data(gpras_sgpr_batch* h, const double* x, const double* y) {
   if (!h || !x || !y) return fail(GPRAS_E_ARG, "null argument");
   DeviceGuard guard(h->device);
+  if (h->fused) {  // one copy of the inputs; targets transposed on the host, one vector per model
+    std::vector<double> yt((size_t)h->p * h->n_pad, 0.0);
+    for (int i = 0; i < h->n; i++)
+      for (int b = 0; b < h->p; b++) yt[(size_t)b * h->n_pad + i] = y[(size_t)i * h->p + b];
+    CU(cudaMemcpyAsync(h->Xsh, x, sizeof(double) * h->n * h->d, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->yv, yt.data(), sizeof(double) * yt.size(), cudaMemcpyHostToDevice, h->stream));
+    sf_yy_kernel<<<h->p, 256, 0, h->stream>>>(h->yv, h->n, h->n_pad, h->yy);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    h->has_data = true;
+    return 0;
+  }
   for (int b = 0; b < h->p; b++) {
     CU(cudaMemcpyAsync(h->X + b * h->bs, x, sizeof(double) * h->n * h->d, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpy2DAsync(h->Y + b * h->bs, sizeof(double) * h->r_pad, y + b, sizeof(double) * h->p, sizeof(double), h->n,
@@ -448,7 +560,7 @@ int gpras_sgpr_batch_elbo_grad(gpras_sgpr_batch* h, const double* theta, const d
   CU(cudaMemset2DAsync(h->info, pitch, 0, sizeof(int), P, s));
   h->launches = 0;
   int r;
-  if ((r = sb_record_eval(h, jitter))) return r;
+  if ((r = sb_eval(h, jitter))) return r;
   h->warmed = true;
   const size_t nres = 3 + D + (size_t)m * D;
   std::vector<double> res(nres * P);
@@ -505,7 +617,7 @@ int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hy
     sgpr_batch_unpack_kernel<<<P, 128, 0, s>>>(h->au, h->theta, h->Z, h->info, D, m, n_ls, transform, noise_floor, h->bs);
     h->launches++;
     CU(cudaGetLastError());
-    int rr = sb_record_eval(h, jitter);
+    int rr = sb_eval(h, jitter);
     if (rr) return rr;
     sgpr_batch_adam_kernel<<<P, 128, 0, s>>>(h->result, h->info, h->au, h->amom, h->avel, h->ast, h->losses, P, D, m, cfg, h->bs);
     h->launches++;
@@ -515,7 +627,7 @@ int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hy
   if (!h->warmed && max_iter > 0) {  // first evaluation eagerly (kernel attributes); its results are recomputed by step 1
     sgpr_batch_unpack_kernel<<<P, 128, 0, s>>>(h->au, h->theta, h->Z, h->info, D, m, n_ls, transform, noise_floor, h->bs);
     CU(cudaGetLastError());
-    if ((r = sb_record_eval(h, jitter))) return r;
+    if ((r = sb_eval(h, jitter))) return r;
     h->warmed = true;
   }
   cudaGraphExec_t exec = nullptr;

@@ -1,0 +1,641 @@
+// Fused evaluation of the sparse model for M <= 64 inducing points and D <= 32 features: FOUR kernels per evaluation
+// instead of ~45 ("one persistent launch sequence per SGPR evaluation").
+//
+// At reference scale (gpras/gpr.py:293-308 with M = 50, N = 5 000, D = 10) the general path (sgpr_abi.cuh) pads every M x M
+// matrix to one 128-tile and runs each dense step as its own launch on the tile engine: an evaluation is a chain of ~45
+// dependent microsecond kernels, most of them one CTA, and takes ~0.5 ms however many models are batched.  Here every
+// M x M step of one model runs inside ONE CTA with the matrices in shared memory (padded to a multiple of 8 only), and the
+// N-wide steps are two passes over 128-row tiles of the training inputs:
+//   sf_prep      (1 CTA / model)   Zs = Z / l, Kuu + jitter I, L = chol(Kuu), W = L^-1
+//   sf_forward   (tiles x models)  Kuf tile from the features, A' = W Kuf (stored), partial A' A'^T and A' y per CTA
+//   sf_mid       (1 CTA / model)   B = I + A'A'^T / s2, LB, WB, c, chat, u, B^-1, the bound's scalars, Rm, RA,
+//                                  RW = W^T Rm, Guu = 1/2 W^T RA W and the chain rule through Kuu
+//   sf_backward  (tiles x models)  G = (RW A' + u y^T) / s2 per tile and the chain rule through Kuf to theta and Z
+// followed by sgpr_finalize_kernel (shared with the general path).  Same formulas and notation as sgpr_kernels.cuh; the
+// arithmetic is plain FP64 FMA on register tiles (on this part DFMA and DMMA share one datapath, DESIGN.md section 4, and
+// the matrices are far too small for the tile engine's 128-wide shapes).
+#pragma once
+#include "gp_kernels.cuh"
+
+namespace gpras {
+
+constexpr int SF_MP = 64;            // largest padded number of inducing points
+constexpr int SF_LD = SF_MP + 1;     // shared-memory pitch of the M x M matrices (odd: rows and columns conflict free)
+constexpr int SF_THREADS = 256;
+constexpr int SF_TN = 128;           // training rows per tile
+constexpr int SF_MAX_D = 32;
+constexpr int SF_MAT = SF_MP * SF_LD;
+
+struct SfArgs {
+  const double* X;    // [n_pad][D]   shared by the models
+  const double* yv;   // [P][n_pad]   targets, zero padded
+  const double* yy;   // [P]          |y|^2
+  // per model; consecutive models are bs doubles apart
+  const double* theta;  // [2 + D]
+  const double* Z;      // [m][D]
+  double* Zs;           // [SF_MP][D]
+  double* W;            // [SF_MP][SF_MP]   L^-1, zeros above the diagonal, identity on the padding
+  double* Ap;           // [mp][n_pad]
+  double* slabs;        // [nct][SF_MP * SF_MP]
+  double* aep;          // [nct][SF_MP]
+  double* RW;           // [SF_MP][SF_MP]
+  double* uvec;         // [SF_MP]
+  double* scal;         // [8]
+  double* logdetB;      // [1]
+  double* partA;        // [nct][1 + D]
+  double* zpA;          // [nct][SF_MP][D]
+  double* partB;        // [1 + D]
+  double* zpB;          // [SF_MP][D]
+  int* info;
+  long bs;
+  int n, n_pad, D, m, mp, nct, tpc, ntn;
+  double jitter;
+};
+
+// ---- in-CTA dense helpers on mp x mp shared-memory matrices (pitch SF_LD), 256 threads --------------------------------
+
+// L = chol(A) (lower; A's lower triangle is consumed), rs[j] = 1 / L_jj.  A non-positive pivot records info = column + 1
+// (LAPACK convention) and continues with a unit pivot.  Ends with a barrier.
+__device__ __forceinline__ void sf_chol(double* __restrict__ A, double* __restrict__ L, double* __restrict__ rs, int mp,
+                                        int* __restrict__ info) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int j = 0; j < mp; j++) {
+    __syncthreads();  // the trailing update of step j - 1 is complete
+    double dj = A[j * SF_LD + j];
+    if (!(dj > 0.0)) {
+      if (tid == 0) atomicCAS(info, 0, j + 1);
+      dj = 1.0;
+    }
+    const double r = 1.0 / sqrt(dj);
+    if (tid == 0) rs[j] = r;
+    if (tid >= j && tid < mp) L[tid * SF_LD + j] = tid == j ? dj * r : A[tid * SF_LD + j] * r;
+    for (int i = j + 1 + ty; i < mp; i += 16) {
+      const double lij = A[i * SF_LD + j] * r;
+      for (int k = j + 1 + tx; k <= i; k += 16) A[i * SF_LD + k] -= lij * (A[k * SF_LD + j] * r);
+    }
+  }
+  __syncthreads();
+}
+
+// Wm = L^-1 (lower triangular, zeros above the diagonal): thread c solves column c by forward substitution in place.
+// Ends with a barrier.
+__device__ __forceinline__ void sf_trinv(const double* __restrict__ L, double* __restrict__ Wm, int mp) {
+  const int c = threadIdx.x;
+  if (c < mp) {
+    for (int i = 0; i < mp; i++) Wm[i * SF_LD + c] = i == c ? 1.0 : 0.0;
+    for (int k = c; k < mp; k++) {
+      const double wk = Wm[k * SF_LD + c] / L[k * SF_LD + k];
+      Wm[k * SF_LD + c] = wk;
+#pragma unroll 4
+      for (int i = k + 1; i < mp; i++) Wm[i * SF_LD + c] -= L[i * SF_LD + k] * wk;
+    }
+  }
+  __syncthreads();
+}
+
+// C = alpha * op(A) op(B), all mp x mp; thread (ty, tx) owns rows ty + 16 r, columns tx + 16 s.  C aliases neither operand.
+// No barrier inside.
+template <bool TA, bool TB>
+__device__ __forceinline__ void sf_mm(double* __restrict__ C, const double* __restrict__ A, const double* __restrict__ B, int mp,
+                                      double alpha) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int s = 0; s < 4; s++) acc[r][s] = 0.0;
+  for (int k = 0; k < mp; k++) {
+    double a[4], b[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) a[r] = TA ? A[k * SF_LD + ty + 16 * r] : A[(ty + 16 * r) * SF_LD + k];
+#pragma unroll
+    for (int s = 0; s < 4; s++) b[s] = TB ? B[(tx + 16 * s) * SF_LD + k] : B[k * SF_LD + tx + 16 * s];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int s = 0; s < 4; s++) acc[r][s] = fma(a[r], b[s], acc[r][s]);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const int i = ty + 16 * r, j = tx + 16 * s;
+      if (i < mp && j < mp) C[i * SF_LD + j] = alpha * acc[r][s];
+    }
+}
+
+// fixed-shape block sum of NV values per thread (red: [NV][SF_THREADS] shared); result valid on every thread after return
+template <int NV>
+__device__ __forceinline__ void sf_block_sum(double (&v)[NV], double* __restrict__ red) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; k++) red[k * SF_THREADS + tid] = v[k];
+  __syncthreads();
+  for (int o = SF_THREADS / 2; o > 0; o >>= 1) {
+    if (tid < o)
+#pragma unroll
+      for (int k = 0; k < NV; k++) red[k * SF_THREADS + tid] += red[k * SF_THREADS + tid + o];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < NV; k++) v[k] = red[k * SF_THREADS];
+  __syncthreads();
+}
+
+// ---- 1. per model: scaled inducing inputs, Kuu, its Cholesky factor and the factor's inverse ---------------------------
+constexpr int sf_prep_smem(int D) { return (3 * SF_MAT + SF_MP * D + SF_MP + SF_MAX_D) * (int)sizeof(double); }
+
+template <int KID>
+__global__ void __launch_bounds__(SF_THREADS, 1) sf_prep_kernel(const SfArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* SA = smem;             // Kuu
+  double* SL = SA + SF_MAT;      // L
+  double* SWm = SL + SF_MAT;     // W
+  double* zs = SWm + SF_MAT;     // [mp][D]
+  double* rs = zs + SF_MP * a.D;
+  double* ls = rs + SF_MP;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long off = (long)blockIdx.y * a.bs;
+  const int D = a.D, m = a.m, mp = a.mp;
+  const double* theta = a.theta + off;
+  const double* Z = a.Z + off;
+  int* info = a.info + off * 2;
+  if (tid == 0) *info = 0;
+  if (tid < D) ls[tid] = theta[2 + tid];
+  __syncthreads();
+  for (int e = tid; e < mp * D; e += SF_THREADS) {
+    const int i = e / D, dd = e - i * D;
+    const double v = i < m ? Z[e] / ls[dd] : 0.0;
+    zs[e] = v;
+    (a.Zs + off)[e] = v;
+  }
+  __syncthreads();
+  const double variance = theta[0];
+  for (int i = ty; i < mp; i += 16)
+    for (int j = tx; j <= i; j += 16) {
+      double r2 = 0.0;
+      for (int dd = 0; dd < D; dd++) {
+        const double df = zs[i * D + dd] - zs[j * D + dd];
+        r2 = fma(df, df, r2);
+      }
+      double k = variance * kernel_value<KID>(r2);
+      if (i == j) k += a.jitter;
+      if (i >= m || j >= m) k = i == j ? 1.0 : 0.0;
+      SA[i * SF_LD + j] = k;
+    }
+  sf_chol(SA, SL, rs, mp, info);
+  sf_trinv(SL, SWm, mp);
+  double* Wg = a.W + off;
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    Wg[i * SF_MP + j] = SWm[i * SF_LD + j];
+  }
+}
+
+// ---- 2. per (group of training-row tiles, model): A' = W Kuf, partial A' A'^T and A' y ---------------------------------
+struct SfTileSmem {
+  double *xsT;   // [D][128]        scaled features of the tile's training rows, transposed
+  double *zs;    // [mp][D]         scaled inducing inputs
+  double *M;     // [mp][SF_LD]     W (forward) or RW (backward)
+  double *KA;    // [mp][128]       Kuf tile / A' tile;  forward: afterwards A'^T [128][mp + 1]
+  double *ysm;   // [128]           targets of the tile
+  double *us;    // [SF_MP]         u (backward)
+  double *ls;    // [SF_MAX_D]      lengthscales
+  double *zacc;  // [mp][D]         Z-gradient accumulators (backward)
+};
+__host__ __device__ constexpr int sf_tile_doubles(int D, int mp) {
+  return D * SF_TN + mp * D + mp * SF_LD + SF_TN * (mp + 1) + SF_TN + SF_MP + SF_MAX_D + mp * D;
+}
+__device__ __forceinline__ SfTileSmem sf_tile_layout(double* smem, int D, int mp) {
+  SfTileSmem t;
+  t.xsT = smem;
+  t.zs = t.xsT + D * SF_TN;
+  t.M = t.zs + mp * D;
+  t.KA = t.M + mp * SF_LD;
+  t.ysm = t.KA + SF_TN * (mp + 1);
+  t.us = t.ysm + SF_TN;
+  t.ls = t.us + SF_MP;
+  t.zacc = t.ls + SF_MAX_D;
+  return t;
+}
+
+// features of rows [n0, n0 + 128) scaled by the lengthscales, transposed: xsT[d][c]; targets of the tile
+__device__ __forceinline__ void sf_stage_rows(const SfArgs& a, int n0, const double* __restrict__ ls, double* __restrict__ xsT,
+                                              double* __restrict__ ysm, int model) {
+  const int tid = threadIdx.x, D = a.D;
+  for (int e = tid; e < SF_TN * D; e += SF_THREADS) {
+    const int c = e / D, dd = e - c * D;
+    xsT[dd * SF_TN + c] = n0 + c < a.n ? a.X[(long)(n0 + c) * D + dd] / ls[dd] : 0.0;
+  }
+  if (tid < SF_TN) ysm[tid] = a.yv[(long)model * a.n_pad + n0 + tid];
+}
+
+template <int KID>
+__global__ void __launch_bounds__(SF_THREADS, 2) sf_forward_kernel(const SfArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3, q4 = mp >> 2;
+  const SfTileSmem sm = sf_tile_layout(smem, D, mp);
+  double *xsT = sm.xsT, *zs = sm.zs, *Wsm = sm.M, *KA = sm.KA, *ysm = sm.ysm, *ls = sm.ls;
+  const int ldt = mp + 1;  // pitch of A'^T
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int model = blockIdx.y;
+  const long off = (long)model * a.bs;
+  const double* theta = a.theta + off;
+  const double variance = theta[0];
+  if (tid < D) ls[tid] = theta[2 + tid];
+  for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    Wsm[i * SF_LD + j] = (a.W + off)[i * SF_MP + j];
+  }
+  const int ti = tid / q4, tj = tid - ti * q4;  // A' A'^T: rows ti + q4 r, columns tj + q4 s
+  const bool aat_active = ti < q4;
+  double acc2[4][4], aeacc[8];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int s = 0; s < 4; s++) acc2[r][s] = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) aeacc[r] = 0.0;
+  double* Apg = a.Ap + off;
+
+  for (int t = 0; t < a.tpc; t++) {
+    const int tile = blockIdx.x * a.tpc + t;
+    if (tile >= a.ntn) break;
+    const int n0 = tile * SF_TN;
+    __syncthreads();  // (first pass: ls, zs, W are in place; later: the previous tile's reads of KA are done)
+    sf_stage_rows(a, n0, ls, xsT, ysm, model);
+    __syncthreads();
+    // Kuf entries of this thread: rows warp + 8 r, columns lane + 32 s
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      if (r < na) {
+        const int i = warp + 8 * r;
+        double r2[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int dd = 0; dd < D; dd++) {
+          const double zi = zs[i * D + dd];
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            const double df = zi - xsT[dd * SF_TN + lane + 32 * s];
+            r2[s] = fma(df, df, r2[s]);
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          double k = variance * kernel_value<KID>(r2[s]);
+          if (i >= m || n0 + lane + 32 * s >= a.n) k = 0.0;
+          KA[i * SF_TN + lane + 32 * s] = k;
+        }
+      }
+    }
+    __syncthreads();
+    double acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int s = 0; s < 4; s++) acc[r][s] = 0.0;
+    for (int k = 0; k < mp; k++) {
+      double kv[4];
+#pragma unroll
+      for (int s = 0; s < 4; s++) kv[s] = KA[k * SF_TN + lane + 32 * s];
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (r < na) {
+          const double w = Wsm[(warp + 8 * r) * SF_LD + k];
+#pragma unroll
+          for (int s = 0; s < 4; s++) acc[r][s] = fma(w, kv[s], acc[r][s]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < na) {
+        const int i = warp + 8 * r;
+        double sy = 0.0;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          Apg[(long)i * a.n_pad + n0 + lane + 32 * s] = acc[r][s];
+          sy = fma(acc[r][s], ysm[lane + 32 * s], sy);
+        }
+        aeacc[r] += warp_sum(sy);
+      }
+    __syncthreads();  // every read of the Kuf tile is done: the buffer becomes A'^T
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < na) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) KA[(lane + 32 * s) * ldt + warp + 8 * r] = acc[r][s];
+      }
+    __syncthreads();
+    if (aat_active) {
+      for (int k = 0; k < SF_TN; k++) {
+        double ai[4], aj[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) ai[r] = KA[k * ldt + ti + q4 * r];
+#pragma unroll
+        for (int s = 0; s < 4; s++) aj[s] = KA[k * ldt + tj + q4 * s];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+          for (int s = 0; s < 4; s++) acc2[r][s] = fma(ai[r], aj[s], acc2[r][s]);
+      }
+    }
+  }
+  double* slab = a.slabs + off + (long)blockIdx.x * SF_MP * SF_MP;
+  if (aat_active) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int s = 0; s < 4; s++) slab[(ti + q4 * r) * SF_MP + tj + q4 * s] = acc2[r][s];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < na) (a.aep + off)[(long)blockIdx.x * SF_MP + warp + 8 * r] = aeacc[r];
+  }
+}
+
+// ---- 3. per model: everything M x M between the two passes -------------------------------------------------------------
+constexpr int sf_mid_smem(int D) {
+  return (4 * SF_MAT + SF_MP * D + 6 * SF_MP + 5 * SF_THREADS + 8 * (SF_MAX_D + 1)) * (int)sizeof(double);
+}
+
+template <int KID>
+__global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* SW = smem;            // W = L^-1
+  double* SA = SW + SF_MAT;     // AATs -> RA -> Guu
+  double* SB = SA + SF_MAT;     // B -> WB -> Rm -> T1
+  double* SL = SB + SF_MAT;     // LB -> Binv -> RW
+  double* zs = SL + SF_MAT;     // [mp][D]
+  double* ae = zs + SF_MP * a.D;
+  double* cv = ae + SF_MP;
+  double* chat = cv + SF_MP;
+  double* uv = chat + SF_MP;
+  double* rs = uv + SF_MP;
+  double* lgs = rs + SF_MP;                 // [SF_MP] scratch
+  double* red = lgs + SF_MP;                // [5][256]
+  double* glw = red + 5 * SF_THREADS;       // [8][D + 1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3;
+  const long off = (long)blockIdx.y * a.bs;
+  const double* theta = a.theta + off;
+  const double s2 = theta[1];
+  int* info = a.info + off * 2;
+
+  for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    SW[i * SF_LD + j] = (a.W + off)[i * SF_MP + j];
+    double s = 0.0;
+    for (int t = 0; t < a.nct; t++) s += (a.slabs + off)[(long)t * SF_MP * SF_MP + i * SF_MP + j];
+    s /= s2;
+    SA[i * SF_LD + j] = s;
+    SB[i * SF_LD + j] = s + (i == j ? 1.0 : 0.0);
+  }
+  if (tid < mp) {
+    double s = 0.0;
+    for (int t = 0; t < a.nct; t++) s += (a.aep + off)[(long)t * SF_MP + tid];
+    ae[tid] = s / s2;
+  }
+  // LB = chol(B), WB = LB^-1 (into SB), log det
+  sf_chol(SB, SL, rs, mp, info);
+  sf_trinv(SL, SB, mp);
+  if (tid < 64) {
+    double lg = tid < mp ? -log(rs[tid]) : 0.0;
+    lg = warp_sum(lg);
+    if (lane == 0) lgs[warp] = lg;
+  }
+  __syncthreads();
+  if (tid == 0) (a.logdetB + off)[0] = lgs[0] + lgs[1];
+  // c = WB ae ; chat = WB^T c ; u = W^T chat
+  if (tid < mp) {
+    double s = 0.0;
+    for (int k = 0; k <= tid; k++) s = fma(SB[tid * SF_LD + k], ae[k], s);
+    cv[tid] = s;
+  }
+  __syncthreads();
+  if (tid < mp) {
+    double s = 0.0;
+    for (int k = tid; k < mp; k++) s = fma(SB[k * SF_LD + tid], cv[k], s);
+    chat[tid] = s;
+  }
+  __syncthreads();
+  if (tid < mp) {
+    double s = 0.0;
+    for (int k = tid; k < mp; k++) s = fma(SW[k * SF_LD + tid], chat[k], s);
+    uv[tid] = s;
+    (a.uvec + off)[tid] = s;
+  }
+  // Binv = WB^T WB -> SL
+  sf_mm<true, false>(SL, SB, SB, mp, 1.0);
+  __syncthreads();
+  // the bound's scalars: tr(AATs), tr(Binv), |c|^2, chat^T AATs chat (real rows only)
+  {
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (tid < m) {
+      v[0] = SA[tid * SF_LD + tid];
+      v[1] = SL[tid * SF_LD + tid];
+      v[2] = cv[tid] * cv[tid];
+    }
+    for (int e = tid; e < m * m; e += SF_THREADS) {
+      const int i = e / m, j = e - i * m;
+      v[3] = fma(chat[i] * chat[j], SA[i * SF_LD + j], v[3]);
+    }
+    sf_block_sum<4>(v, red);
+    if (tid == 0) {
+      double* sc = a.scal + off;
+      sc[0] = v[0], sc[1] = v[1], sc[2] = v[2], sc[3] = a.yy[blockIdx.y], sc[4] = v[3];
+    }
+  }
+  // Rm = (I - Binv) - chat chat^T -> SB ;  RA = Rm - AATs -> SA
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    const double r = ((i == j ? 1.0 : 0.0) - SL[i * SF_LD + j]) - chat[i] * chat[j];
+    SB[i * SF_LD + j] = r;
+    SA[i * SF_LD + j] = r - SA[i * SF_LD + j];
+  }
+  __syncthreads();
+  // RW = W^T Rm -> SL -> global
+  sf_mm<true, false>(SL, SW, SB, mp, 1.0);
+  __syncthreads();
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    (a.RW + off)[i * SF_MP + j] = SL[i * SF_LD + j];
+  }
+  // T1 = W^T RA -> SB ;  Guu = 1/2 T1 W -> SA
+  sf_mm<true, false>(SB, SW, SA, mp, 1.0);
+  __syncthreads();
+  sf_mm<false, false>(SA, SB, SW, mp, 0.5);
+  __syncthreads();
+  // chain rule through Kuu (g = Guu, k(z_i, z_j) depends on z_i twice): rows warp + 8 r, columns lane + 32 s
+  for (int e = tid; e < 8 * (D + 1); e += SF_THREADS) glw[e] = 0.0;
+  __syncthreads();
+  double gvar = 0.0;
+  for (int r = 0; r < na; r++) {
+    const int i = warp + 8 * r;
+    double w[2], zj[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const int j = lane + 32 * s;
+      double r2 = 0.0;
+      if (j < mp)
+        for (int dd = 0; dd < D; dd++) {
+          const double df = zs[i * D + dd] - zs[j * D + dd];
+          r2 = fma(df, df, r2);
+        }
+      const double g = (i < m && j < m) ? SA[i * SF_LD + j] : 0.0;
+      double kval, fval;
+      kernel_eval<KID>(r2, kval, fval);
+      gvar = fma(g, kval, gvar);
+      w[s] = g * fval;
+    }
+    for (int dd = 0; dd < D; dd++) {
+      const double zi = zs[i * D + dd];
+      double zr = 0.0, sl = 0.0;
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const int j = lane + 32 * s;
+        zj[s] = j < mp ? zs[j * D + dd] : zi;
+        const double df = zi - zj[s];
+        const double wd = w[s] * df;
+        zr += wd;
+        sl = fma(wd, df, sl);
+      }
+      zr = warp_sum(zr);
+      sl = warp_sum(sl);
+      if (lane == 0) {
+        (a.zpB + off)[i * D + dd] = 2.0 * zr;
+        glw[warp * (D + 1) + 1 + dd] += sl;
+      }
+    }
+  }
+  gvar = warp_sum(gvar);
+  if (lane == 0) glw[warp * (D + 1)] = gvar;
+  __syncthreads();
+  if (tid < 1 + D) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) s += glw[wv * (D + 1) + tid];
+    (a.partB + off)[tid] = s;
+  }
+}
+
+// ---- 4. per (group of tiles, model): chain rule through Kuf ------------------------------------------------------------
+template <int KID>
+__global__ void __launch_bounds__(SF_THREADS, 2) sf_backward_kernel(const SfArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3;
+  const SfTileSmem sm = sf_tile_layout(smem, D, mp);
+  double *xsT = sm.xsT, *zs = sm.zs, *RWs = sm.M, *KA = sm.KA, *ysm = sm.ysm, *us = sm.us, *ls = sm.ls, *zacc = sm.zacc;
+  __shared__ double glw[8][SF_MAX_D + 1];  // per warp: variance term, lengthscale terms
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int model = blockIdx.y;
+  const long off = (long)model * a.bs;
+  const double* theta = a.theta + off;
+  const double inv_s2 = 1.0 / theta[1];
+  if (tid < D) ls[tid] = theta[2 + tid];
+  if (tid < mp) us[tid] = (a.uvec + off)[tid];
+  for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e], zacc[e] = 0.0;
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    RWs[i * SF_LD + j] = (a.RW + off)[i * SF_MP + j];
+  }
+  for (int e = tid; e < 8 * (SF_MAX_D + 1); e += SF_THREADS) (&glw[0][0])[e] = 0.0;
+  double gvar = 0.0;
+  const double* Apg = a.Ap + off;
+
+  for (int t = 0; t < a.tpc; t++) {
+    const int tile = blockIdx.x * a.tpc + t;
+    if (tile >= a.ntn) break;
+    const int n0 = tile * SF_TN;
+    __syncthreads();
+    sf_stage_rows(a, n0, ls, xsT, ysm, model);
+    for (int e = tid; e < mp * SF_TN; e += SF_THREADS) {
+      const int k = e >> 7, c = e & (SF_TN - 1);
+      KA[e] = Apg[(long)k * a.n_pad + n0 + c];
+    }
+    __syncthreads();
+    // G1 = RW A'
+    double acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int s = 0; s < 4; s++) acc[r][s] = 0.0;
+    for (int k = 0; k < mp; k++) {
+      double kv[4];
+#pragma unroll
+      for (int s = 0; s < 4; s++) kv[s] = KA[k * SF_TN + lane + 32 * s];
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (r < na) {
+          const double w = RWs[(warp + 8 * r) * SF_LD + k];
+#pragma unroll
+          for (int s = 0; s < 4; s++) acc[r][s] = fma(w, kv[s], acc[r][s]);
+        }
+    }
+    // g = (G1 + u y^T) / s2 ; acc <- g * F ; variance term
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < na) {
+        const int i = warp + 8 * r;
+        const double ui = us[i];
+        double r2[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int dd = 0; dd < D; dd++) {
+          const double zi = zs[i * D + dd];
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            const double df = zi - xsT[dd * SF_TN + lane + 32 * s];
+            r2[s] = fma(df, df, r2[s]);
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const int c = lane + 32 * s;
+          const double g = (i < m && n0 + c < a.n) ? fma(ui, ysm[c], acc[r][s]) * inv_s2 : 0.0;
+          double kval, fval;
+          kernel_eval<KID>(r2[s], kval, fval);
+          gvar = fma(g, kval, gvar);
+          acc[r][s] = g * fval;
+        }
+      }
+    // lengthscale and Z terms
+    for (int dd = 0; dd < D; dd++) {
+      double xv[4];
+#pragma unroll
+      for (int s = 0; s < 4; s++) xv[s] = xsT[dd * SF_TN + lane + 32 * s];
+      double sl = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (r < na) {
+          const int i = warp + 8 * r;
+          const double zi = zs[i * D + dd];
+          double zr = 0.0;
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            const double df = zi - xv[s];
+            const double wd = acc[r][s] * df;
+            zr += wd;
+            sl = fma(wd, df, sl);
+          }
+          zr = warp_sum(zr);
+          if (lane == 0) zacc[i * D + dd] += zr;  // row i belongs to this warp alone
+        }
+      sl = warp_sum(sl);
+      if (lane == 0) glw[warp][1 + dd] += sl;
+    }
+  }
+  gvar = warp_sum(gvar);
+  if (lane == 0) glw[warp][0] = gvar;
+  __syncthreads();
+  if (tid < 1 + D) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) s += glw[wv][tid];
+    (a.partA + off)[(long)blockIdx.x * (1 + D) + tid] = s;
+  }
+  double* zp = a.zpA + off + (long)blockIdx.x * SF_MP * D;
+  for (int e = tid; e < mp * D; e += SF_THREADS) zp[e] = zacc[e];
+}
+
+}  // namespace gpras
