@@ -451,7 +451,7 @@ int gpras_sgpr_batch_create(gpras_sgpr_batch** out, int device, int kernel_id, i
     if (tpc < 1) tpc = 1;
     fa.tpc = tpc, fa.nct = (h->ntn + tpc - 1) / tpc;
     parts = {{&h->theta, (size_t)2 + d}, {&h->Z, (size_t)m * d}, {&fa.Zs, (size_t)SF_MP * d}, {&fa.W, (size_t)SF_MP * SF_MP},
-             {&fa.Ap, (size_t)fa.mp * h->n_pad}, {&fa.slabs, (size_t)fa.nct * SF_MP * SF_MP}, {&fa.aep, (size_t)fa.nct * SF_MP},
+             {&fa.Ap, (size_t)fa.mp * h->n_pad}, {&fa.Kv, (size_t)fa.mp * h->n_pad}, {&fa.Fv, (size_t)fa.mp * h->n_pad}, {&fa.slabs, (size_t)fa.nct * SF_MP * SF_MP}, {&fa.aep, (size_t)fa.nct * SF_MP},
              {&fa.RW, (size_t)SF_MP * SF_MP}, {&fa.uvec, (size_t)SF_MP}, {&fa.scal, 8}, {&fa.logdetB, 1},
              {&fa.partA, (size_t)fa.nct * (1 + d)}, {&fa.zpA, (size_t)fa.nct * SF_MP * d}, {&fa.partB, (size_t)1 + d},
              {&fa.zpB, (size_t)SF_MP * d}, {&h->result, 3 + d + (size_t)m * d}, {&h->au, (size_t)h->nu}, {&h->amom, (size_t)h->nu},

@@ -16,6 +16,7 @@
 // the matrices are far too small for the tile engine's 128-wide shapes).
 #pragma once
 #include "gp_kernels.cuh"
+#include "leaf.cuh"
 
 namespace gpras {
 
@@ -36,6 +37,8 @@ struct SfArgs {
   double* Zs;           // [SF_MP][D]
   double* W;            // [SF_MP][SF_MP]   L^-1, zeros above the diagonal, identity on the padding
   double* Ap;           // [mp][n_pad]
+  double* Kv;           // [mp][n_pad]   k(z_i, x_n) / variance      (forward pass -> backward pass)
+  double* Fv;           // [mp][n_pad]   derivative factor F / variance
   double* slabs;        // [nct][SF_MP * SF_MP]
   double* aep;          // [nct][SF_MP]
   double* RW;           // [SF_MP][SF_MP]
@@ -54,41 +57,135 @@ struct SfArgs {
 
 // ---- in-CTA dense helpers on mp x mp shared-memory matrices (pitch SF_LD), 256 threads --------------------------------
 
-// L = chol(A) (lower; A's lower triangle is consumed), rs[j] = 1 / L_jj.  A non-positive pivot records info = column + 1
-// (LAPACK convention) and continues with a unit pivot.  Ends with a barrier.
+// L = chol(A) (lower; A's lower triangle is consumed), rs[j] = 1 / L_jj.  Right-looking with 8-column panels: every thread
+// factors the 8 x 8 diagonal block redundantly in registers (no broadcast, no barrier), one thread per row solves the panel
+// below it, then the trailing triangle takes the rank-8 update on a 16 x 16 thread grid: two barriers per panel.  A
+// non-positive pivot records info = column + 1 (LAPACK convention) and continues with a unit pivot.  Ends with a barrier.
 __device__ __forceinline__ void sf_chol(double* __restrict__ A, double* __restrict__ L, double* __restrict__ rs, int mp,
                                         int* __restrict__ info) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int j = 0; j < mp; j++) {
-    __syncthreads();  // the trailing update of step j - 1 is complete
-    double dj = A[j * SF_LD + j];
-    if (!(dj > 0.0)) {
-      if (tid == 0) atomicCAS(info, 0, j + 1);
-      dj = 1.0;
+  for (int j0 = 0; j0 < mp; j0 += 8) {
+    __syncthreads();  // the trailing update of the previous panel is complete
+    double Dg[8][8], rsv[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int c = 0; c <= r; c++) Dg[r][c] = A[(j0 + r) * SF_LD + j0 + c];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      double dp = Dg[c][c];
+      if (!(dp > 0.0)) {  // identical on every thread
+        if (tid == 0) atomicCAS(info, 0, j0 + c + 1);
+        dp = 1.0;
+      }
+      const double r_ = leaf_rsqrt(dp);
+      rsv[c] = r_;
+      Dg[c][c] = dp * r_;
+#pragma unroll
+      for (int r = c + 1; r < 8; r++) Dg[r][c] *= r_;
+#pragma unroll
+      for (int c2 = c + 1; c2 < 8; c2++)
+#pragma unroll
+        for (int r = c2; r < 8; r++) Dg[r][c2] -= Dg[r][c] * Dg[c2][c];
     }
-    const double r = 1.0 / sqrt(dj);
-    if (tid == 0) rs[j] = r;
-    if (tid >= j && tid < mp) L[tid * SF_LD + j] = tid == j ? dj * r : A[tid * SF_LD + j] * r;
-    for (int i = j + 1 + ty; i < mp; i += 16) {
-      const double lij = A[i * SF_LD + j] * r;
-      for (int k = j + 1 + tx; k <= i; k += 16) A[i * SF_LD + k] -= lij * (A[k * SF_LD + j] * r);
+    const int i = j0 + tid;
+    if (tid < 8) {
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (tid == r) {
+#pragma unroll
+          for (int c = 0; c <= r; c++) L[i * SF_LD + j0 + c] = Dg[r][c];
+          rs[i] = rsv[r];
+        }
+    } else if (i < mp) {  // x = a L_JJ^-T
+      double v[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) v[c] = A[i * SF_LD + j0 + c];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        double sacc = v[c];
+#pragma unroll
+        for (int c1 = 0; c1 < c; c1++) sacc = fma(-v[c1], Dg[c][c1], sacc);
+        v[c] = sacc * rsv[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) L[i * SF_LD + j0 + c] = v[c];
+    }
+    __syncthreads();
+    for (int ii = j0 + 8 + ty; ii < mp; ii += 16) {
+      double li[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) li[c] = L[ii * SF_LD + j0 + c];
+      for (int k = j0 + 8 + tx; k <= ii; k += 16) {
+        double sacc = A[ii * SF_LD + k];
+#pragma unroll
+        for (int c = 0; c < 8; c++) sacc = fma(-li[c], L[k * SF_LD + j0 + c], sacc);
+        A[ii * SF_LD + k] = sacc;
+      }
     }
   }
   __syncthreads();
 }
 
-// Wm = L^-1 (lower triangular, zeros above the diagonal): thread c solves column c by forward substitution in place.
-// Ends with a barrier.
-__device__ __forceinline__ void sf_trinv(const double* __restrict__ L, double* __restrict__ Wm, int mp) {
-  const int c = threadIdx.x;
-  if (c < mp) {
-    for (int i = 0; i < mp; i++) Wm[i * SF_LD + c] = i == c ? 1.0 : 0.0;
-    for (int k = c; k < mp; k++) {
-      const double wk = Wm[k * SF_LD + c] / L[k * SF_LD + k];
-      Wm[k * SF_LD + c] = wk;
-#pragma unroll 4
-      for (int i = k + 1; i < mp; i++) Wm[i * SF_LD + c] -= L[i * SF_LD + k] * wk;
+// Wm = L^-1 (lower triangular, zeros above the diagonal; rs[j] = 1 / L_jj from sf_chol): the 8 x 8 diagonal blocks are
+// inverted by one thread each in registers, then recursive doubling -- for adjacent diagonal blocks of size b,
+// W21 = -W22 (L21 W11) -- with every entry of a level computed in parallel (T = L21 W11 is parked transposed in the unused
+// upper triangle of Wm).  Ends with a barrier.
+__device__ __forceinline__ void sf_trinv(const double* __restrict__ L, const double* __restrict__ rs, double* __restrict__ Wm,
+                                         int mp) {
+  const int tid = threadIdx.x;
+  if (tid < (mp >> 3)) {
+    const int j0 = 8 * tid;
+    double Lb[8][8], X[8][8], rsv[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      rsv[r] = rs[j0 + r];
+#pragma unroll
+      for (int c = 0; c < r; c++) Lb[r][c] = L[(j0 + r) * SF_LD + j0 + c];
     }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      X[c][c] = rsv[c];
+#pragma unroll
+      for (int r = c + 1; r < 8; r++) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = c; k < r; k++) sacc = fma(Lb[r][k], X[k][c], sacc);
+        X[r][c] = -sacc * rsv[r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int c = 0; c <= r; c++) Wm[(j0 + r) * SF_LD + j0 + c] = X[r][c];
+  }
+  __syncthreads();
+  for (int b = 8; b < mp; b <<= 1) {
+    const int npairs = (mp + 2 * b - 1) / (2 * b), bb = b * b, total = npairs * bb;
+    for (int e = tid; e < total; e += SF_THREADS) {  // T[i][j] = sum_k L[i][k] W[k][j], k in the first block, k >= j
+      const int pr = e / bb, rem = e - pr * bb, ii = rem / b, jj = rem - ii * b;
+      const int r0 = pr * 2 * b, i = r0 + b + ii, j = r0 + jj;
+      if (i < mp) {
+        double sacc = 0.0;
+        for (int k = j; k < r0 + b; k++) sacc = fma(L[i * SF_LD + k], Wm[k * SF_LD + j], sacc);
+        Wm[j * SF_LD + i] = sacc;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < total; e += SF_THREADS) {  // W[i][j] = -sum_k W[i][k] T[k][j], k in the second block, k <= i
+      const int pr = e / bb, rem = e - pr * bb, ii = rem / b, jj = rem - ii * b;
+      const int r0 = pr * 2 * b, i = r0 + b + ii, j = r0 + jj;
+      if (i < mp) {
+        double sacc = 0.0;
+        for (int k = r0 + b; k <= i; k++) sacc = fma(Wm[i * SF_LD + k], Wm[j * SF_LD + k], sacc);
+        Wm[i * SF_LD + j] = -sacc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    if (j > i) Wm[i * SF_LD + j] = 0.0;
   }
   __syncthreads();
 }
@@ -185,7 +282,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_prep_kernel(const SfArgs a) 
       SA[i * SF_LD + j] = k;
     }
   sf_chol(SA, SL, rs, mp, info);
-  sf_trinv(SL, SWm, mp);
+  sf_trinv(SL, rs, SWm, mp);
   double* Wg = a.W + off;
   for (int e = tid; e < mp * mp; e += SF_THREADS) {
     const int i = e / mp, j = e - i * mp;
@@ -194,26 +291,32 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_prep_kernel(const SfArgs a) 
 }
 
 // ---- 2. per (group of training-row tiles, model): A' = W Kuf, partial A' A'^T and A' y ---------------------------------
+// Tile kernels: 8 warps; the three products (A' = W Kuf, A' A'^T here, RW A' in the backward pass) run on the FP64 tensor
+// pipe (DMMA.8x8x4, fragment layout of common.cuh) from shared-memory operands whose pitches are == 4 (mod 16) doubles, which
+// makes every fragment load conflict free.  Warp w owns the 8 rows [8w, 8w + 8) of the M-row tile, all 128 columns.
+constexpr int SF_LDM = SF_MP + 4;   // pitch of W / RW in the tile kernels
+constexpr int SF_LDK = SF_TN + 4;   // pitch of the Kuf / A' tile  [mp][128]
+
 struct SfTileSmem {
   double *xsT;   // [D][128]        scaled features of the tile's training rows, transposed
   double *zs;    // [mp][D]         scaled inducing inputs
-  double *M;     // [mp][SF_LD]     W (forward) or RW (backward)
-  double *KA;    // [mp][128]       Kuf tile / A' tile;  forward: afterwards A'^T [128][mp + 1]
+  double *M;     // [mp][SF_LDM]    W (forward) or RW (backward)
+  double *KA;    // [mp][SF_LDK]    Kuf tile, then A' tile
   double *ysm;   // [128]           targets of the tile
   double *us;    // [SF_MP]         u (backward)
   double *ls;    // [SF_MAX_D]      lengthscales
   double *zacc;  // [mp][D]         Z-gradient accumulators (backward)
 };
 __host__ __device__ constexpr int sf_tile_doubles(int D, int mp) {
-  return D * SF_TN + mp * D + mp * SF_LD + SF_TN * (mp + 1) + SF_TN + SF_MP + SF_MAX_D + mp * D;
+  return D * SF_TN + mp * D + mp * SF_LDM + mp * SF_LDK + SF_TN + SF_MP + SF_MAX_D + mp * D;
 }
 __device__ __forceinline__ SfTileSmem sf_tile_layout(double* smem, int D, int mp) {
   SfTileSmem t;
   t.xsT = smem;
-  t.zs = t.xsT + D * SF_TN;
-  t.M = t.zs + mp * D;
-  t.KA = t.M + mp * SF_LD;
-  t.ysm = t.KA + SF_TN * (mp + 1);
+  t.KA = t.xsT + D * SF_TN;   // (16-byte aligned: D * 128 doubles)
+  t.M = t.KA + mp * SF_LDK;
+  t.zs = t.M + mp * SF_LDM;
+  t.ysm = t.zs + mp * D;
   t.us = t.ysm + SF_TN;
   t.ls = t.us + SF_MP;
   t.zacc = t.ls + SF_MAX_D;
@@ -231,14 +334,15 @@ __device__ __forceinline__ void sf_stage_rows(const SfArgs& a, int n0, const dou
   if (tid < SF_TN) ysm[tid] = a.yv[(long)model * a.n_pad + n0 + tid];
 }
 
+constexpr int SF_AAT_SLOTS = 5;  // lower 8 x 8 tiles of A' A'^T per warp: ceil(36 / 8)
+
 template <int KID>
 __global__ void __launch_bounds__(SF_THREADS, 2) sf_forward_kernel(const SfArgs a) {
   extern __shared__ __align__(16) double smem[];
-  const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3, q4 = mp >> 2;
+  const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3, mt = mp >> 3;
   const SfTileSmem sm = sf_tile_layout(smem, D, mp);
   double *xsT = sm.xsT, *zs = sm.zs, *Wsm = sm.M, *KA = sm.KA, *ysm = sm.ysm, *ls = sm.ls;
-  const int ldt = mp + 1;  // pitch of A'^T
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int model = blockIdx.y;
   const long off = (long)model * a.bs;
   const double* theta = a.theta + off;
@@ -247,18 +351,30 @@ __global__ void __launch_bounds__(SF_THREADS, 2) sf_forward_kernel(const SfArgs 
   for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
   for (int e = tid; e < mp * mp; e += SF_THREADS) {
     const int i = e / mp, j = e - i * mp;
-    Wsm[i * SF_LD + j] = (a.W + off)[i * SF_MP + j];
+    Wsm[i * SF_LDM + j] = (a.W + off)[i * SF_MP + j];
   }
-  const int ti = tid / q4, tj = tid - ti * q4;  // A' A'^T: rows ti + q4 r, columns tj + q4 s
-  const bool aat_active = ti < q4;
-  double acc2[4][4], aeacc[8];
+  // lower tiles (it >= jt) of A' A'^T owned by this warp: t = warp, warp + 8, ...
+  int tit[SF_AAT_SLOTS], tjt[SF_AAT_SLOTS];
 #pragma unroll
-  for (int r = 0; r < 4; r++)
+  for (int sl = 0; sl < SF_AAT_SLOTS; sl++) {
+    const int t = warp + 8 * sl;
+    int it = -1, jt = 0;
+    if (t < mt * (mt + 1) / 2) {
+      it = 0;
+      while ((it + 1) * (it + 2) / 2 <= t) it++;
+      jt = t - it * (it + 1) / 2;
+    }
+    tit[sl] = it, tjt[sl] = jt;
+  }
+  double acc2[SF_AAT_SLOTS][2];
 #pragma unroll
-    for (int s = 0; s < 4; s++) acc2[r][s] = 0.0;
-#pragma unroll
-  for (int r = 0; r < 8; r++) aeacc[r] = 0.0;
+  for (int sl = 0; sl < SF_AAT_SLOTS; sl++) acc2[sl][0] = acc2[sl][1] = 0.0;
+  double aeacc = 0.0;
   double* Apg = a.Ap + off;
+  double* Kvg = a.Kv + off;
+  double* Fvg = a.Fv + off;
+  const bool row_warp = warp < mt;
+  const int irow = 8 * warp + g;  // this lane's row of the M-row tile in the DMMA accumulator layout
 
   for (int t = 0; t < a.tpc; t++) {
     const int tile = blockIdx.x * a.tpc + t;
@@ -267,7 +383,8 @@ __global__ void __launch_bounds__(SF_THREADS, 2) sf_forward_kernel(const SfArgs 
     __syncthreads();  // (first pass: ls, zs, W are in place; later: the previous tile's reads of KA are done)
     sf_stage_rows(a, n0, ls, xsT, ysm, model);
     __syncthreads();
-    // Kuf entries of this thread: rows warp + 8 r, columns lane + 32 s
+    // Kuf entries of this thread: rows warp + 8 r, columns lane + 32 s; k / variance and the derivative factor are kept for
+    // the backward pass
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       if (r < na) {
@@ -283,76 +400,71 @@ __global__ void __launch_bounds__(SF_THREADS, 2) sf_forward_kernel(const SfArgs 
         }
 #pragma unroll
         for (int s = 0; s < 4; s++) {
-          double k = variance * kernel_value<KID>(r2[s]);
-          if (i >= m || n0 + lane + 32 * s >= a.n) k = 0.0;
-          KA[i * SF_TN + lane + 32 * s] = k;
+          const int c = lane + 32 * s;
+          double kval, fval;
+          kernel_eval<KID>(r2[s], kval, fval);
+          Kvg[(long)i * a.n_pad + n0 + c] = kval;
+          Fvg[(long)i * a.n_pad + n0 + c] = fval;
+          KA[i * SF_LDK + c] = (i >= m || n0 + c >= a.n) ? 0.0 : variance * kval;
         }
       }
     }
     __syncthreads();
-    double acc[8][4];
+    // A' = W Kuf: W is lower triangular, so rows [8w, 8w + 8) need k < 8w + 8 only
+    double acc[16][2];
 #pragma unroll
-    for (int r = 0; r < 8; r++)
+    for (int ct = 0; ct < 16; ct++) acc[ct][0] = acc[ct][1] = 0.0;
+    if (row_warp) {
+      const int kend = 2 * (warp + 1);
+      for (int k4 = 0; k4 < kend; k4++) {
+        const double av = Wsm[irow * SF_LDM + 4 * k4 + q];
+        const double* bp = KA + (4 * k4 + q) * SF_LDK + g;
 #pragma unroll
-      for (int s = 0; s < 4; s++) acc[r][s] = 0.0;
-    for (int k = 0; k < mp; k++) {
-      double kv[4];
+        for (int ct = 0; ct < 16; ct++) dmma(acc[ct][0], acc[ct][1], av, bp[8 * ct]);
+      }
+      double sy = 0.0;
 #pragma unroll
-      for (int s = 0; s < 4; s++) kv[s] = KA[k * SF_TN + lane + 32 * s];
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-        if (r < na) {
-          const double w = Wsm[(warp + 8 * r) * SF_LD + k];
-#pragma unroll
-          for (int s = 0; s < 4; s++) acc[r][s] = fma(w, kv[s], acc[r][s]);
-        }
+      for (int ct = 0; ct < 16; ct++) {
+        const int c = 8 * ct + 2 * q;
+        *reinterpret_cast<double2*>(Apg + (long)irow * a.n_pad + n0 + c) = make_double2(acc[ct][0], acc[ct][1]);
+        sy = fma(acc[ct][0], ysm[c], sy);
+        sy = fma(acc[ct][1], ysm[c + 1], sy);
+      }
+      sy += __shfl_xor_sync(0xffffffffu, sy, 1);
+      sy += __shfl_xor_sync(0xffffffffu, sy, 2);
+      aeacc += sy;
     }
+    __syncthreads();  // every read of the Kuf tile is done: the buffer becomes the A' tile
+    if (row_warp) {
 #pragma unroll
-    for (int r = 0; r < 8; r++)
-      if (r < na) {
-        const int i = warp + 8 * r;
-        double sy = 0.0;
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-          Apg[(long)i * a.n_pad + n0 + lane + 32 * s] = acc[r][s];
-          sy = fma(acc[r][s], ysm[lane + 32 * s], sy);
-        }
-        aeacc[r] += warp_sum(sy);
-      }
-    __syncthreads();  // every read of the Kuf tile is done: the buffer becomes A'^T
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-      if (r < na) {
-#pragma unroll
-        for (int s = 0; s < 4; s++) KA[(lane + 32 * s) * ldt + warp + 8 * r] = acc[r][s];
-      }
+      for (int ct = 0; ct < 16; ct++)
+        *reinterpret_cast<double2*>(KA + irow * SF_LDK + 8 * ct + 2 * q) = make_double2(acc[ct][0], acc[ct][1]);
+    }
     __syncthreads();
-    if (aat_active) {
-      for (int k = 0; k < SF_TN; k++) {
-        double ai[4], aj[4];
 #pragma unroll
-        for (int r = 0; r < 4; r++) ai[r] = KA[k * ldt + ti + q4 * r];
-#pragma unroll
-        for (int s = 0; s < 4; s++) aj[s] = KA[k * ldt + tj + q4 * s];
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-          for (int s = 0; s < 4; s++) acc2[r][s] = fma(ai[r], aj[s], acc2[r][s]);
+    for (int sl = 0; sl < SF_AAT_SLOTS; sl++) {
+      if (tit[sl] >= 0) {
+        const double* ap = KA + (8 * tit[sl] + g) * SF_LDK + q;
+        const double* bp = KA + (8 * tjt[sl] + g) * SF_LDK + q;
+#pragma unroll 8
+        for (int k4 = 0; k4 < SF_TN / 4; k4++) dmma(acc2[sl][0], acc2[sl][1], ap[4 * k4], bp[4 * k4]);
       }
     }
   }
-  double* slab = a.slabs + off + (long)blockIdx.x * SF_MP * SF_MP;
-  if (aat_active) {
+  double* slab = a.slabs + off + (long)blockIdx.x * SF_MP * SF_MP;  // compact mp x mp, both triangles
 #pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int s = 0; s < 4; s++) slab[(ti + q4 * r) * SF_MP + tj + q4 * s] = acc2[r][s];
+  for (int sl = 0; sl < SF_AAT_SLOTS; sl++) {
+    if (tit[sl] >= 0) {
+      const int i = 8 * tit[sl] + g, j = 8 * tjt[sl] + 2 * q;
+      slab[i * mp + j] = acc2[sl][0];
+      slab[i * mp + j + 1] = acc2[sl][1];
+      if (tit[sl] != tjt[sl]) {
+        slab[j * mp + i] = acc2[sl][0];
+        slab[(j + 1) * mp + i] = acc2[sl][1];
+      }
+    }
   }
-  if (lane == 0) {
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-      if (r < na) (a.aep + off)[(long)blockIdx.x * SF_MP + warp + 8 * r] = aeacc[r];
-  }
+  if (row_warp && q == 0) (a.aep + off)[(long)blockIdx.x * SF_MP + irow] = aeacc;
 }
 
 // ---- 3. per model: everything M x M between the two passes -------------------------------------------------------------
@@ -384,14 +496,32 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
   int* info = a.info + off * 2;
 
   for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
-  for (int e = tid; e < mp * mp; e += SF_THREADS) {
-    const int i = e / mp, j = e - i * mp;
-    SW[i * SF_LD + j] = (a.W + off)[i * SF_MP + j];
-    double s = 0.0;
-    for (int t = 0; t < a.nct; t++) s += (a.slabs + off)[(long)t * SF_MP * SF_MP + i * SF_MP + j];
-    s /= s2;
-    SA[i * SF_LD + j] = s;
-    SB[i * SF_LD + j] = s + (i == j ? 1.0 : 0.0);
+  {
+    // AATs = (sum of the forward pass's partial matrices, in order) / s2: 16 entries per thread, all their loads of one
+    // partial in flight together
+    double sacc[SF_MP * SF_MP / SF_THREADS];
+#pragma unroll
+    for (int qq = 0; qq < SF_MP * SF_MP / SF_THREADS; qq++) sacc[qq] = 0.0;
+    const double* sp = a.slabs + off;
+#pragma unroll 2
+    for (int t = 0; t < a.nct; t++) {
+#pragma unroll
+      for (int qq = 0; qq < SF_MP * SF_MP / SF_THREADS; qq++) {
+        const int e = tid + SF_THREADS * qq;
+        if (e < mp * mp) sacc[qq] += sp[(long)t * SF_MP * SF_MP + e];
+      }
+    }
+#pragma unroll
+    for (int qq = 0; qq < SF_MP * SF_MP / SF_THREADS; qq++) {
+      const int e = tid + SF_THREADS * qq;
+      if (e < mp * mp) {
+        const int i = e / mp, j = e - i * mp;
+        const double sv = sacc[qq] / s2;
+        SW[i * SF_LD + j] = (a.W + off)[i * SF_MP + j];
+        SA[i * SF_LD + j] = sv;
+        SB[i * SF_LD + j] = sv + (i == j ? 1.0 : 0.0);
+      }
+    }
   }
   if (tid < mp) {
     double s = 0.0;
@@ -400,7 +530,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
   }
   // LB = chol(B), WB = LB^-1 (into SB), log det
   sf_chol(SB, SL, rs, mp, info);
-  sf_trinv(SL, SB, mp);
+  sf_trinv(SL, rs, SB, mp);
   if (tid < 64) {
     double lg = tid < mp ? -log(rs[tid]) : 0.0;
     lg = warp_sum(lg);
@@ -525,11 +655,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
 template <int KID>
 __global__ void __launch_bounds__(SF_THREADS, 2) sf_backward_kernel(const SfArgs a) {
   extern __shared__ __align__(16) double smem[];
-  const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3;
+  const int D = a.D, m = a.m, mp = a.mp, mt = mp >> 3;
   const SfTileSmem sm = sf_tile_layout(smem, D, mp);
   double *xsT = sm.xsT, *zs = sm.zs, *RWs = sm.M, *KA = sm.KA, *ysm = sm.ysm, *us = sm.us, *ls = sm.ls, *zacc = sm.zacc;
   __shared__ double glw[8][SF_MAX_D + 1];  // per warp: variance term, lengthscale terms
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int model = blockIdx.y;
   const long off = (long)model * a.bs;
   const double* theta = a.theta + off;
@@ -539,11 +669,15 @@ __global__ void __launch_bounds__(SF_THREADS, 2) sf_backward_kernel(const SfArgs
   for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e], zacc[e] = 0.0;
   for (int e = tid; e < mp * mp; e += SF_THREADS) {
     const int i = e / mp, j = e - i * mp;
-    RWs[i * SF_LD + j] = (a.RW + off)[i * SF_MP + j];
+    RWs[i * SF_LDM + j] = (a.RW + off)[i * SF_MP + j];
   }
   for (int e = tid; e < 8 * (SF_MAX_D + 1); e += SF_THREADS) (&glw[0][0])[e] = 0.0;
   double gvar = 0.0;
   const double* Apg = a.Ap + off;
+  const double* Kvg = a.Kv + off;
+  const double* Fvg = a.Fv + off;
+  const bool row_warp = warp < mt;
+  const int irow = 8 * warp + g;
 
   for (int t = 0; t < a.tpc; t++) {
     const int tile = blockIdx.x * a.tpc + t;
@@ -551,78 +685,59 @@ __global__ void __launch_bounds__(SF_THREADS, 2) sf_backward_kernel(const SfArgs
     const int n0 = tile * SF_TN;
     __syncthreads();
     sf_stage_rows(a, n0, ls, xsT, ysm, model);
-    for (int e = tid; e < mp * SF_TN; e += SF_THREADS) {
-      const int k = e >> 7, c = e & (SF_TN - 1);
-      KA[e] = Apg[(long)k * a.n_pad + n0 + c];
+    for (int e = tid; e < mp * (SF_TN / 2); e += SF_THREADS) {
+      const int k = e >> 6, c = 2 * (e & 63);
+      *reinterpret_cast<double2*>(KA + k * SF_LDK + c) = *reinterpret_cast<const double2*>(Apg + (long)k * a.n_pad + n0 + c);
     }
     __syncthreads();
-    // G1 = RW A'
-    double acc[8][4];
+    if (row_warp) {
+      // G1 = RW A'
+      double acc[16][2];
 #pragma unroll
-    for (int r = 0; r < 8; r++)
+      for (int ct = 0; ct < 16; ct++) acc[ct][0] = acc[ct][1] = 0.0;
+      for (int k4 = 0; k4 < (mp >> 2); k4++) {
+        const double av = RWs[irow * SF_LDM + 4 * k4 + q];
+        const double* bp = KA + (4 * k4 + q) * SF_LDK + g;
 #pragma unroll
-      for (int s = 0; s < 4; s++) acc[r][s] = 0.0;
-    for (int k = 0; k < mp; k++) {
-      double kv[4];
-#pragma unroll
-      for (int s = 0; s < 4; s++) kv[s] = KA[k * SF_TN + lane + 32 * s];
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-        if (r < na) {
-          const double w = RWs[(warp + 8 * r) * SF_LD + k];
-#pragma unroll
-          for (int s = 0; s < 4; s++) acc[r][s] = fma(w, kv[s], acc[r][s]);
-        }
-    }
-    // g = (G1 + u y^T) / s2 ; acc <- g * F ; variance term
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-      if (r < na) {
-        const int i = warp + 8 * r;
-        const double ui = us[i];
-        double r2[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int dd = 0; dd < D; dd++) {
-          const double zi = zs[i * D + dd];
-#pragma unroll
-          for (int s = 0; s < 4; s++) {
-            const double df = zi - xsT[dd * SF_TN + lane + 32 * s];
-            r2[s] = fma(df, df, r2[s]);
-          }
-        }
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-          const int c = lane + 32 * s;
-          const double g = (i < m && n0 + c < a.n) ? fma(ui, ysm[c], acc[r][s]) * inv_s2 : 0.0;
-          double kval, fval;
-          kernel_eval<KID>(r2[s], kval, fval);
-          gvar = fma(g, kval, gvar);
-          acc[r][s] = g * fval;
-        }
+        for (int ct = 0; ct < 16; ct++) dmma(acc[ct][0], acc[ct][1], av, bp[8 * ct]);
       }
-    // lengthscale and Z terms
-    for (int dd = 0; dd < D; dd++) {
-      double xv[4];
+      // g = (G1 + u y^T) / s2 ; acc <- g * F ; variance term   (k / variance and F were stored by the forward pass)
+      const double ui = us[irow];
+      const double* kp = Kvg + (long)irow * a.n_pad + n0 + 2 * q;
+      const double* fp = Fvg + (long)irow * a.n_pad + n0 + 2 * q;
 #pragma unroll
-      for (int s = 0; s < 4; s++) xv[s] = xsT[dd * SF_TN + lane + 32 * s];
-      double sl = 0.0;
+      for (int ct = 0; ct < 16; ct++) {
+        const int c = 8 * ct + 2 * q;
+        const double2 kv = *reinterpret_cast<const double2*>(kp + 8 * ct);
+        const double2 fv = *reinterpret_cast<const double2*>(fp + 8 * ct);
+        const double g0 = (irow < m && n0 + c < a.n) ? fma(ui, ysm[c], acc[ct][0]) * inv_s2 : 0.0;
+        const double g1 = (irow < m && n0 + c + 1 < a.n) ? fma(ui, ysm[c + 1], acc[ct][1]) * inv_s2 : 0.0;
+        gvar = fma(g0, kv.x, gvar);
+        gvar = fma(g1, kv.y, gvar);
+        acc[ct][0] = g0 * fv.x;
+        acc[ct][1] = g1 * fv.y;
+      }
+      // lengthscale and Z terms
+      for (int dd = 0; dd < D; dd++) {
+        const double zi = zs[irow * D + dd];
+        const double* xp = xsT + dd * SF_TN + 2 * q;
+        double zr = 0.0, sl = 0.0;
 #pragma unroll
-      for (int r = 0; r < 8; r++)
-        if (r < na) {
-          const int i = warp + 8 * r;
-          const double zi = zs[i * D + dd];
-          double zr = 0.0;
-#pragma unroll
-          for (int s = 0; s < 4; s++) {
-            const double df = zi - xv[s];
-            const double wd = acc[r][s] * df;
-            zr += wd;
-            sl = fma(wd, df, sl);
-          }
-          zr = warp_sum(zr);
-          if (lane == 0) zacc[i * D + dd] += zr;  // row i belongs to this warp alone
+        for (int ct = 0; ct < 16; ct++) {
+          const double2 xv = *reinterpret_cast<const double2*>(xp + 8 * ct);
+          const double d0 = zi - xv.x, d1 = zi - xv.y;
+          const double w0 = acc[ct][0] * d0, w1 = acc[ct][1] * d1;
+          zr += w0;
+          zr += w1;
+          sl = fma(w0, d0, sl);
+          sl = fma(w1, d1, sl);
         }
-      sl = warp_sum(sl);
-      if (lane == 0) glw[warp][1 + dd] += sl;
+        zr += __shfl_xor_sync(0xffffffffu, zr, 1);
+        zr += __shfl_xor_sync(0xffffffffu, zr, 2);
+        if (q == 0) zacc[irow * D + dd] += zr;  // row irow belongs to this warp alone
+        sl = warp_sum(sl);
+        if (lane == 0) glw[warp][1 + dd] += sl;
+      }
     }
   }
   gvar = warp_sum(gvar);
