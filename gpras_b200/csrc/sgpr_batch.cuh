@@ -379,10 +379,11 @@ int sf_launch_t(gpras_sgpr_batch* h, const SfArgs& a) {
   }
   const int tile_smem = sf_tile_doubles(a.D, a.mp) * (int)sizeof(double);
   sf_prep_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a);
-  sf_forward_kernel<KID><<<dim3(a.nct, P), SF_THREADS, tile_smem, s>>>(a);
+  sf_forward_kernel<KID><<<dim3(a.ntn, P), SF_THREADS, tile_smem, s>>>(a);
+  sf_reduce_kernel<<<dim3((a.mp * a.mp + a.mp + SF_THREADS - 1) / SF_THREADS, P), SF_THREADS, 0, s>>>(a);
   sf_mid_kernel<KID><<<dim3(1, P), SF_THREADS, sf_mid_smem(a.D), s>>>(a);
-  sf_backward_kernel<KID><<<dim3(a.nct, P), SF_THREADS, tile_smem, s>>>(a);
-  h->launches += 4;
+  sf_backward_kernel<KID><<<dim3(a.ntn, P), SF_THREADS, tile_smem, s>>>(a);
+  h->launches += 5;
   CU(cudaGetLastError());
   return 0;
 }
@@ -401,7 +402,7 @@ int sf_record_eval(gpras_sgpr_batch* h, double jitter) {
     default: return fail(GPRAS_E_ARG, "unknown kernel id");
   }
   if (r) return r;
-  sgpr_finalize_kernel<<<dim3(8, h->p), 256, 0, h->stream>>>(a.scal, a.logdetB, 1, a.partA, a.nct, a.partB, 1, 1 + a.D, a.zpA, a.nct,
+  sgpr_finalize_kernel<<<dim3(8, h->p), 256, 0, h->stream>>>(a.scal, a.logdetB, 1, a.partA, a.ntn, a.partB, 1, 1 + a.D, a.zpA, a.ntn,
                                                            a.zpB, 1, a.theta, a.n, a.m, SF_MP, a.D, 1, h->result, h->bs);
   h->launches++;
   CU(cudaGetLastError());
@@ -443,17 +444,14 @@ int gpras_sgpr_batch_create(gpras_sgpr_batch** out, int device, int kernel_id, i
   std::vector<Carve> parts;
   SfArgs& fa = h->fa;
   if (h->fused) {
-    // tiles of 128 training rows, grouped so that the grid is about 1.5 waves of the 148 SMs and a model has at most 32 groups
-    // (each group leaves one partial M x M matrix for the model's mid kernel to add up)
+    // one CTA per tile of 128 training rows and model; every tile leaves a partial M x M matrix that sf_reduce_kernel adds up
     fa.n = n, fa.n_pad = h->n_pad, fa.D = d, fa.m = m, fa.mp = round_up(m, 8), fa.ntn = h->ntn;
-    int tpc = (int)(((long)p * h->ntn + 111) / 222);
-    if (tpc < (h->ntn + 31) / 32) tpc = (h->ntn + 31) / 32;
-    if (tpc < 1) tpc = 1;
-    fa.tpc = tpc, fa.nct = (h->ntn + tpc - 1) / tpc;
+    const size_t nt = (size_t)h->ntn;
     parts = {{&h->theta, (size_t)2 + d}, {&h->Z, (size_t)m * d}, {&fa.Zs, (size_t)SF_MP * d}, {&fa.W, (size_t)SF_MP * SF_MP},
-             {&fa.Ap, (size_t)fa.mp * h->n_pad}, {&fa.Kv, (size_t)fa.mp * h->n_pad}, {&fa.Fv, (size_t)fa.mp * h->n_pad}, {&fa.slabs, (size_t)fa.nct * SF_MP * SF_MP}, {&fa.aep, (size_t)fa.nct * SF_MP},
+             {&fa.Ap, (size_t)fa.mp * h->n_pad}, {&fa.Kv, (size_t)fa.mp * h->n_pad}, {&fa.Fv, (size_t)fa.mp * h->n_pad},
+             {&fa.slabs, nt * SF_MP * SF_MP}, {&fa.aep, nt * SF_MP}, {&fa.aats, (size_t)SF_MP * SF_MP}, {&fa.aes, (size_t)SF_MP},
              {&fa.RW, (size_t)SF_MP * SF_MP}, {&fa.uvec, (size_t)SF_MP}, {&fa.scal, 8}, {&fa.logdetB, 1},
-             {&fa.partA, (size_t)fa.nct * (1 + d)}, {&fa.zpA, (size_t)fa.nct * SF_MP * d}, {&fa.partB, (size_t)1 + d},
+             {&fa.partA, nt * (1 + d)}, {&fa.zpA, nt * SF_MP * d}, {&fa.partB, (size_t)1 + d},
              {&fa.zpB, (size_t)SF_MP * d}, {&h->result, 3 + d + (size_t)m * d}, {&h->au, (size_t)h->nu}, {&h->amom, (size_t)h->nu},
              {&h->avel, (size_t)h->nu}, {&h->ast, (size_t)gpras::AST}};
   } else {

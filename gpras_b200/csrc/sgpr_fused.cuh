@@ -39,19 +39,21 @@ struct SfArgs {
   double* Ap;           // [mp][n_pad]
   double* Kv;           // [mp][n_pad]   k(z_i, x_n) / variance      (forward pass -> backward pass)
   double* Fv;           // [mp][n_pad]   derivative factor F / variance
-  double* slabs;        // [nct][SF_MP * SF_MP]
-  double* aep;          // [nct][SF_MP]
+  double* slabs;        // [ntn][SF_MP * SF_MP]   per tile: partial A' A'^T (compact mp x mp)
+  double* aep;          // [ntn][SF_MP]           per tile: partial A' y
+  double* aats;         // [SF_MP * SF_MP]        their sums over the tiles (sf_reduce_kernel)
+  double* aes;          // [SF_MP]
   double* RW;           // [SF_MP][SF_MP]
   double* uvec;         // [SF_MP]
   double* scal;         // [8]
   double* logdetB;      // [1]
-  double* partA;        // [nct][1 + D]
-  double* zpA;          // [nct][SF_MP][D]
+  double* partA;        // [ntn][1 + D]
+  double* zpA;          // [ntn][SF_MP][D]
   double* partB;        // [1 + D]
   double* zpB;          // [SF_MP][D]
   int* info;
   long bs;
-  int n, n_pad, D, m, mp, nct, tpc, ntn;
+  int n, n_pad, D, m, mp, ntn;
   double jitter;
 };
 
@@ -290,46 +292,38 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_prep_kernel(const SfArgs a) 
   }
 }
 
-// ---- 2. per (group of training-row tiles, model): A' = W Kuf, partial A' A'^T and A' y ---------------------------------
-// Tile kernels: 8 warps; the three products (A' = W Kuf, A' A'^T here, RW A' in the backward pass) run on the FP64 tensor
-// pipe (DMMA.8x8x4, fragment layout of common.cuh) from shared-memory operands whose pitches are == 4 (mod 16) doubles, which
-// makes every fragment load conflict free.  Warp w owns the 8 rows [8w, 8w + 8) of the M-row tile, all 128 columns.
-constexpr int SF_LDM = SF_MP + 4;   // pitch of W / RW in the tile kernels
+// ---- 2. per (tile of 128 training rows, model): A' = W Kuf, partial A' A'^T and A' y -----------------------------------
+// Tile kernels: 8 warps, one tile per CTA; the three products (A' = W Kuf, A' A'^T here, RW A' in the backward pass) run on
+// the FP64 tensor pipe (DMMA.8x8x4, fragment layout of common.cuh).  Warp w owns rows [8w, 8w + 8) of the M-row tile and all
+// 128 columns; its A fragments (8 rows of W or RW) sit in registers, the B operand (Kuf / A' tile) in shared memory with a
+// pitch == 4 (mod 16) doubles, which makes the fragment loads conflict free.
 constexpr int SF_LDK = SF_TN + 4;   // pitch of the Kuf / A' tile  [mp][128]
 
 struct SfTileSmem {
   double *xsT;   // [D][128]        scaled features of the tile's training rows, transposed
-  double *zs;    // [mp][D]         scaled inducing inputs
-  double *M;     // [mp][SF_LDM]    W (forward) or RW (backward)
   double *KA;    // [mp][SF_LDK]    Kuf tile, then A' tile
+  double *zs;    // [mp][D]         scaled inducing inputs
   double *ysm;   // [128]           targets of the tile
   double *us;    // [SF_MP]         u (backward)
-  double *ls;    // [SF_MAX_D]      lengthscales
-  double *zacc;  // [mp][D]         Z-gradient accumulators (backward)
 };
-__host__ __device__ constexpr int sf_tile_doubles(int D, int mp) {
-  return D * SF_TN + mp * D + mp * SF_LDM + mp * SF_LDK + SF_TN + SF_MP + SF_MAX_D + mp * D;
-}
+__host__ __device__ constexpr int sf_tile_doubles(int D, int mp) { return D * SF_TN + mp * SF_LDK + mp * D + SF_TN + SF_MP; }
 __device__ __forceinline__ SfTileSmem sf_tile_layout(double* smem, int D, int mp) {
   SfTileSmem t;
   t.xsT = smem;
   t.KA = t.xsT + D * SF_TN;   // (16-byte aligned: D * 128 doubles)
-  t.M = t.KA + mp * SF_LDK;
-  t.zs = t.M + mp * SF_LDM;
+  t.zs = t.KA + mp * SF_LDK;
   t.ysm = t.zs + mp * D;
   t.us = t.ysm + SF_TN;
-  t.ls = t.us + SF_MP;
-  t.zacc = t.ls + SF_MAX_D;
   return t;
 }
 
 // features of rows [n0, n0 + 128) scaled by the lengthscales, transposed: xsT[d][c]; targets of the tile
-__device__ __forceinline__ void sf_stage_rows(const SfArgs& a, int n0, const double* __restrict__ ls, double* __restrict__ xsT,
+__device__ __forceinline__ void sf_stage_rows(const SfArgs& a, int n0, const double* __restrict__ theta, double* __restrict__ xsT,
                                               double* __restrict__ ysm, int model) {
   const int tid = threadIdx.x, D = a.D;
   for (int e = tid; e < SF_TN * D; e += SF_THREADS) {
     const int c = e / D, dd = e - c * D;
-    xsT[dd * SF_TN + c] = n0 + c < a.n ? a.X[(long)(n0 + c) * D + dd] / ls[dd] : 0.0;
+    xsT[dd * SF_TN + c] = n0 + c < a.n ? a.X[(long)(n0 + c) * D + dd] / theta[2 + dd] : 0.0;
   }
   if (tid < SF_TN) ysm[tid] = a.yv[(long)model * a.n_pad + n0 + tid];
 }
@@ -341,130 +335,123 @@ __global__ void __launch_bounds__(SF_THREADS, 2) sf_forward_kernel(const SfArgs 
   extern __shared__ __align__(16) double smem[];
   const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3, mt = mp >> 3;
   const SfTileSmem sm = sf_tile_layout(smem, D, mp);
-  double *xsT = sm.xsT, *zs = sm.zs, *Wsm = sm.M, *KA = sm.KA, *ysm = sm.ysm, *ls = sm.ls;
+  double *xsT = sm.xsT, *zs = sm.zs, *KA = sm.KA, *ysm = sm.ysm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  const int model = blockIdx.y;
+  const int model = blockIdx.y, n0 = blockIdx.x * SF_TN;
   const long off = (long)model * a.bs;
   const double* theta = a.theta + off;
   const double variance = theta[0];
-  if (tid < D) ls[tid] = theta[2 + tid];
-  for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
-  for (int e = tid; e < mp * mp; e += SF_THREADS) {
-    const int i = e / mp, j = e - i * mp;
-    Wsm[i * SF_LDM + j] = (a.W + off)[i * SF_MP + j];
-  }
-  // lower tiles (it >= jt) of A' A'^T owned by this warp: t = warp, warp + 8, ...
-  int tit[SF_AAT_SLOTS], tjt[SF_AAT_SLOTS];
-#pragma unroll
-  for (int sl = 0; sl < SF_AAT_SLOTS; sl++) {
-    const int t = warp + 8 * sl;
-    int it = -1, jt = 0;
-    if (t < mt * (mt + 1) / 2) {
-      it = 0;
-      while ((it + 1) * (it + 2) / 2 <= t) it++;
-      jt = t - it * (it + 1) / 2;
-    }
-    tit[sl] = it, tjt[sl] = jt;
-  }
-  double acc2[SF_AAT_SLOTS][2];
-#pragma unroll
-  for (int sl = 0; sl < SF_AAT_SLOTS; sl++) acc2[sl][0] = acc2[sl][1] = 0.0;
-  double aeacc = 0.0;
-  double* Apg = a.Ap + off;
-  double* Kvg = a.Kv + off;
-  double* Fvg = a.Fv + off;
   const bool row_warp = warp < mt;
   const int irow = 8 * warp + g;  // this lane's row of the M-row tile in the DMMA accumulator layout
-
-  for (int t = 0; t < a.tpc; t++) {
-    const int tile = blockIdx.x * a.tpc + t;
-    if (tile >= a.ntn) break;
-    const int n0 = tile * SF_TN;
-    __syncthreads();  // (first pass: ls, zs, W are in place; later: the previous tile's reads of KA are done)
-    sf_stage_rows(a, n0, ls, xsT, ysm, model);
-    __syncthreads();
-    // Kuf entries of this thread: rows warp + 8 r, columns lane + 32 s; k / variance and the derivative factor are kept for
-    // the backward pass
+  sf_stage_rows(a, n0, theta, xsT, ysm, model);
+  for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
+  // A fragments of W for this warp's rows: W is lower triangular, so rows [8w, 8w + 8) need k < 8w + 8 only
+  double wfrag[2 * (SF_MP / 8)];
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      if (r < na) {
-        const int i = warp + 8 * r;
-        double r2[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int dd = 0; dd < D; dd++) {
-          const double zi = zs[i * D + dd];
+  for (int k4 = 0; k4 < 2 * (SF_MP / 8); k4++)
+    wfrag[k4] = (row_warp && k4 < 2 * (warp + 1)) ? (a.W + off)[irow * SF_MP + 4 * k4 + q] : 0.0;
+  __syncthreads();
+  // Kuf entries of this thread: rows warp + 8 r, columns lane + 32 s; k / variance and the derivative factor are kept for
+  // the backward pass
+  double* Kvg = a.Kv + off;
+  double* Fvg = a.Fv + off;
+#pragma unroll 1
+  for (int r = 0; r < na; r++) {
+    const int i = warp + 8 * r;
+    double r2[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int dd = 0; dd < D; dd++) {
+      const double zi = zs[i * D + dd];
 #pragma unroll
-          for (int s = 0; s < 4; s++) {
-            const double df = zi - xsT[dd * SF_TN + lane + 32 * s];
-            r2[s] = fma(df, df, r2[s]);
-          }
-        }
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-          const int c = lane + 32 * s;
-          double kval, fval;
-          kernel_eval<KID>(r2[s], kval, fval);
-          Kvg[(long)i * a.n_pad + n0 + c] = kval;
-          Fvg[(long)i * a.n_pad + n0 + c] = fval;
-          KA[i * SF_LDK + c] = (i >= m || n0 + c >= a.n) ? 0.0 : variance * kval;
-        }
+      for (int s = 0; s < 4; s++) {
+        const double df = zi - xsT[dd * SF_TN + lane + 32 * s];
+        r2[s] = fma(df, df, r2[s]);
       }
     }
-    __syncthreads();
-    // A' = W Kuf: W is lower triangular, so rows [8w, 8w + 8) need k < 8w + 8 only
-    double acc[16][2];
 #pragma unroll
-    for (int ct = 0; ct < 16; ct++) acc[ct][0] = acc[ct][1] = 0.0;
-    if (row_warp) {
-      const int kend = 2 * (warp + 1);
-      for (int k4 = 0; k4 < kend; k4++) {
-        const double av = Wsm[irow * SF_LDM + 4 * k4 + q];
+    for (int s = 0; s < 4; s++) {
+      const int c = lane + 32 * s;
+      double kval, fval;
+      kernel_eval<KID>(r2[s], kval, fval);
+      Kvg[(long)i * a.n_pad + n0 + c] = kval;
+      Fvg[(long)i * a.n_pad + n0 + c] = fval;
+      KA[i * SF_LDK + c] = (i >= m || n0 + c >= a.n) ? 0.0 : variance * kval;
+    }
+  }
+  __syncthreads();
+  double acc[16][2];
+#pragma unroll
+  for (int ct = 0; ct < 16; ct++) acc[ct][0] = acc[ct][1] = 0.0;
+  if (row_warp) {
+#pragma unroll
+    for (int k4 = 0; k4 < 2 * (SF_MP / 8); k4++) {
+      if (k4 < 2 * (warp + 1)) {
         const double* bp = KA + (4 * k4 + q) * SF_LDK + g;
 #pragma unroll
-        for (int ct = 0; ct < 16; ct++) dmma(acc[ct][0], acc[ct][1], av, bp[8 * ct]);
+        for (int ct = 0; ct < 16; ct++) dmma(acc[ct][0], acc[ct][1], wfrag[k4], bp[8 * ct]);
       }
-      double sy = 0.0;
-#pragma unroll
-      for (int ct = 0; ct < 16; ct++) {
-        const int c = 8 * ct + 2 * q;
-        *reinterpret_cast<double2*>(Apg + (long)irow * a.n_pad + n0 + c) = make_double2(acc[ct][0], acc[ct][1]);
-        sy = fma(acc[ct][0], ysm[c], sy);
-        sy = fma(acc[ct][1], ysm[c + 1], sy);
-      }
-      sy += __shfl_xor_sync(0xffffffffu, sy, 1);
-      sy += __shfl_xor_sync(0xffffffffu, sy, 2);
-      aeacc += sy;
     }
-    __syncthreads();  // every read of the Kuf tile is done: the buffer becomes the A' tile
-    if (row_warp) {
+    double* Apg = a.Ap + off + (long)irow * a.n_pad + n0;
+    double sy = 0.0;
 #pragma unroll
-      for (int ct = 0; ct < 16; ct++)
-        *reinterpret_cast<double2*>(KA + irow * SF_LDK + 8 * ct + 2 * q) = make_double2(acc[ct][0], acc[ct][1]);
+    for (int ct = 0; ct < 16; ct++) {
+      const int c = 8 * ct + 2 * q;
+      *reinterpret_cast<double2*>(Apg + c) = make_double2(acc[ct][0], acc[ct][1]);
+      sy = fma(acc[ct][0], ysm[c], sy);
+      sy = fma(acc[ct][1], ysm[c + 1], sy);
     }
-    __syncthreads();
+    sy += __shfl_xor_sync(0xffffffffu, sy, 1);
+    sy += __shfl_xor_sync(0xffffffffu, sy, 2);
+    if (q == 0) (a.aep + off)[(long)blockIdx.x * SF_MP + irow] = sy;
+  }
+  __syncthreads();  // every read of the Kuf tile is done: the buffer becomes the A' tile
+  if (row_warp) {
 #pragma unroll
-    for (int sl = 0; sl < SF_AAT_SLOTS; sl++) {
-      if (tit[sl] >= 0) {
-        const double* ap = KA + (8 * tit[sl] + g) * SF_LDK + q;
-        const double* bp = KA + (8 * tjt[sl] + g) * SF_LDK + q;
+    for (int ct = 0; ct < 16; ct++)
+      *reinterpret_cast<double2*>(KA + irow * SF_LDK + 8 * ct + 2 * q) = make_double2(acc[ct][0], acc[ct][1]);
+  }
+  __syncthreads();
+  // partial A' A'^T of this tile: lower 8 x 8 tiles t = warp, warp + 8, ...; both triangles are written (compact mp x mp)
+  double* slab = a.slabs + off + (long)blockIdx.x * SF_MP * SF_MP;
+  for (int t = warp; t < mt * (mt + 1) / 2; t += 8) {
+    int it = 0;
+    while ((it + 1) * (it + 2) / 2 <= t) it++;
+    const int jt = t - it * (it + 1) / 2;
+    const double* ap = KA + (8 * it + g) * SF_LDK + q;
+    const double* bp = KA + (8 * jt + g) * SF_LDK + q;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: even / odd k4 (shorter dependency chain)
+#pragma unroll 4
+    for (int k4 = 0; k4 < SF_TN / 4; k4 += 2) {
+      dmma(c0, c1, ap[4 * k4], bp[4 * k4]);
+      dmma(e0, e1, ap[4 * k4 + 4], bp[4 * k4 + 4]);
+    }
+    c0 += e0, c1 += e1;
+    const int i = 8 * it + g, j = 8 * jt + 2 * q;
+    slab[i * mp + j] = c0;
+    slab[i * mp + j + 1] = c1;
+    if (it != jt) {
+      slab[j * mp + i] = c0;
+      slab[(j + 1) * mp + i] = c1;
+    }
+  }
+}
+
+// sum of the tiles' partial matrices and vectors, in tile order: slabs[0] <- sum_t slabs[t], aep[0] <- sum_t aep[t]
+__global__ void __launch_bounds__(SF_THREADS) sf_reduce_kernel(const SfArgs a) {
+  const long off = (long)blockIdx.y * a.bs;
+  const int e = blockIdx.x * SF_THREADS + threadIdx.x, mm = a.mp * a.mp;
+  if (e < mm) {
+    double* sp = a.slabs + off + e;
+    double s = 0.0;
 #pragma unroll 8
-        for (int k4 = 0; k4 < SF_TN / 4; k4++) dmma(acc2[sl][0], acc2[sl][1], ap[4 * k4], bp[4 * k4]);
-      }
-    }
+    for (int t = 0; t < a.ntn; t++) s += sp[(long)t * SF_MP * SF_MP];
+    (a.aats + off)[e] = s;
+  } else if (e < mm + a.mp) {
+    double* sp = a.aep + off + (e - mm);
+    double s = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < a.ntn; t++) s += sp[(long)t * SF_MP];
+    (a.aes + off)[e - mm] = s;
   }
-  double* slab = a.slabs + off + (long)blockIdx.x * SF_MP * SF_MP;  // compact mp x mp, both triangles
-#pragma unroll
-  for (int sl = 0; sl < SF_AAT_SLOTS; sl++) {
-    if (tit[sl] >= 0) {
-      const int i = 8 * tit[sl] + g, j = 8 * tjt[sl] + 2 * q;
-      slab[i * mp + j] = acc2[sl][0];
-      slab[i * mp + j + 1] = acc2[sl][1];
-      if (tit[sl] != tjt[sl]) {
-        slab[j * mp + i] = acc2[sl][0];
-        slab[(j + 1) * mp + i] = acc2[sl][1];
-      }
-    }
-  }
-  if (row_warp && q == 0) (a.aep + off)[(long)blockIdx.x * SF_MP + irow] = aeacc;
 }
 
 // ---- 3. per model: everything M x M between the two passes -------------------------------------------------------------
@@ -496,38 +483,15 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
   int* info = a.info + off * 2;
 
   for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
-  {
-    // AATs = (sum of the forward pass's partial matrices, in order) / s2: 16 entries per thread, all their loads of one
-    // partial in flight together
-    double sacc[SF_MP * SF_MP / SF_THREADS];
-#pragma unroll
-    for (int qq = 0; qq < SF_MP * SF_MP / SF_THREADS; qq++) sacc[qq] = 0.0;
-    const double* sp = a.slabs + off;
-#pragma unroll 2
-    for (int t = 0; t < a.nct; t++) {
-#pragma unroll
-      for (int qq = 0; qq < SF_MP * SF_MP / SF_THREADS; qq++) {
-        const int e = tid + SF_THREADS * qq;
-        if (e < mp * mp) sacc[qq] += sp[(long)t * SF_MP * SF_MP + e];
-      }
-    }
-#pragma unroll
-    for (int qq = 0; qq < SF_MP * SF_MP / SF_THREADS; qq++) {
-      const int e = tid + SF_THREADS * qq;
-      if (e < mp * mp) {
-        const int i = e / mp, j = e - i * mp;
-        const double sv = sacc[qq] / s2;
-        SW[i * SF_LD + j] = (a.W + off)[i * SF_MP + j];
-        SA[i * SF_LD + j] = sv;
-        SB[i * SF_LD + j] = sv + (i == j ? 1.0 : 0.0);
-      }
-    }
+  // AATs = (sum over the tiles of A' A'^T, from sf_reduce_kernel) / s2 ;  B = I + AATs ;  ae = A' y / s2
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    const double sv = (a.aats + off)[e] / s2;
+    SW[i * SF_LD + j] = (a.W + off)[i * SF_MP + j];
+    SA[i * SF_LD + j] = sv;
+    SB[i * SF_LD + j] = sv + (i == j ? 1.0 : 0.0);
   }
-  if (tid < mp) {
-    double s = 0.0;
-    for (int t = 0; t < a.nct; t++) s += (a.aep + off)[(long)t * SF_MP + tid];
-    ae[tid] = s / s2;
-  }
+  if (tid < mp) ae[tid] = (a.aes + off)[tid] / s2;
   // LB = chol(B), WB = LB^-1 (into SB), log det
   sf_chol(SB, SL, rs, mp, info);
   sf_trinv(SL, rs, SB, mp);
@@ -598,150 +562,137 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
   __syncthreads();
   sf_mm<false, false>(SA, SB, SW, mp, 0.5);
   __syncthreads();
-  // chain rule through Kuu (g = Guu, k(z_i, z_j) depends on z_i twice): rows warp + 8 r, columns lane + 32 s
-  for (int e = tid; e < 8 * (D + 1); e += SF_THREADS) glw[e] = 0.0;
-  __syncthreads();
+  // chain rule through Kuu (g = Guu; k(z_i, z_j) depends on z_i twice).  First w = g F and the variance term, one entry
+  // per thread at a time (w -> SB, T1 is dead); then one thread per (row, feature) pair sums over the columns.
   double gvar = 0.0;
-  for (int r = 0; r < na; r++) {
-    const int i = warp + 8 * r;
-    double w[2], zj[2];
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      const int j = lane + 32 * s;
-      double r2 = 0.0;
-      if (j < mp)
-        for (int dd = 0; dd < D; dd++) {
-          const double df = zs[i * D + dd] - zs[j * D + dd];
-          r2 = fma(df, df, r2);
-        }
-      const double g = (i < m && j < m) ? SA[i * SF_LD + j] : 0.0;
-      double kval, fval;
-      kernel_eval<KID>(r2, kval, fval);
-      gvar = fma(g, kval, gvar);
-      w[s] = g * fval;
-    }
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    double r2 = 0.0;
     for (int dd = 0; dd < D; dd++) {
-      const double zi = zs[i * D + dd];
-      double zr = 0.0, sl = 0.0;
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const int j = lane + 32 * s;
-        zj[s] = j < mp ? zs[j * D + dd] : zi;
-        const double df = zi - zj[s];
-        const double wd = w[s] * df;
-        zr += wd;
-        sl = fma(wd, df, sl);
-      }
-      zr = warp_sum(zr);
-      sl = warp_sum(sl);
-      if (lane == 0) {
-        (a.zpB + off)[i * D + dd] = 2.0 * zr;
-        glw[warp * (D + 1) + 1 + dd] += sl;
-      }
+      const double df = zs[i * D + dd] - zs[j * D + dd];
+      r2 = fma(df, df, r2);
     }
+    const double g = (i < m && j < m) ? SA[i * SF_LD + j] : 0.0;
+    double kval, fval;
+    kernel_eval<KID>(r2, kval, fval);
+    gvar = fma(g, kval, gvar);
+    SB[i * SF_LD + j] = g * fval;
   }
-  gvar = warp_sum(gvar);
-  if (lane == 0) glw[warp * (D + 1)] = gvar;
+  {
+    double v[1] = {gvar};
+    sf_block_sum<1>(v, red);  // (its leading barrier also publishes w)
+    gvar = v[0];
+  }
+  double* slp = SL;  // [mp][D] partial lengthscale terms per row (RW has been stored)
+  for (int pr = tid; pr < mp * D; pr += SF_THREADS) {
+    const int i = pr / D, dd = pr - i * D;
+    const double zi = zs[pr];
+    double zr = 0.0, sl = 0.0;
+    for (int j = 0; j < mp; j++) {
+      const double df = zi - zs[j * D + dd];
+      const double wd = SB[i * SF_LD + j] * df;
+      zr += wd;
+      sl = fma(wd, df, sl);
+    }
+    (a.zpB + off)[pr] = 2.0 * zr;
+    slp[pr] = sl;
+  }
   __syncthreads();
-  if (tid < 1 + D) {
-    double s = 0.0;
-#pragma unroll
-    for (int wv = 0; wv < 8; wv++) s += glw[wv * (D + 1) + tid];
-    (a.partB + off)[tid] = s;
+  if (tid == 0) (a.partB + off)[0] = gvar;
+  if (tid >= 1 && tid < 1 + D) {
+    double sacc = 0.0;
+    for (int i = 0; i < mp; i++) sacc += slp[i * D + tid - 1];
+    (a.partB + off)[tid] = sacc;
   }
 }
 
-// ---- 4. per (group of tiles, model): chain rule through Kuf ------------------------------------------------------------
+// ---- 4. per (tile, model): chain rule through Kuf ----------------------------------------------------------------------
 template <int KID>
 __global__ void __launch_bounds__(SF_THREADS, 2) sf_backward_kernel(const SfArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int D = a.D, m = a.m, mp = a.mp, mt = mp >> 3;
   const SfTileSmem sm = sf_tile_layout(smem, D, mp);
-  double *xsT = sm.xsT, *zs = sm.zs, *RWs = sm.M, *KA = sm.KA, *ysm = sm.ysm, *us = sm.us, *ls = sm.ls, *zacc = sm.zacc;
+  double *xsT = sm.xsT, *zs = sm.zs, *KA = sm.KA, *ysm = sm.ysm, *us = sm.us;
   __shared__ double glw[8][SF_MAX_D + 1];  // per warp: variance term, lengthscale terms
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  const int model = blockIdx.y;
+  const int model = blockIdx.y, n0 = blockIdx.x * SF_TN;
   const long off = (long)model * a.bs;
   const double* theta = a.theta + off;
   const double inv_s2 = 1.0 / theta[1];
-  if (tid < D) ls[tid] = theta[2 + tid];
-  if (tid < mp) us[tid] = (a.uvec + off)[tid];
-  for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e], zacc[e] = 0.0;
-  for (int e = tid; e < mp * mp; e += SF_THREADS) {
-    const int i = e / mp, j = e - i * mp;
-    RWs[i * SF_LDM + j] = (a.RW + off)[i * SF_MP + j];
-  }
-  for (int e = tid; e < 8 * (SF_MAX_D + 1); e += SF_THREADS) (&glw[0][0])[e] = 0.0;
-  double gvar = 0.0;
-  const double* Apg = a.Ap + off;
-  const double* Kvg = a.Kv + off;
-  const double* Fvg = a.Fv + off;
   const bool row_warp = warp < mt;
   const int irow = 8 * warp + g;
-
-  for (int t = 0; t < a.tpc; t++) {
-    const int tile = blockIdx.x * a.tpc + t;
-    if (tile >= a.ntn) break;
-    const int n0 = tile * SF_TN;
-    __syncthreads();
-    sf_stage_rows(a, n0, ls, xsT, ysm, model);
+  // A fragments of RW (full) for this warp's rows
+  double rfrag[2 * (SF_MP / 8)];
+#pragma unroll
+  for (int k4 = 0; k4 < 2 * (SF_MP / 8); k4++)
+    rfrag[k4] = (row_warp && 4 * k4 < mp) ? (a.RW + off)[irow * SF_MP + 4 * k4 + q] : 0.0;
+  {
+    const double* Apg = a.Ap + off + n0;
     for (int e = tid; e < mp * (SF_TN / 2); e += SF_THREADS) {
       const int k = e >> 6, c = 2 * (e & 63);
-      *reinterpret_cast<double2*>(KA + k * SF_LDK + c) = *reinterpret_cast<const double2*>(Apg + (long)k * a.n_pad + n0 + c);
-    }
-    __syncthreads();
-    if (row_warp) {
-      // G1 = RW A'
-      double acc[16][2];
-#pragma unroll
-      for (int ct = 0; ct < 16; ct++) acc[ct][0] = acc[ct][1] = 0.0;
-      for (int k4 = 0; k4 < (mp >> 2); k4++) {
-        const double av = RWs[irow * SF_LDM + 4 * k4 + q];
-        const double* bp = KA + (4 * k4 + q) * SF_LDK + g;
-#pragma unroll
-        for (int ct = 0; ct < 16; ct++) dmma(acc[ct][0], acc[ct][1], av, bp[8 * ct]);
-      }
-      // g = (G1 + u y^T) / s2 ; acc <- g * F ; variance term   (k / variance and F were stored by the forward pass)
-      const double ui = us[irow];
-      const double* kp = Kvg + (long)irow * a.n_pad + n0 + 2 * q;
-      const double* fp = Fvg + (long)irow * a.n_pad + n0 + 2 * q;
-#pragma unroll
-      for (int ct = 0; ct < 16; ct++) {
-        const int c = 8 * ct + 2 * q;
-        const double2 kv = *reinterpret_cast<const double2*>(kp + 8 * ct);
-        const double2 fv = *reinterpret_cast<const double2*>(fp + 8 * ct);
-        const double g0 = (irow < m && n0 + c < a.n) ? fma(ui, ysm[c], acc[ct][0]) * inv_s2 : 0.0;
-        const double g1 = (irow < m && n0 + c + 1 < a.n) ? fma(ui, ysm[c + 1], acc[ct][1]) * inv_s2 : 0.0;
-        gvar = fma(g0, kv.x, gvar);
-        gvar = fma(g1, kv.y, gvar);
-        acc[ct][0] = g0 * fv.x;
-        acc[ct][1] = g1 * fv.y;
-      }
-      // lengthscale and Z terms
-      for (int dd = 0; dd < D; dd++) {
-        const double zi = zs[irow * D + dd];
-        const double* xp = xsT + dd * SF_TN + 2 * q;
-        double zr = 0.0, sl = 0.0;
-#pragma unroll
-        for (int ct = 0; ct < 16; ct++) {
-          const double2 xv = *reinterpret_cast<const double2*>(xp + 8 * ct);
-          const double d0 = zi - xv.x, d1 = zi - xv.y;
-          const double w0 = acc[ct][0] * d0, w1 = acc[ct][1] * d1;
-          zr += w0;
-          zr += w1;
-          sl = fma(w0, d0, sl);
-          sl = fma(w1, d1, sl);
-        }
-        zr += __shfl_xor_sync(0xffffffffu, zr, 1);
-        zr += __shfl_xor_sync(0xffffffffu, zr, 2);
-        if (q == 0) zacc[irow * D + dd] += zr;  // row irow belongs to this warp alone
-        sl = warp_sum(sl);
-        if (lane == 0) glw[warp][1 + dd] += sl;
-      }
+      *reinterpret_cast<double2*>(KA + k * SF_LDK + c) = *reinterpret_cast<const double2*>(Apg + (long)k * a.n_pad + c);
     }
   }
-  gvar = warp_sum(gvar);
-  if (lane == 0) glw[warp][0] = gvar;
+  sf_stage_rows(a, n0, theta, xsT, ysm, model);
+  if (tid < mp) us[tid] = (a.uvec + off)[tid];
+  for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
+  for (int e = tid; e < 8 * (SF_MAX_D + 1); e += SF_THREADS) (&glw[0][0])[e] = 0.0;
+  double* zp = a.zpA + off + (long)blockIdx.x * SF_MP * D;
+  __syncthreads();
+  if (row_warp) {
+    // G1 = RW A'
+    double acc[16][2];
+#pragma unroll
+    for (int ct = 0; ct < 16; ct++) acc[ct][0] = acc[ct][1] = 0.0;
+#pragma unroll
+    for (int k4 = 0; k4 < 2 * (SF_MP / 8); k4++) {
+      if (4 * k4 < mp) {
+        const double* bp = KA + (4 * k4 + q) * SF_LDK + g;
+#pragma unroll
+        for (int ct = 0; ct < 16; ct++) dmma(acc[ct][0], acc[ct][1], rfrag[k4], bp[8 * ct]);
+      }
+    }
+    // g = (G1 + u y^T) / s2 ; acc <- g * F ; variance term   (k / variance and F were stored by the forward pass)
+    const double ui = us[irow];
+    const double* kp = a.Kv + off + (long)irow * a.n_pad + n0 + 2 * q;
+    const double* fp = a.Fv + off + (long)irow * a.n_pad + n0 + 2 * q;
+    double gvar = 0.0;
+#pragma unroll
+    for (int ct = 0; ct < 16; ct++) {
+      const int c = 8 * ct + 2 * q;
+      const double2 kv = *reinterpret_cast<const double2*>(kp + 8 * ct);
+      const double2 fv = *reinterpret_cast<const double2*>(fp + 8 * ct);
+      const double g0 = (irow < m && n0 + c < a.n) ? fma(ui, ysm[c], acc[ct][0]) * inv_s2 : 0.0;
+      const double g1 = (irow < m && n0 + c + 1 < a.n) ? fma(ui, ysm[c + 1], acc[ct][1]) * inv_s2 : 0.0;
+      gvar = fma(g0, kv.x, gvar);
+      gvar = fma(g1, kv.y, gvar);
+      acc[ct][0] = g0 * fv.x;
+      acc[ct][1] = g1 * fv.y;
+    }
+    gvar = warp_sum(gvar);
+    if (lane == 0) glw[warp][0] = gvar;
+    // lengthscale and Z terms
+    for (int dd = 0; dd < D; dd++) {
+      const double zi = zs[irow * D + dd];
+      const double* xp = xsT + dd * SF_TN + 2 * q;
+      double zr = 0.0, sl = 0.0;
+#pragma unroll
+      for (int ct = 0; ct < 16; ct++) {
+        const double2 xv = *reinterpret_cast<const double2*>(xp + 8 * ct);
+        const double d0 = zi - xv.x, d1 = zi - xv.y;
+        const double w0 = acc[ct][0] * d0, w1 = acc[ct][1] * d1;
+        zr += w0;
+        zr += w1;
+        sl = fma(w0, d0, sl);
+        sl = fma(w1, d1, sl);
+      }
+      zr += __shfl_xor_sync(0xffffffffu, zr, 1);
+      zr += __shfl_xor_sync(0xffffffffu, zr, 2);
+      if (q == 0) zp[irow * D + dd] = zr;  // row irow belongs to this warp alone
+      sl = warp_sum(sl);
+      if (lane == 0) glw[warp][1 + dd] = sl;
+    }
+  }
   __syncthreads();
   if (tid < 1 + D) {
     double s = 0.0;
@@ -749,8 +700,6 @@ __global__ void __launch_bounds__(SF_THREADS, 2) sf_backward_kernel(const SfArgs
     for (int wv = 0; wv < 8; wv++) s += glw[wv][tid];
     (a.partA + off)[(long)blockIdx.x * (1 + D) + tid] = s;
   }
-  double* zp = a.zpA + off + (long)blockIdx.x * SF_MP * D;
-  for (int e = tid; e < mp * D; e += SF_THREADS) zp[e] = zacc[e];
 }
 
 }  // namespace gpras
