@@ -4,7 +4,12 @@ Test infrastructure only (see ``oracle/__init__.py``).  PARITY UNPINNED: GPflow 
 un-vendored, un-pinned dependency of the reference (``pyproject.toml:17``) and cannot be installed
 here; this file restates its published algorithm (``gpflow/models/sgpr.py``: ``_common_calculation``,
 ``logdet_term``, ``quad_term``, ``elbo``, ``predict_f``) as summarised in SURVEY.md section 3.4, for
-exactly the model the reference builds at ``gpras/gpr.py:293-308``:
+exactly the model the reference builds at ``gpras/gpr.py:293-308``.  What it IS pinned to
+(``tests/test_oracle.py``): the published definition of the bound and of the predictive distribution
+(Titsias 2009, eqs. 6 and 9) evaluated densely -- N x N matrices, explicit inverses, SciPy's
+multivariate normal, scikit-learn's kernel implementations, sharing no code or algebra with this
+file -- to 1e-9, for every kernel; the exact GP's LML (itself pinned to scikit-learn) at Z = X; and
+finite differences for the gradients.  The model:
 
     one output column, zero mean function, Gaussian likelihood (variance 1.0 initially, softplus
     + 1e-6 shift), stationary kernel with softplus-constrained variance / lengthscales,

@@ -129,6 +129,48 @@ def test_sgpr_bound_below_lml_and_monotone_under_nested_z():
         prev = e
 
 
+def _sklearn_kernel(name, variance, ls):
+    """scikit-learn's implementation of the same covariance functions: independent of oracle/kernels.py and oracle/sgpr.py."""
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern
+
+    base = {"RBF": lambda: RBF(ls), "Matern12": lambda: Matern(ls, nu=0.5), "Matern32": lambda: Matern(ls, nu=1.5),
+            "Matern52": lambda: Matern(ls, nu=2.5), "Exponential": lambda: Matern(2.0 * np.asarray(ls), nu=0.5)}[name]()
+    return ConstantKernel(variance) * base
+
+
+@pytest.mark.parametrize("name,ard", [("RBF", False), ("Matern12", True), ("Matern32", False), ("Matern52", True), ("Exponential", False)])
+def test_sgpr_bound_and_prediction_match_the_published_dense_form(name, ard):
+    """Pin of the restatement to the published definition (Titsias 2009, eqs. 6 and 9; GPflow's SGPR docstring):
+
+        ELBO = log N(y | 0, Qff + s2 I) - tr(Kff - Qff) / (2 s2),      Qff = Kfu Kuu^-1 Kuf,
+        q(f*) : mean = K*u S Kuf y / s2,  cov = K** - K*u Kuu^-1 Ku* + K*u S Ku*,   S = (Kuu + Kuf Kfu / s2)^-1,
+
+    evaluated densely (N x N matrices, explicit inverses, SciPy's multivariate normal) with scikit-learn's kernels, i.e.
+    sharing no code and no algebra with ``oracle/sgpr.py``'s Cholesky form.  Kuu carries GPflow's jitter in both."""
+    import torch
+    from scipy.stats import multivariate_normal
+
+    data, z = _sgpr_setup(n=120, d=3, m=15, seed=5)
+    xs = make_gp_data(40, 3, 1, seed=9).x
+    var, noise = 1.3, 0.07
+    ls = np.array([1.1, 1.9, 0.8]) if ard else np.array([1.4])
+    k = _sklearn_kernel(name, var, ls if ard else float(ls[0]))
+    n, m = data.x.shape[0], z.shape[0]
+    kff, kuf, kuu = k(data.x), k(z, data.x), k(z) + sgpr.JITTER * np.eye(m)
+    qff = kuf.T @ np.linalg.solve(kuu, kuf)
+    dense = multivariate_normal(mean=np.zeros(n), cov=qff + noise * np.eye(n)).logpdf(data.y[:, 0]) - np.trace(kff - qff) / (2 * noise)
+    t = lambda a: torch.tensor(np.asarray(a, np.float64))  # noqa: E731
+    e = float(sgpr.elbo(name, t(data.x), t(data.y), t(z), t(var), t(ls), t(noise)))
+    assert abs(e - dense) <= 1e-9 * abs(dense)
+    sig = np.linalg.inv(kuu + kuf @ kuf.T / noise)
+    ksu = k(xs, z)
+    mean = ksu @ sig @ kuf @ data.y / noise
+    cov = k(xs) - ksu @ np.linalg.solve(kuu, ksu.T) + ksu @ sig @ ksu.T
+    om, ov = sgpr.predict_y(name, data.x, data.y, z, var, ls, noise, xs)
+    np.testing.assert_allclose(om, mean, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(ov[:, 0], np.diag(cov) + noise, rtol=1e-7)
+
+
 def test_sgpr_autograd_matches_finite_differences():
     data, z = _sgpr_setup()
     u = dict(u_var=0.3, u_ls=np.array([0.9]), u_noise=-1.0)
