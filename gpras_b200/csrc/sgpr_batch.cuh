@@ -75,11 +75,9 @@ __device__ __forceinline__ double sb_adam_update(double u, double g, double& mom
   return __dsub_rn(u, __ddiv_rn(__dmul_rn(alpha, mom), __dadd_rn(sqrt(vel), eps)));
 }
 
-// u -> theta (constrained) and Z, info = 0.  One CTA per model.
-static __global__ void sgpr_batch_unpack_kernel(const double* __restrict__ au, double* __restrict__ theta, double* __restrict__ Z,
-                                         int* __restrict__ info, int D, int m, int n_ls, int transform, double noise_floor,
-                                         long bs) {
-  au += blockIdx.x * bs, theta += blockIdx.x * bs, Z += blockIdx.x * bs, info += blockIdx.x * bs * 2;
+// u -> theta (constrained) and Z, info = 0 (pointers of one model).
+__device__ __forceinline__ void sgpr_unpack_body(const double* __restrict__ au, double* __restrict__ theta, double* __restrict__ Z,
+                                                 int* __restrict__ info, int D, int m, int n_ls, int transform, double noise_floor) {
   const int tid = threadIdx.x;
   if (tid == 0) {
     *info = 0;
@@ -90,16 +88,23 @@ static __global__ void sgpr_batch_unpack_kernel(const double* __restrict__ au, d
   for (int e = tid; e < m * D; e += blockDim.x) Z[e] = au[2 + n_ls + e];
 }
 
+// One CTA per model.
+static __global__ void sgpr_batch_unpack_kernel(const double* __restrict__ au, double* __restrict__ theta, double* __restrict__ Z,
+                                         int* __restrict__ info, int D, int m, int n_ls, int transform, double noise_floor,
+                                         long bs) {
+  const long o = blockIdx.x * bs;
+  sgpr_unpack_body(au + o, theta + o, Z + o, info + o * 2, D, m, n_ls, transform, noise_floor);
+}
+
 // One Adam step per still-active model (gpr.py:147-173; Keras Adam: lr, beta 0.9 / 0.999, eps 1e-7):
 //   loss = -(ELBO + log prior of the trainable hyperparameters), gradient w.r.t. the trainable unconstrained variables by the
 //   chain rule (result holds dELBO/dlog theta and dELBO/dZ), update, then the reference's early-stopping bookkeeping.
-// One CTA per model.
-static __global__ void sgpr_batch_adam_kernel(const double* __restrict__ result, const int* __restrict__ info,
-                                       double* __restrict__ au, double* __restrict__ amom, double* __restrict__ avel,
-                                       double* __restrict__ ast, double* __restrict__ losses, int p, int D, int m,
-                                       SgprAdamCfg cfg, long bs) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  result += b * bs, info += b * bs * 2, au += b * bs, amom += b * bs, avel += b * bs, ast += b * bs;
+// Pointers of model b; called by every thread of the model's CTA.
+__device__ __forceinline__ void sgpr_adam_body(const double* __restrict__ result, const int* __restrict__ info,
+                                               double* __restrict__ au, double* __restrict__ amom, double* __restrict__ avel,
+                                               double* __restrict__ ast, double* __restrict__ losses, int p, int b, int D, int m,
+                                               const SgprAdamCfg& cfg) {
+  const int tid = threadIdx.x;
   if (ast[2] == 0.0) return;  // stopped earlier
   __shared__ double s_alpha;
   __shared__ int s_fail;
@@ -157,6 +162,36 @@ static __global__ void sgpr_batch_adam_kernel(const double* __restrict__ result,
       au[k] = sb_adam_update(au[k], g, amom[k], avel[k], alpha);
     }
   }
+}
+
+// One CTA per model.
+static __global__ void sgpr_batch_adam_kernel(const double* __restrict__ result, const int* __restrict__ info,
+                                       double* __restrict__ au, double* __restrict__ amom, double* __restrict__ avel,
+                                       double* __restrict__ ast, double* __restrict__ losses, int p, int D, int m,
+                                       SgprAdamCfg cfg, long bs) {
+  const long o = blockIdx.x * bs;
+  sgpr_adam_body(result + o, info + o * 2, au + o, amom + o, avel + o, ast + o, losses, p, blockIdx.x, D, m, cfg);
+}
+
+// Fused path, trainer: [u -> theta, Z] + sf_prep in one launch, and [bound / gradient from the pieces] + [Adam step] in another.
+template <int KID>
+__global__ void __launch_bounds__(SF_THREADS, 1) sf_prep_train_kernel(const SfArgs a, const double* __restrict__ au, int n_ls,
+                                                                      int transform, double noise_floor) {
+  const long o = (long)blockIdx.y * a.bs;
+  sgpr_unpack_body(au + o, const_cast<double*>(a.theta) + o, const_cast<double*>(a.Z) + o, a.info + o * 2, a.D, a.m, n_ls, transform,
+                   noise_floor);
+  __syncthreads();  // theta and Z are read back from global memory by this CTA only
+  sf_prep_body<KID>(a);
+}
+
+static __global__ void __launch_bounds__(SF_THREADS) sf_finish_train_kernel(const SfArgs a, double* __restrict__ result,
+                                                                     double* __restrict__ au, double* __restrict__ amom,
+                                                                     double* __restrict__ avel, double* __restrict__ ast,
+                                                                     double* __restrict__ losses, int p, SgprAdamCfg cfg) {
+  const long o = (long)blockIdx.y * a.bs;
+  sf_finalize_body(a, result + o);
+  __syncthreads();
+  sgpr_adam_body(result + o, a.info + o * 2, au + o, amom + o, avel + o, ast + o, losses, p, blockIdx.y, a.D, a.m, cfg);
 }
 
 // start of a stage: zero moments, best = +inf, count = 0, active = 1, t = 0, failed = 0
@@ -364,49 +399,61 @@ __global__ void sf_yy_kernel(const double* __restrict__ yv, int n, long n_pad, d
 }
 
 template <int KID>
-int sf_launch_t(gpras_sgpr_batch* h, const SfArgs& a) {
+int sf_attrs_t() {
+  int r;
+  if ((r = opt_in_smem(sf_prep_kernel<KID>, 220 * 1024)) || (r = opt_in_smem(sf_prep_train_kernel<KID>, 220 * 1024)) ||
+      (r = opt_in_smem(sf_forward_kernel<KID>, 220 * 1024)) || (r = opt_in_smem(sf_mid_kernel<KID>, 220 * 1024)) ||
+      (r = opt_in_smem(sf_backward_kernel<KID>, 220 * 1024)))
+    return r;
+  return 0;
+}
+
+// shared-memory opt-in of the fused kernels of one covariance function on the current device (idempotent)
+int sf_prepare(int kid) {
+  switch (kid) {
+    case K_RBF: return sf_attrs_t<K_RBF>();
+    case K_MATERN12: return sf_attrs_t<K_MATERN12>();
+    case K_MATERN32: return sf_attrs_t<K_MATERN32>();
+    case K_MATERN52: return sf_attrs_t<K_MATERN52>();
+    case K_EXPONENTIAL: return sf_attrs_t<K_EXPONENTIAL>();
+  }
+  return fail(GPRAS_E_ARG, "unknown kernel id");
+}
+
+// cfg == nullptr: theta / Z in device memory -> result.  cfg != nullptr: one whole Adam step, u -> u (six launches).
+template <int KID>
+int sf_launch_t(gpras_sgpr_batch* h, const SfArgs& a, const SgprAdamCfg* cfg) {
   cudaStream_t s = h->stream;
   const int P = h->p;
-  static std::atomic<bool> attr_done[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_done[dev]) {
-    int r;
-    if ((r = opt_in_smem(sf_prep_kernel<KID>, 220 * 1024)) || (r = opt_in_smem(sf_forward_kernel<KID>, 220 * 1024)) ||
-        (r = opt_in_smem(sf_mid_kernel<KID>, 220 * 1024)) || (r = opt_in_smem(sf_backward_kernel<KID>, 220 * 1024)))
-      return r;
-    attr_done[dev] = true;
-  }
   const int tile_smem = sf_tile_doubles(a.D, a.mp) * (int)sizeof(double);
-  sf_prep_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a);
+  if (cfg)
+    sf_prep_train_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a, h->au, cfg->n_ls, cfg->transform, cfg->noise_floor);
+  else
+    sf_prep_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a);
   sf_forward_kernel<KID><<<dim3(a.ntn, P), SF_THREADS, tile_smem, s>>>(a);
   sf_reduce_kernel<<<dim3((a.mp * a.mp + a.mp + SF_THREADS - 1) / SF_THREADS, P), SF_THREADS, 0, s>>>(a);
   sf_mid_kernel<KID><<<dim3(1, P), SF_THREADS, sf_mid_smem(a.D), s>>>(a);
   sf_backward_kernel<KID><<<dim3(a.ntn, P), SF_THREADS, tile_smem, s>>>(a);
-  h->launches += 5;
+  if (cfg)
+    sf_finish_train_kernel<<<dim3(1, P), SF_THREADS, 0, s>>>(a, h->result, h->au, h->amom, h->avel, h->ast, h->losses, P, *cfg);
+  else
+    sf_finalize_kernel<<<dim3(1, P), SF_THREADS, 0, s>>>(a, h->result);
+  h->launches += 6;
   CU(cudaGetLastError());
   return 0;
 }
 
-// the fused evaluation: theta / Z in device memory -> result
-int sf_record_eval(gpras_sgpr_batch* h, double jitter) {
+int sf_record_eval(gpras_sgpr_batch* h, double jitter, const SgprAdamCfg* cfg = nullptr) {
   SfArgs a = h->fa;
   a.jitter = jitter;
-  int r = 0;
   switch (h->kid) {
-    case K_RBF: r = sf_launch_t<K_RBF>(h, a); break;
-    case K_MATERN12: r = sf_launch_t<K_MATERN12>(h, a); break;
-    case K_MATERN32: r = sf_launch_t<K_MATERN32>(h, a); break;
-    case K_MATERN52: r = sf_launch_t<K_MATERN52>(h, a); break;
-    case K_EXPONENTIAL: r = sf_launch_t<K_EXPONENTIAL>(h, a); break;
-    default: return fail(GPRAS_E_ARG, "unknown kernel id");
+    case K_RBF: return sf_launch_t<K_RBF>(h, a, cfg);
+    case K_MATERN12: return sf_launch_t<K_MATERN12>(h, a, cfg);
+    case K_MATERN32: return sf_launch_t<K_MATERN32>(h, a, cfg);
+    case K_MATERN52: return sf_launch_t<K_MATERN52>(h, a, cfg);
+    case K_EXPONENTIAL: return sf_launch_t<K_EXPONENTIAL>(h, a, cfg);
   }
-  if (r) return r;
-  sgpr_finalize_kernel<<<dim3(8, h->p), 256, 0, h->stream>>>(a.scal, a.logdetB, 1, a.partA, a.ntn, a.partB, 1, 1 + a.D, a.zpA, a.ntn,
-                                                           a.zpB, 1, a.theta, a.n, a.m, SF_MP, a.D, 1, h->result, h->bs);
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
+  return fail(GPRAS_E_ARG, "unknown kernel id");
 }
 
 int sb_eval(gpras_sgpr_batch* h, double jitter) { return h->fused ? sf_record_eval(h, jitter) : sb_record_eval(h, jitter); }
@@ -492,6 +539,10 @@ int gpras_sgpr_batch_create(gpras_sgpr_batch** out, int device, int kernel_id, i
     }
     CU(cudaMemsetAsync(h->Xsh, 0, sizeof(double) * h->n_pad * d, h->stream));
     CU(cudaMemsetAsync(h->yv, 0, sizeof(double) * (size_t)p * h->n_pad, h->stream));
+    if ((rc = sf_prepare(kernel_id))) {
+      gpras_sgpr_batch_destroy(h);
+      return rc;
+    }
     fa.X = h->Xsh, fa.yv = h->yv, fa.yy = h->yy, fa.theta = h->theta, fa.Z = h->Z, fa.info = h->info, fa.bs = h->bs;
   }
   CU(cudaMallocHost(&h->h_pinned, sizeof(double) * (size_t)p * (h->nu + gpras::AST)));
@@ -612,6 +663,7 @@ int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hy
   if (max_iter > 0) fill_nan_kernel<<<(unsigned)(((long)max_iter * P + 255) / 256), 256, 0, s>>>(h->losses, (long)max_iter * P);
   CU(cudaGetLastError());
   auto record_step = [&]() -> int {
+    if (h->fused) return sf_record_eval(h, jitter, &cfg);
     sgpr_batch_unpack_kernel<<<P, 128, 0, s>>>(h->au, h->theta, h->Z, h->info, D, m, n_ls, transform, noise_floor, h->bs);
     h->launches++;
     CU(cudaGetLastError());

@@ -246,7 +246,7 @@ __device__ __forceinline__ void sf_block_sum(double (&v)[NV], double* __restrict
 constexpr int sf_prep_smem(int D) { return (3 * SF_MAT + SF_MP * D + SF_MP + SF_MAX_D) * (int)sizeof(double); }
 
 template <int KID>
-__global__ void __launch_bounds__(SF_THREADS, 1) sf_prep_kernel(const SfArgs a) {
+__device__ __forceinline__ void sf_prep_body(const SfArgs& a) {
   extern __shared__ __align__(16) double smem[];
   double* SA = smem;             // Kuu
   double* SL = SA + SF_MAT;      // L
@@ -290,6 +290,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_prep_kernel(const SfArgs a) 
     const int i = e / mp, j = e - i * mp;
     Wg[i * SF_MP + j] = SWm[i * SF_LD + j];
   }
+}
+
+template <int KID>
+__global__ void __launch_bounds__(SF_THREADS, 1) sf_prep_kernel(const SfArgs a) {
+  sf_prep_body<KID>(a);
 }
 
 // ---- 2. per (tile of 128 training rows, model): A' = W Kuf, partial A' A'^T and A' y -----------------------------------
@@ -474,9 +479,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
   double* rs = uv + SF_MP;
   double* lgs = rs + SF_MP;                 // [SF_MP] scratch
   double* red = lgs + SF_MP;                // [5][256]
-  double* glw = red + 5 * SF_THREADS;       // [8][D + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3;
+  const int D = a.D, m = a.m, mp = a.mp;
   const long off = (long)blockIdx.y * a.bs;
   const double* theta = a.theta + off;
   const double s2 = theta[1];
@@ -700,6 +704,49 @@ __global__ void __launch_bounds__(SF_THREADS, 2) sf_backward_kernel(const SfArgs
     for (int wv = 0; wv < 8; wv++) s += glw[wv][tid];
     (a.partA + off)[(long)blockIdx.x * (1 + D) + tid] = s;
   }
+}
+
+// ---- 5. per model: bound and gradient from the pieces (one CTA; same formulas as sgpr_finalize_kernel) -----------------
+//   result = [elbo, dF/dlog variance, dF/dlog noise, dF/dlog l_0.., dF/dZ (m x D)]
+__device__ __forceinline__ void sf_finalize_body(const SfArgs& a, double* __restrict__ result) {
+  const int tid = threadIdx.x, D = a.D, m = a.m, n = a.n;
+  const long off = (long)blockIdx.y * a.bs;
+  const double* theta = a.theta + off;
+  const double* scal = a.scal + off;
+  const double variance = theta[0], s2 = theta[1];
+  if (tid == 0) {
+    const double ldb = (a.logdetB + off)[0];
+    const double tr_aat = scal[0], tr_binv = scal[1], cc = scal[2], yy = scal[3] / s2, caac = scal[4];
+    result[0] = -0.5 * (double)n * 1.8378770664093453 -
+                (ldb + 0.5 * (double)n * log(s2) + 0.5 * ((double)n * variance / s2 - tr_aat)) - 0.5 * (yy - cc);
+    result[2] = -0.5 * (double)n + 0.5 * ((double)m - tr_binv) + 0.5 * yy - cc + 0.5 * caac + 0.5 * (double)n * variance / s2 -
+                0.5 * tr_aat;
+  }
+  if (tid < 1 + D) {
+    const double* pa = a.partA + off + tid;
+    double s = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < a.ntn; i++) s += pa[(long)i * (1 + D)];
+    s += (a.partB + off)[tid];
+    s *= variance;
+    if (tid == 0)
+      result[1] = s - 0.5 * (double)n * variance / s2;
+    else
+      result[2 + tid] = s;
+  }
+  for (int e = tid; e < m * D; e += SF_THREADS) {
+    const int dd = e % D;
+    const double* za = a.zpA + off + e;
+    double s = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < a.ntn; t++) s += za[(long)t * SF_MP * D];
+    s += (a.zpB + off)[e];
+    result[3 + D + e] = -variance * s / theta[2 + dd];
+  }
+}
+
+static __global__ void __launch_bounds__(SF_THREADS) sf_finalize_kernel(const SfArgs a, double* __restrict__ result) {
+  sf_finalize_body(a, result + (long)blockIdx.y * a.bs);
 }
 
 }  // namespace gpras
