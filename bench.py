@@ -589,6 +589,45 @@ def run_ours(args) -> None:
         pp.close()
         del xs_
 
+    sparse_fit = None
+    if rank == 0 and leg("sparse"):
+        # The reference's DEFAULT call at the reference's own scale (gpras/gpr.py:237-275: one SGPR per column, "two-stage" =
+        # Adam 100 steps on the inducing inputs + Adam 100 steps on the hyperparameters): device-resident batched trainer vs
+        # the host-driven loops of the same device evaluation.
+        from gpras_b200 import GPRAS
+        from gpras_b200.synth import make_gp_data as _mk
+
+        ns_, ds_, ms_, ps_ = 5000, 10, 50, 10
+        sd = _mk(ns_, ds_, ps_, 0, seed=3)
+        secs, pars = {}, {}
+        for name, kw in (("device_trainer", {}), ("host_lockstep", {"device_trainer": False}), ("sequential", {"lockstep_models": False})):
+            for rep in range(2):  # first call creates handles / graphs
+                gs = GPRAS("Matern52")
+                t0 = time.perf_counter()
+                gs.fit(sd.x, sd.y, ms_, "grid", "two-stage", **kw)
+                secs[name] = time.perf_counter() - t0
+            pars[name] = np.concatenate([np.concatenate([m_.theta(), np.asarray(m_.inducing_variable.Z).ravel()]) for m_ in gs.models])
+            steps_ = sum(m_.n_evals for m_ in gs.models)
+            gs.release()
+        err = float(np.max(np.abs(pars["device_trainer"] - pars["sequential"]) / np.maximum(np.abs(pars["sequential"]), 1e-3)))
+        sparse_fit = {"workload": f"reference default fit: N={ns_}, D={ds_}, M={ms_}, {ps_} per-column SGPR models, two-stage Adam 100 + 100, "
+                                  "grid inducing inputs",
+                      "seconds": secs, "model_steps": steps_, "device_trainer_us_per_lockstep_iteration": secs["device_trainer"] / 200 * 1e6,
+                      "speedup_vs_sequential": secs["sequential"] / secs["device_trainer"],
+                      "max_rel_diff_of_fitted_parameters_vs_sequential": err, "launches_per_iteration": 6}
+        if world == 1 and not args.no_cpu_baseline:
+            import torch as _t
+
+            from oracle import sgpr as _sg
+
+            z_ = GPRAS("Matern52")._create_inducing(sd.x, ms_, "grid")
+            t0 = time.perf_counter()
+            for _ in range(3):
+                _sg.training_loss_and_grads("Matern52", sd.x, sd.y[:, :1], z_, 0.54, np.array([0.54]), 0.54)
+            sparse_fit["cpu_port_ms_per_loss_and_grad"] = (time.perf_counter() - t0) / 3 * 1e3
+            sparse_fit["cpu_port_fit_seconds_extrapolated"] = sparse_fit["cpu_port_ms_per_loss_and_grad"] * 1e-3 * steps_
+            del _t
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         dtc, cores = cpu_port_eval_seconds(data, thetas, 1, 0)
@@ -616,6 +655,7 @@ def run_ours(args) -> None:
             "cfg5_sweep": cfg5,
             "strong": strong,
             "preprocess": preprocess,
+            "sparse_fit": sparse_fit,
         }
         print(json.dumps(line), flush=True)
     for g_ in gps:
@@ -633,7 +673,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline + predict legs only (profiling runs)")
     ap.add_argument("--concurrent", type=int, default=4, help="independent evaluations in flight per GPU (throughput saturates at 4)")
-    ap.add_argument("--legs", default="all", help="comma list of extra legs to run (sustained,predict,cfg5,strong,cfg4,preprocess) or 'all'")
+    ap.add_argument("--legs", default="all", help="comma list of extra legs to run (sustained,predict,cfg5,strong,cfg4,preprocess,sparse) or 'all'")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -584,8 +584,10 @@ def _optimize_multi_start(model, n_starts: int = 40, iter_initial: int = 20, ite
     Faithful to the reference by default: its ``best_loss`` is never assigned (``gpr.py:86,96``), so the LAST
     start is the one that gets polished; ``pick_best=True`` selects the lowest coarse loss instead.  The
     reference's generator is unseeded (``gpr.py:76-77``); ``seed`` / ``starts`` ((R, 3) constrained
-    [variance, lengthscale, noise]) make runs reproducible.  ``lockstep`` (default: on for models without trainable
-    inducing inputs) advances all starts together so that their device evaluations overlap; the result is identical.
+    [variance, lengthscale, noise]) make runs reproducible.  ``lockstep`` (default on) advances all starts together: exact
+    models evaluate the starts' objectives in flight together (identical result); sparse models with at most 128 inducing
+    points put the starts into one device batch whose coarse Adam stage runs device resident (``gpras_sgpr_batch_adam``; same
+    draws, same trajectories up to the rounding of the device's transcendental functions).
     The reference overwrites ``model.inducing_variable.Z`` with a raw ndarray (``gpr.py:91,108``), which replaces the GPflow
     ``Parameter``: from the first redraw on Z is no longer a trainable variable, so Adam and the final L-BFGS move only the
     three hyperparameters.  That is the default here too; ``train_z=True`` keeps the redrawn Z trainable instead.
@@ -595,8 +597,15 @@ def _optimize_multi_start(model, n_starts: int = 40, iter_initial: int = 20, ite
     mins, maxs = x.min(axis=0), x.max(axis=0)
     best_loss, best = None, None
     if lockstep is None:
-        lockstep = hasattr(model, "loss_and_grad_many") and not _has_z(model)
-    if lockstep:
+        lockstep = (hasattr(model, "loss_and_grad_many") and not _has_z(model)) or _has_z(model)
+    if lockstep and _has_z(model):
+        # sparse model: every start becomes one model of a device batch (same draws in the same order), the coarse Adam stage
+        # runs device resident for all starts at once; None when the model does not qualify (then the loop below runs)
+        from .sparse import multi_start_device
+
+        best = multi_start_device(model, rng, int(n_starts), int(iter_initial), starts, pick_best, bool(train_z))
+        lockstep = best is not None
+    elif lockstep:
         best = _multi_start_lockstep(model, rng, int(n_starts), int(iter_initial), starts, pick_best)
     for r in range(0 if lockstep else int(n_starts)):
         if starts is not None:

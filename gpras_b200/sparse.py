@@ -38,6 +38,7 @@ def release_other_threads() -> None:
 
 class SparseModel:
     supports_z_training = True
+    device_batch = True  # may join a device batch (``SparseBatch``); test doubles that replace the device evaluation say False
 
     def __init__(self, kernel_name, x, y, z, lengthscales, device: int = 0, priors: bool = True,
                  parameterisation: str = "softplus"):
@@ -253,7 +254,7 @@ def _device_batch(models):
     from .engine import SparseBatch
 
     m0 = models[0]
-    if not all(isinstance(mdl, SparseModel) for mdl in models):
+    if not all(isinstance(mdl, SparseModel) and mdl.device_batch for mdl in models):
         return None
     m, d = m0.inducing_variable.Z.shape
     cfg0 = _trainer_config(m0)
@@ -313,6 +314,70 @@ def adam_device(models, batch, max_iter: int, learning_rate: float = 0.001) -> b
         mdl.n_evals += int(iters[b])
         mdl.adam_losses = losses[: int(iters[b]), b].copy()
     return True
+
+
+def multi_start_device(model, rng, n_starts: int, iter_initial: int, starts, pick_best: bool, train_z: bool):
+    """Coarse stage of the "stochastic" recipe (``gpr.py:73-101``) for ONE sparse model with all starts as the models of a
+    device batch: per start the reference's draws in the reference's order (variance, lengthscale, noise, then the inducing
+    inputs uniformly in the data's bounding box), ``iter_initial`` Adam steps on the device, the final loss of every start,
+    and the reference's pick (the last start; the lowest loss with ``pick_best``).  Returns (variance, lengthscales, noise, Z)
+    of the selected start, or None if the model does not qualify for the device batch."""
+    from .engine import SparseBatch
+
+    cfg = _trainer_config(model)
+    m, d = model.inducing_variable.Z.shape
+    if (cfg is None or not model.device_batch or m > SparseBatch.MAX_INDUCING or model.y.shape[1] != 1 or n_starts < 1
+            or len({p.trainable for p in model.parameters}) != 1):
+        return None
+    _, transform, prior, floor, n_ls = cfg
+    x = model.data[0]
+    mins, maxs = x.min(axis=0), x.max(axis=0)
+    u0 = []
+    for r in range(n_starts):
+        if starts is not None:
+            var0, ls0, noise0 = starts[r]
+        else:
+            var0, ls0, noise0 = 10 ** rng.uniform(-1, 1), 10 ** rng.uniform(-1, 1), 10 ** rng.uniform(-3, 0)
+        model.kernel.variance.assign(var0)
+        model.kernel.lengthscales.assign(np.full(n_ls, ls0) if n_ls > 1 else ls0)
+        model.likelihood.variance.assign(noise0)
+        z = rng.uniform(mins, maxs, size=(m, d))
+        u0.append(np.concatenate([model.kernel.variance.unconstrained, model.likelihood.variance.unconstrained,
+                                  model.kernel.lengthscales.unconstrained, z.ravel()]))
+    model.inducing_variable.trainable = bool(train_z)
+    n = x.shape[0]
+    key = (threading.get_ident(), model.kernel.name, n, d, m, n_starts, model.device)
+    if key not in _BATCH_POOL:
+        for old in [k for k in _BATCH_POOL if k[0] == key[0]]:
+            _BATCH_POOL.pop(old).close()
+        _BATCH_POOL[key] = SparseBatch(model.kernel.name, n, d, m, n_starts, device=model.device)
+    batch = _BATCH_POOL[key]
+    batch.set_data(x, np.repeat(model.y, n_starts, axis=1))
+    hyp = all(p.trainable for p in model.parameters)
+    u, _, iters = batch.adam(np.stack(u0), n_ls, hyp, bool(train_z), int(iter_initial), 0.001, JITTER, transform, prior is not None, floor)
+    model.n_evals += int(iters.sum())
+
+    def assign(row):
+        model.kernel.variance.unconstrained = row[0:1].copy()
+        model.likelihood.variance.unconstrained = row[1:2].copy()
+        model.kernel.lengthscales.unconstrained = row[2:2 + n_ls].copy()
+        model.inducing_variable.Z = row[2 + n_ls:].reshape(m, d).copy()
+
+    pick = n_starts - 1
+    if pick_best:  # final loss of every start (one batched evaluation; the log prior is host logic), first minimum
+        thetas, zs, lps = [], [], []
+        for r in range(n_starts):
+            assign(u[r])
+            thetas.append(model.theta())
+            zs.append(np.asarray(model.inducing_variable.Z))
+            lps.append(model._log_prior())
+        elbo, _, _, info = batch.elbo_grad(np.stack(thetas), np.stack(zs), JITTER)
+        final = [np.inf if info[r] else -(elbo[r] + lps[r]) for r in range(n_starts)]
+        model.n_evals += n_starts
+        pick = min(range(n_starts), key=lambda r: (final[r], r))
+    assign(u[pick])
+    return (model.kernel.variance.numpy(), model.kernel.lengthscales.numpy(), model.likelihood.variance.numpy(),
+            np.array(model.inducing_variable.Z))
 
 
 def fit_lockstep(models, method: str, max_iter: int = 100, device_trainer: bool = True) -> bool:

@@ -129,6 +129,24 @@ def test_device_trainer_matches_oracle_backed_recipe(cuda, method, ard, param):
     assert mean.shape == (10, 3) and np.all(var > 0)
 
 
+@pytest.mark.parametrize("pick_best,train_z", [(False, False), (True, False), (True, True)])
+def test_multi_start_on_the_device_batch_equals_the_sequential_loop(cuda, pick_best, train_z):
+    """"stochastic" recipe (``gpr.py:73-109``) on a sparse model: all starts as one device batch (same draws in the same order,
+    coarse Adam stage device resident) against one start after the other on the host-driven path; then the same final L-BFGS."""
+    from gpras_b200 import GPRAS
+    from gpras_b200.synth import make_gp_data
+
+    data = make_gp_data(400, 4, 1, 0, seed=31)
+    out = []
+    for lock in (False, True):
+        g = GPRAS("Matern52")
+        g.fit(data.x, data.y, 16, "grid", "stochastic", lockstep_models=False, n_starts=7, iter_initial=12, iter_final=0, seed=6,
+              pick_best=pick_best, train_z=train_z, lockstep=lock)
+        mdl = g.models[0]
+        out.append(np.concatenate([mdl.theta(), np.asarray(mdl.inducing_variable.Z).ravel()]))
+    np.testing.assert_allclose(out[1], out[0], rtol=1e-9, atol=1e-12)
+
+
 def test_device_trainer_follows_the_host_loop_step_by_step(cuda):
     """Loss history of the device-resident stage == the losses the host-driven ``_optimize_adam`` sees on the same device
     evaluation (priors included), for every model and step; without priors too."""

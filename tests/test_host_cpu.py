@@ -39,6 +39,8 @@ class OracleBackedModel(gpr.ExactModel):
 class OracleBackedSparseModel(sparse.SparseModel):
     """SparseModel whose device evaluation is replaced by the torch-CPU SGPR oracle (autograd).  Test infrastructure only."""
 
+    device_batch = False  # never joins a device batch: every evaluation must come from the oracle
+
     class _GP:
         def __init__(self, outer):
             self.outer = outer
