@@ -48,9 +48,11 @@ struct gpras_sgpr_batch {
   double* h_pinned = nullptr;  // p x (nu + 8) staging
   std::vector<std::pair<SgprAdamCfg, cudaGraphExec_t>> graphs;
   // fused evaluation (sgpr_fused.cuh) for m <= 64, d <= 32: four kernels per evaluation, inputs shared by the models
-  bool fused = false;
+  bool fused = false, conditioned = false;
   gpras::SfArgs fa = {};
   double *Xsh = nullptr, *yv = nullptr, *yy = nullptr;
+  double *xt = nullptr, *pmean = nullptr, *pvar = nullptr;  // prediction staging: test inputs, mean / variance (t x p)
+  int pred_cap = 0;
 };
 
 namespace gpras {
@@ -402,6 +404,7 @@ template <int KID>
 int sf_attrs_t() {
   int r;
   if ((r = opt_in_smem(sf_prep_kernel<KID>, 220 * 1024)) || (r = opt_in_smem(sf_prep_train_kernel<KID>, 220 * 1024)) ||
+      (r = opt_in_smem(sf_predict_kernel<KID>, 200 * 1024)) ||  // (+ 24 KB static)
       (r = opt_in_smem(sf_forward_kernel<KID>, 220 * 1024)) || (r = opt_in_smem(sf_mid_kernel<KID>, 220 * 1024)) ||
       (r = opt_in_smem(sf_backward_kernel<KID>, 220 * 1024)))
     return r;
@@ -441,6 +444,50 @@ int sf_launch_t(gpras_sgpr_batch* h, const SfArgs& a, const SgprAdamCfg* cfg) {
   h->launches += 6;
   CU(cudaGetLastError());
   return 0;
+}
+
+// conditioning for prediction: the first four kernels of the evaluation (W, WB, u per model)
+template <int KID>
+int sf_condition_t(gpras_sgpr_batch* h, const SfArgs& a) {
+  cudaStream_t s = h->stream;
+  const int P = h->p;
+  const int tile_smem = sf_tile_doubles(a.D, a.mp) * (int)sizeof(double);
+  sf_prep_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a);
+  sf_forward_kernel<KID><<<dim3(a.ntn, P), SF_THREADS, tile_smem, s>>>(a);
+  sf_reduce_kernel<<<dim3((a.mp * a.mp + a.mp + SF_THREADS - 1) / SF_THREADS, P), SF_THREADS, 0, s>>>(a);
+  sf_mid_kernel<KID><<<dim3(1, P), SF_THREADS, sf_mid_smem(a.D), s>>>(a);
+  h->launches += 4;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int KID>
+int sf_predict_t(gpras_sgpr_batch* h, const SfArgs& a, int t) {
+  const int tile_smem = sf_tile_doubles(a.D, a.mp) * (int)sizeof(double);
+  sf_predict_kernel<KID><<<dim3((t + SF_TN - 1) / SF_TN, h->p), SF_THREADS, tile_smem, h->stream>>>(a, h->xt, t, h->pmean, h->pvar, h->p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+#define GPRAS_SF_DISPATCH(FN, ...)                                   \
+  switch (h->kid) {                                                  \
+    case K_RBF: return FN<K_RBF>(__VA_ARGS__);                       \
+    case K_MATERN12: return FN<K_MATERN12>(__VA_ARGS__);             \
+    case K_MATERN32: return FN<K_MATERN32>(__VA_ARGS__);             \
+    case K_MATERN52: return FN<K_MATERN52>(__VA_ARGS__);             \
+    case K_EXPONENTIAL: return FN<K_EXPONENTIAL>(__VA_ARGS__);       \
+  }                                                                  \
+  return fail(GPRAS_E_ARG, "unknown kernel id")
+
+int sf_condition(gpras_sgpr_batch* h, double jitter) {
+  SfArgs a = h->fa;
+  a.jitter = jitter;
+  GPRAS_SF_DISPATCH(sf_condition_t, h, a);
+}
+
+int sf_predict(gpras_sgpr_batch* h, int t) {
+  GPRAS_SF_DISPATCH(sf_predict_t, h, h->fa, t);
 }
 
 int sf_record_eval(gpras_sgpr_batch* h, double jitter, const SgprAdamCfg* cfg = nullptr) {
@@ -497,7 +544,7 @@ int gpras_sgpr_batch_create(gpras_sgpr_batch** out, int device, int kernel_id, i
     parts = {{&h->theta, (size_t)2 + d}, {&h->Z, (size_t)m * d}, {&fa.Zs, (size_t)SF_MP * d}, {&fa.W, (size_t)SF_MP * SF_MP},
              {&fa.Ap, (size_t)fa.mp * h->n_pad}, {&fa.Kv, (size_t)fa.mp * h->n_pad}, {&fa.Fv, (size_t)fa.mp * h->n_pad},
              {&fa.slabs, nt * SF_MP * SF_MP}, {&fa.aep, nt * SF_MP}, {&fa.aats, (size_t)SF_MP * SF_MP}, {&fa.aes, (size_t)SF_MP},
-             {&fa.RW, (size_t)SF_MP * SF_MP}, {&fa.uvec, (size_t)SF_MP}, {&fa.scal, 8}, {&fa.logdetB, 1},
+             {&fa.RW, (size_t)SF_MP * SF_MP}, {&fa.WBg, (size_t)SF_MP * SF_MP}, {&fa.uvec, (size_t)SF_MP}, {&fa.scal, 8}, {&fa.logdetB, 1},
              {&fa.partA, nt * (1 + d)}, {&fa.zpA, nt * SF_MP * d}, {&fa.partB, (size_t)1 + d},
              {&fa.zpB, (size_t)SF_MP * d}, {&h->result, 3 + d + (size_t)m * d}, {&h->au, (size_t)h->nu}, {&h->amom, (size_t)h->nu},
              {&h->avel, (size_t)h->nu}, {&h->ast, (size_t)gpras::AST}};
@@ -561,6 +608,9 @@ int gpras_sgpr_batch_destroy(gpras_sgpr_batch* h) {
   if (h->Xsh) cudaFree(h->Xsh);
   if (h->yv) cudaFree(h->yv);
   if (h->yy) cudaFree(h->yy);
+  if (h->xt) cudaFree(h->xt);
+  if (h->pmean) cudaFree(h->pmean);
+  if (h->pvar) cudaFree(h->pvar);
   if (h->losses) cudaFree(h->losses);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -582,6 +632,7 @@ int gpras_sgpr_batch_set_data(gpras_sgpr_batch* h, const double* x, const double
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     h->has_data = true;
+    h->conditioned = false;
     return 0;
   }
   for (int b = 0; b < h->p; b++) {
@@ -608,6 +659,7 @@ int gpras_sgpr_batch_elbo_grad(gpras_sgpr_batch* h, const double* theta, const d
   CU(cudaMemcpy2DAsync(h->Z, pitch, z, sizeof(double) * m * D, sizeof(double) * m * D, P, cudaMemcpyHostToDevice, s));
   CU(cudaMemset2DAsync(h->info, pitch, 0, sizeof(int), P, s));
   h->launches = 0;
+  h->conditioned = false;
   int r;
   if ((r = sb_eval(h, jitter))) return r;
   h->warmed = true;
@@ -644,6 +696,7 @@ int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hy
   const int D = h->d, m = h->m, P = h->p;
   const int nu = 2 + n_ls + m * D;
   const size_t pitch = sizeof(double) * h->bs;
+  h->conditioned = false;
   const SgprAdamCfg cfg{n_ls, train_hypers != 0, train_z != 0, transform, priors != 0, lr, jitter, noise_floor};
   int r;
   if (max_iter > h->losses_cap) {
@@ -727,6 +780,56 @@ int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hy
   for (int b = 0; b < P; b++) {
     iters[b] = (int)h_st[(size_t)b * gpras::AST + 3];
     info[b] = (int)h_st[(size_t)b * gpras::AST + 4];
+  }
+  return 0;
+}
+
+// predict_y (gpr.py:337) of all models: condition at host-supplied (theta [p x (2+d)], z [p x m x d]); info [p] as in elbo_grad.
+// Fused layout only (m <= 64, d <= 32); otherwise GPRAS_E_ARG and the caller uses one gpras_sgpr handle per model.
+int gpras_sgpr_batch_condition(gpras_sgpr_batch* h, const double* theta, const double* z, double jitter, int* info) {
+  if (!h || !theta || !z || !info) return fail(GPRAS_E_ARG, "null argument");
+  if (!h->fused) return fail(GPRAS_E_ARG, "batched prediction needs m <= 64 and d <= 32");
+  if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = h->stream;
+  const int D = h->d, m = h->m, P = h->p;
+  const size_t pitch = sizeof(double) * h->bs;
+  h->conditioned = false;
+  CU(cudaMemcpy2DAsync(h->theta, pitch, theta, sizeof(double) * (2 + D), sizeof(double) * (2 + D), P, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpy2DAsync(h->Z, pitch, z, sizeof(double) * m * D, sizeof(double) * m * D, P, cudaMemcpyHostToDevice, s));
+  h->launches = 0;
+  int r;
+  if ((r = sf_condition(h, jitter))) return r;
+  CU(cudaMemcpy2DAsync(info, sizeof(int), h->info, pitch, sizeof(int), P, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int b = 0; b < P; b++)
+    if (info[b]) return 0;  // reported per model; the handle stays unconditioned
+  h->conditioned = true;
+  return 0;
+}
+
+// xs: t x d host array; mean, var: t x p host arrays (variance includes the likelihood noise).
+int gpras_sgpr_batch_predict(gpras_sgpr_batch* h, const double* xs, int t, double* mean, double* var) {
+  if (!h || !xs || t < 0 || !mean || !var) return fail(GPRAS_E_ARG, "bad argument");
+  if (!h->conditioned) return fail(GPRAS_E_STATE, "condition() has not been called");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = h->stream;
+  const int D = h->d, P = h->p;
+  constexpr int CHUNK = 1 << 16;  // test rows per launch
+  int r;
+  if (h->pred_cap == 0) {
+    if ((r = dalloc(&h->xt, (size_t)CHUNK * D)) || (r = dalloc(&h->pmean, (size_t)CHUNK * P)) || (r = dalloc(&h->pvar, (size_t)CHUNK * P)))
+      return r;
+    h->pred_cap = CHUNK;
+  }
+  h->launches = 0;
+  for (int t0 = 0; t0 < t; t0 += CHUNK) {
+    const int tb = t - t0 < CHUNK ? t - t0 : CHUNK;
+    CU(cudaMemcpyAsync(h->xt, xs + (size_t)t0 * D, sizeof(double) * (size_t)tb * D, cudaMemcpyHostToDevice, s));
+    if ((r = sf_predict(h, tb))) return r;
+    CU(cudaMemcpyAsync(mean + (size_t)t0 * P, h->pmean, sizeof(double) * (size_t)tb * P, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(var + (size_t)t0 * P, h->pvar, sizeof(double) * (size_t)tb * P, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
   }
   return 0;
 }

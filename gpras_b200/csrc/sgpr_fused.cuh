@@ -44,6 +44,7 @@ struct SfArgs {
   double* aats;         // [SF_MP * SF_MP]        their sums over the tiles (sf_reduce_kernel)
   double* aes;          // [SF_MP]
   double* RW;           // [SF_MP][SF_MP]
+  double* WBg;          // [SF_MP][SF_MP]   LB^-1, kept for prediction
   double* uvec;         // [SF_MP]
   double* scal;         // [8]
   double* logdetB;      // [1]
@@ -506,6 +507,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
   }
   __syncthreads();
   if (tid == 0) (a.logdetB + off)[0] = lgs[0] + lgs[1];
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    (a.WBg + off)[i * SF_MP + j] = SB[i * SF_LD + j];
+  }
   // c = WB ae ; chat = WB^T c ; u = W^T chat
   if (tid < mp) {
     double s = 0.0;
@@ -747,6 +752,112 @@ __device__ __forceinline__ void sf_finalize_body(const SfArgs& a, double* __rest
 
 static __global__ void __launch_bounds__(SF_THREADS) sf_finalize_kernel(const SfArgs a, double* __restrict__ result) {
   sf_finalize_body(a, result + (long)blockIdx.y * a.bs);
+}
+
+// ---- 6. prediction (predict_y, gpr.py:337) for a conditioned batch: per (tile of 128 test rows, model) ----------------
+//   mean = Kus^T u,  var = variance + s2 + |WB W Kus|^2 - |W Kus|^2   (columnwise; GPflow SGPR.predict_f + likelihood noise)
+// xs: [t_pad][D] test inputs (device), mean / var: [t][P] row-major.
+template <int KID>
+__global__ void __launch_bounds__(SF_THREADS, 2) sf_predict_kernel(const SfArgs a, const double* __restrict__ xs, int t_total,
+                                                                   double* __restrict__ mean, double* __restrict__ var, int P) {
+  extern __shared__ __align__(16) double smem[];
+  const int D = a.D, m = a.m, mp = a.mp, na = mp >> 3, mt = mp >> 3;
+  const SfTileSmem sm = sf_tile_layout(smem, D, mp);
+  double *xsT = sm.xsT, *zs = sm.zs, *KA = sm.KA, *us = sm.us;
+  __shared__ double red[3][8][SF_TN];  // per warp and column: mean, |W Kus|^2, |WB W Kus|^2 partial sums
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int model = blockIdx.y, t0 = blockIdx.x * SF_TN;
+  const long off = (long)model * a.bs;
+  const double* theta = a.theta + off;
+  const double variance = theta[0];
+  const bool row_warp = warp < mt;
+  const int irow = 8 * warp + g;
+  for (int e = tid; e < SF_TN * D; e += SF_THREADS) {
+    const int c = e / D, dd = e - c * D;
+    xsT[dd * SF_TN + c] = t0 + c < t_total ? xs[(long)(t0 + c) * D + dd] / theta[2 + dd] : 0.0;
+  }
+  for (int e = tid; e < mp * D; e += SF_THREADS) zs[e] = (a.Zs + off)[e];
+  if (tid < mp) us[tid] = (a.uvec + off)[tid];
+  double wfrag[2 * (SF_MP / 8)], bfrag[2 * (SF_MP / 8)];  // rows [8w, 8w + 8) of W and of WB (both lower triangular)
+#pragma unroll
+  for (int k4 = 0; k4 < 2 * (SF_MP / 8); k4++) {
+    const bool on = row_warp && k4 < 2 * (warp + 1);
+    wfrag[k4] = on ? (a.W + off)[irow * SF_MP + 4 * k4 + q] : 0.0;
+    bfrag[k4] = on ? (a.WBg + off)[irow * SF_MP + 4 * k4 + q] : 0.0;
+  }
+  for (int e = tid; e < 3 * 8 * SF_TN; e += SF_THREADS) (&red[0][0][0])[e] = 0.0;
+  __syncthreads();
+  // Kus entries (rows warp + 8 r, columns lane + 32 s) and this warp's part of the mean
+  double msum[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int r = 0; r < na; r++) {
+    const int i = warp + 8 * r;
+    double r2[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int dd = 0; dd < D; dd++) {
+      const double zi = zs[i * D + dd];
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        const double df = zi - xsT[dd * SF_TN + lane + 32 * s];
+        r2[s] = fma(df, df, r2[s]);
+      }
+    }
+    const double ui = us[i];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const double k = i < m ? variance * kernel_value<KID>(r2[s]) : 0.0;
+      KA[i * SF_LDK + lane + 32 * s] = k;
+      msum[s] = fma(k, ui, msum[s]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 4; s++) red[0][warp][lane + 32 * s] = msum[s];
+  __syncthreads();
+  double acc[16][2];
+  auto product = [&](const double (&frag)[2 * (SF_MP / 8)], int which) {
+#pragma unroll
+    for (int ct = 0; ct < 16; ct++) acc[ct][0] = acc[ct][1] = 0.0;
+    if (row_warp) {
+#pragma unroll
+      for (int k4 = 0; k4 < 2 * (SF_MP / 8); k4++) {
+        if (k4 < 2 * (warp + 1)) {
+          const double* bp = KA + (4 * k4 + q) * SF_LDK + g;
+#pragma unroll
+          for (int ct = 0; ct < 16; ct++) dmma(acc[ct][0], acc[ct][1], frag[k4], bp[8 * ct]);
+        }
+      }
+      // column sums of squares over this warp's 8 rows (lanes with equal q hold the same columns)
+#pragma unroll
+      for (int ct = 0; ct < 16; ct++) {
+        double s0 = acc[ct][0] * acc[ct][0], s1 = acc[ct][1] * acc[ct][1];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (g == 0) {
+          red[which][warp][8 * ct + 2 * q] = s0;
+          red[which][warp][8 * ct + 2 * q + 1] = s1;
+        }
+      }
+    }
+  };
+  product(wfrag, 1);  // tmp1 = W Kus
+  __syncthreads();    // every read of the Kus tile is done: the buffer becomes tmp1
+  if (row_warp) {
+#pragma unroll
+    for (int ct = 0; ct < 16; ct++)
+      *reinterpret_cast<double2*>(KA + irow * SF_LDK + 8 * ct + 2 * q) = make_double2(acc[ct][0], acc[ct][1]);
+  }
+  __syncthreads();
+  product(bfrag, 2);  // tmp2 = WB tmp1
+  __syncthreads();
+  if (tid < SF_TN && t0 + tid < t_total) {
+    double mu = 0.0, q1 = 0.0, p2 = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) mu += red[0][wv][tid], q1 += red[1][wv][tid], p2 += red[2][wv][tid];
+    mean[(long)(t0 + tid) * P + model] = mu;
+    var[(long)(t0 + tid) * P + model] = variance + theta[1] + p2 - q1;
+  }
 }
 
 }  // namespace gpras

@@ -303,6 +303,7 @@ class SparseBatch:
         x, y = _f64(x), _f64(y)
         if x.shape != (self.n, self.d) or y.shape != (self.n, self.p):
             raise ValueError(f"expected x {(self.n, self.d)} and y {(self.n, self.p)}, got {x.shape}, {y.shape}")
+        self._cond = None
         check(self.lib.gpras_sgpr_batch_set_data(self._h, ptr(x), ptr(y)))
 
     def elbo_grad(self, theta, z, jitter: float = 1e-6):
@@ -312,6 +313,7 @@ class SparseBatch:
             raise ValueError(f"expected theta {(self.p, 2 + self.d)} and z {(self.p, self.m, self.d)}, got {theta.shape}, {z.shape}")
         elbo, gt, gz = np.empty(self.p), np.empty((self.p, 2 + self.d)), np.empty((self.p, self.m, self.d))
         info = np.zeros(self.p, np.int32)
+        self._cond = None
         check(self.lib.gpras_sgpr_batch_elbo_grad(self._h, ptr(theta), ptr(z), float(jitter), ptr(elbo), ptr(gt), ptr(gz),
                                                   info.ctypes.data))
         return elbo, gt, gz, info
@@ -326,6 +328,7 @@ class SparseBatch:
             raise ValueError(f"expected u of shape {(self.p, nu)}, got {u.shape}")
         losses = np.empty((int(max_iter), self.p))
         iters, info = np.zeros(self.p, np.int32), np.zeros(self.p, np.int32)
+        self._cond = None
         check(self.lib.gpras_sgpr_batch_adam(self._h, ptr(u), int(n_ls), int(train_hypers), int(train_z), int(max_iter),
                                              float(learning_rate), float(jitter), 1 if transform == "log" else 0, int(priors),
                                              float(noise_floor), ptr(losses) if max_iter > 0 else None, iters.ctypes.data,
@@ -335,6 +338,38 @@ class SparseBatch:
             raise _lib.NotPositiveDefiniteError(
                 f"Kuu or B lost positive definiteness in model {int(bad[0])} (first failing pivot {int(info[bad[0]])})")
         return u, losses, iters
+
+    @property
+    def fused(self) -> bool:
+        """The fused evaluation (and with it batched prediction) covers m <= 64 inducing points and d <= 32 features."""
+        return self.m <= 64 and self.d <= 32
+
+    def condition(self, theta, z, jitter: float = 1e-6) -> None:
+        """Condition all models for ``predict`` (skipped when they are already conditioned at the same values)."""
+        theta, z = _f64(theta), _f64(z)
+        if theta.shape != (self.p, 2 + self.d) or z.shape != (self.p, self.m, self.d):
+            raise ValueError(f"expected theta {(self.p, 2 + self.d)} and z {(self.p, self.m, self.d)}, got {theta.shape}, {z.shape}")
+        c = getattr(self, "_cond", None)
+        if c is not None and c[2] == float(jitter) and np.array_equal(c[0], theta) and np.array_equal(c[1], z):
+            return
+        self._cond = None
+        info = np.zeros(self.p, np.int32)
+        check(self.lib.gpras_sgpr_batch_condition(self._h, ptr(theta), ptr(z), float(jitter), info.ctypes.data))
+        bad = np.flatnonzero(info)
+        if bad.size:
+            raise _lib.NotPositiveDefiniteError(
+                f"Kuu or B lost positive definiteness in model {int(bad[0])} (first failing pivot {int(info[bad[0]])})")
+        self._cond = (theta.copy(), z.copy(), float(jitter))
+
+    def predict(self, xs):
+        """``predict_y`` of all models: (mean, variance), both (T, p), likelihood noise included."""
+        xs = _f64(xs)
+        if xs.ndim != 2 or xs.shape[1] != self.d:
+            raise ValueError(f"expected (T, {self.d}) test inputs, got {xs.shape}")
+        t = xs.shape[0]
+        mean, var = np.empty((t, self.p)), np.empty((t, self.p))
+        check(self.lib.gpras_sgpr_batch_predict(self._h, ptr(xs), t, ptr(mean), ptr(var)))
+        return mean, var
 
     def last_launches(self) -> int:
         return int(self.lib.gpras_sgpr_batch_last_launches(self._h))

@@ -904,6 +904,13 @@ class GPRAS:
         x = np.asarray(x).astype(np.float64)
         if self._opts.get("shared_kernel") and self._opts.get("exact") and self.models:
             return self.models[0].predict_y(x)
+        if self.models and not self._opts.get("exact") and self._opts.get("batched_predict", True):
+            # the reference's model family: all per-column sparse models conditioned and predicted in one batched device pass
+            from .sparse import predict_batched
+
+            out = predict_batched(self.models, x)
+            if out is not None:
+                return out
         # Per-column models: each keeps its conditioned factor on a handle of its own while they fit in the budget, so a
         # second predict() costs only the predictor (the reference loops over the models, gpr.py:336-339).
         keep = self._predict_handles_fit()

@@ -271,8 +271,26 @@ def _device_batch(models):
             _BATCH_POOL.pop(old).close()
         _BATCH_POOL[key] = SparseBatch(m0.kernel.name, n, d, m, len(models), device=m0.device)
     batch = _BATCH_POOL[key]
-    batch.set_data(m0.x, np.concatenate([mdl.y for mdl in models], axis=1))
+    owners = tuple(id(mdl) for mdl in models)
+    if getattr(batch, "_owners", None) != owners:  # (a model's data never change after construction)
+        batch.set_data(m0.x, np.concatenate([mdl.y for mdl in models], axis=1))
+        batch._owners = owners
+        batch._keep = list(models)  # keeps the ids alive
     return batch
+
+
+def predict_batched(models, xs):
+    """``predict_y`` of all per-column sparse models in one device pass per tile of test inputs (``gpras_sgpr_batch_predict``),
+    or None when they do not qualify (then the caller predicts model by model)."""
+    if not models or len(models) < 2:
+        return None
+    batch = _device_batch(models)
+    if batch is None or not batch.fused:
+        return None
+    theta = np.stack([mdl.theta() for mdl in models])
+    z = np.stack([np.asarray(mdl.inducing_variable.Z, np.float64) for mdl in models])
+    batch.condition(theta, z, JITTER)
+    return batch.predict(xs)
 
 
 def _trainer_config(mdl):
@@ -352,6 +370,7 @@ def multi_start_device(model, rng, n_starts: int, iter_initial: int, starts, pic
             _BATCH_POOL.pop(old).close()
         _BATCH_POOL[key] = SparseBatch(model.kernel.name, n, d, m, n_starts, device=model.device)
     batch = _BATCH_POOL[key]
+    batch._owners = None
     batch.set_data(x, np.repeat(model.y, n_starts, axis=1))
     hyp = all(p.trainable for p in model.parameters)
     u, _, iters = batch.adam(np.stack(u0), n_ls, hyp, bool(train_z), int(iter_initial), 0.001, JITTER, transform, prior is not None, floor)

@@ -85,6 +85,72 @@ def test_batched_evaluation_matches_the_single_model_one(cuda, kernel, ard, n, d
     batch.close()
 
 
+@pytest.mark.parametrize("kernel,ard,n,d,m,p,t", [("Matern52", False, 700, 5, 24, 6, 300), ("RBF", True, 1000, 10, 50, 10, 1),
+                                                  ("Matern12", True, 300, 32, 64, 2, 129), ("Exponential", False, 130, 2, 1, 3, 70000)])
+def test_batched_prediction_matches_the_single_model_one_and_the_oracle(cuda, kernel, ard, n, d, m, p, t):
+    """``predict_y`` (``gpr.py:337``) of all models in one pass per tile of test inputs against one handle per model (the general
+    kernels) and the torch oracle; T = 1, T not a tile multiple, and T beyond one staging chunk."""
+    from gpras_b200.engine import SparseBatch, SparseGP
+    from oracle import sgpr
+
+    data, theta, z = _models_setup(n, d, m, p, seed=n + m + 1, ard=ard)
+    xs = np.random.default_rng(t).standard_normal((t, d))
+    batch = SparseBatch(kernel, n, d, m, p)
+    batch.set_data(data.x, data.y)
+    batch.condition(theta, z)
+    mean, var = batch.predict(xs)
+    assert mean.shape == var.shape == (t, p)
+    one = SparseGP(kernel, n, d, m, 1)
+    tt = min(t, 500)
+    for b in range(p):
+        one.set_data(data.x, np.ascontiguousarray(data.y[:, b : b + 1]))
+        one.condition(theta[b], z[b])
+        m1, v1 = one.predict(xs[:tt])
+        np.testing.assert_allclose(mean[:tt, b], m1[:, 0], rtol=1e-10, atol=1e-11 * max(1.0, np.abs(m1).max()))
+        np.testing.assert_allclose(var[:tt, b], v1[:, 0], rtol=1e-10)
+    one.close()
+    for b in (0, p - 1):
+        om, ov = sgpr.predict_y(kernel, data.x, data.y[:, b : b + 1], z[b], theta[b, 0], theta[b, 2:], theta[b, 1], xs[-tt:])
+        np.testing.assert_allclose(mean[-tt:, b], om[:, 0], rtol=1e-8, atol=1e-9 * max(1.0, np.abs(om).max()))
+        np.testing.assert_allclose(np.sqrt(var[-tt:, b]), np.sqrt(ov[:, 0]), rtol=1e-6)
+    # conditioning is remembered; an evaluation in between invalidates it
+    calls = []
+    orig = batch.lib.gpras_sgpr_batch_condition
+    batch.lib.gpras_sgpr_batch_condition = lambda *a: (calls.append(1), orig(*a))[1]
+    try:
+        batch.condition(theta, z)
+        assert not calls
+        batch.elbo_grad(theta, z)
+        batch.condition(theta, z)
+        assert len(calls) == 1
+    finally:
+        batch.lib.gpras_sgpr_batch_condition = orig
+    m2, v2 = batch.predict(xs[:tt])
+    np.testing.assert_array_equal(m2, mean[:tt])
+    np.testing.assert_array_equal(v2, var[:tt])
+    batch.close()
+
+
+def test_gpras_predict_uses_the_batch_for_the_reference_family(cuda):
+    from gpras_b200 import GPRAS
+    from gpras_b200.synth import make_gp_data
+
+    data = make_gp_data(600, 4, 5, 200, seed=13)
+    g = GPRAS("Matern32")
+    g.fit(data.x, data.y, 20, "grid", "adam", max_iter=10)
+    mean, var = g.predict(data.x_test)
+    g._opts["batched_predict"] = False
+    mean1, var1 = g.predict(data.x_test)
+    assert mean.shape == (200, 5)
+    np.testing.assert_allclose(mean, mean1, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(var, var1, rtol=1e-10)
+    # M > 64 falls back to one handle per model
+    g2 = GPRAS("RBF")
+    g2.fit(data.x, data.y, 70, "grid", "adam", max_iter=3)
+    m2, v2 = g2.predict(data.x_test[:10])
+    assert m2.shape == (10, 5) and np.all(v2 > 0)
+
+
 def test_batch_rejects_what_it_cannot_hold(cuda):
     from gpras_b200._lib import GprasError
     from gpras_b200.engine import SparseBatch

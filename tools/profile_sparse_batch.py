@@ -24,6 +24,16 @@ for rep in range(3):
     g.fit(data.x, data.y, m, "grid", "two-stage")
     print(f"fit #{rep}: {time.perf_counter() - t0:.4f} s", flush=True)
 
+xt = np.random.default_rng(1).standard_normal((10000, d))
+for label, flag in (("batched", True), ("one handle per model", False)):
+    g._opts["batched_predict"] = flag
+    g.predict(xt[:10])
+    t0 = time.perf_counter()
+    g.predict(xt)
+    t1 = time.perf_counter()
+    g.predict(xt)
+    print(f"predict 10000 events x {p} models, {label}: first {1e3 * (t1 - t0):.2f} ms (conditions), again {1e3 * (time.perf_counter() - t1):.2f} ms")
+
 batch = SparseBatch("Matern52", n, d, m, p)
 t0 = time.perf_counter()
 batch.set_data(data.x, data.y)
