@@ -590,7 +590,7 @@ def run_ours(args) -> None:
         del xs_
 
     sparse_fit = None
-    if rank == 0 and leg("sparse"):
+    if rank == 0 and world == 1 and leg("sparse"):  # (GPRAS.fit shards per-column models over ranks: a one-rank call would hang)
         # The reference's DEFAULT call at the reference's own scale (gpras/gpr.py:237-275: one SGPR per column, "two-stage" =
         # Adam 100 steps on the inducing inputs + Adam 100 steps on the hyperparameters): device-resident batched trainer vs
         # the host-driven loops of the same device evaluation.

@@ -825,7 +825,15 @@ class GPRAS:
             # one process per GPU: per-column models go round-robin to ranks, parameters are all-gathered at the end
             from .parallel import run_models_sharded
 
-            run_models_sharded(unique, run_one)
+            run_many = None
+            if (lockstep_models and n_jobs == 1 and initial_theta is None and optimization_method in ("adam", "two-stage")
+                    and set(opt_kwargs) <= {"max_iter"} and (not exact or self.x.shape[0] <= 4096)):
+                from .sparse import fit_lockstep
+
+                def run_many(shard):  # this rank's models advance together (device-resident trainer where they qualify)
+                    return fit_lockstep(shard, optimization_method, device_trainer=device_trainer, **opt_kwargs)
+
+            run_models_sharded(unique, run_one, run_many)
         elif n_jobs > 1 and len(unique) > 1:
             from concurrent.futures import ThreadPoolExecutor
 

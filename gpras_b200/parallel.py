@@ -245,15 +245,17 @@ def metrics_sharded(event_ids, summarise_event, keys) -> np.ndarray:
     return table[np.argsort(table[:, 0], kind="stable")]
 
 
-def run_models_sharded(models, run_one) -> None:
+def run_models_sharded(models, run_one, run_many=None) -> None:
     """Per-column models (the reference's default: one independent model per spatial mode, ``gpr.py:273-274``) sharded
     round-robin over ranks: rank r optimises models r, r + world, ...; the optimised parameters (variance, likelihood
     variance, lengthscales, inducing inputs) are all-gathered so that every rank ends with every model.  One exchange of
-    ``P x (2 + n_ls + M D)`` doubles at the end, nothing during optimisation."""
+    ``P x (2 + n_ls + M D)`` doubles at the end, nothing during optimisation.  ``run_many(list_of_models) -> bool`` (optional)
+    trains a rank's whole shard at once (the device-resident batched trainer); when it declines, ``run_one`` runs per model."""
     rank, world, _ = dist_info()
     mine = shard_indices(len(models), rank, world)
-    for i in mine:
-        run_one(models[i])
+    if not (run_many is not None and len(mine) > 0 and run_many([models[i] for i in mine])):
+        for i in mine:
+            run_one(models[i])
 
     def pack(i):
         d = models[i].parameter_dict()

@@ -72,6 +72,21 @@ def _worker(rank, world, port, out_dir):
     models = [OracleBackedModel("RBF", d3.x, d3.y[:, j : j + 1], 1.0) for j in range(3)]
     parallel.run_models_sharded(models, lambda m_: gpr.OPTIMIZERS["L-BFGS-B"](m_, max_iter=15))
     np.save(os.path.join(out_dir, f"models{rank}.npy"), np.array([m_.theta() for m_ in models]))
+    # the same through the whole-shard hook (what the device-resident trainer plugs into): once accepting, once declining
+    for accept in (True, False):
+        models2 = [OracleBackedModel("RBF", d3.x, d3.y[:, j : j + 1], 1.0) for j in range(3)]
+        seen = []
+
+        def run_many(shard, _accept=accept, _seen=seen):
+            _seen.append(len(shard))
+            if _accept:
+                for m_ in shard:
+                    gpr.OPTIMIZERS["L-BFGS-B"](m_, max_iter=15)
+            return _accept
+
+        parallel.run_models_sharded(models2, lambda m_: gpr.OPTIMIZERS["L-BFGS-B"](m_, max_iter=15), run_many)
+        assert seen == [len(parallel.shard_indices(3, rank, world))]
+        assert np.array_equal(np.array([m_.theta() for m_ in models2]), np.array([m_.theta() for m_ in models]))
 
     # events sharded over ranks for the metrics
     rng = np.random.default_rng(3)

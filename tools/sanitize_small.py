@@ -61,3 +61,19 @@ if which in ("all", "sgpr"):
     sp.condition(np.concatenate([[v, s], ls]), data.x[:40].copy())
     print("elbo", e, sp.predict(data.x_test)[0][:2].ravel())
     sp.close()
+if which in ("all", "batch"):
+    from gpras_b200.engine import SparseBatch
+
+    for mm_, dd_ in ((40, d), (70, d)):  # fused path (M <= 64) and the general kernels batched over the models
+        sb = SparseBatch("Matern52", n, d, mm_, 3)
+        sb.set_data(data.x, data.y[:, :3])
+        th3 = np.tile(np.concatenate([[v, s], ls]), (3, 1))
+        z3 = np.stack([data.x[k : k + mm_] for k in (0, 50, 100)])
+        e3, _, _, info3 = sb.elbo_grad(th3, z3)
+        u0 = np.concatenate([np.full((3, 2 + d), 0.5), z3.reshape(3, -1)], axis=1)
+        u1, losses, iters = sb.adam(u0, d, True, True, 3)
+        print("batch elbo", e3, info3, "adam", losses[-1], iters)
+        if sb.fused:
+            sb.condition(th3, z3)
+            print("batch predict", sb.predict(data.x_test)[0][0])
+        sb.close()
