@@ -59,6 +59,10 @@ SYMBOLS = {
         C.c_int,
         [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, vp, vp, vp],
     ),
+    "gpras_sgpr_batch_train": (
+        C.c_int,
+        [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, vp],
+    ),
     "gpras_sgpr_batch_condition": (C.c_int, [vp, vp, vp, C.c_double, vp]),
     "gpras_sgpr_batch_predict": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "gpras_sgpr_batch_last_launches": (C.c_int, [vp]),

@@ -17,10 +17,11 @@
 
 struct SgprAdamCfg {
   int n_ls, train_hypers, train_z, transform, priors;
+  int rule;  // 0: Keras Adam + the reference's early-stopping rule (gpr.py:147-173); 1: Keras Adadelta, fixed number of steps (gpr.py:176-192)
   double lr, jitter, noise_floor;
   bool operator==(const SgprAdamCfg& o) const {
     return n_ls == o.n_ls && train_hypers == o.train_hypers && train_z == o.train_z && transform == o.transform &&
-           priors == o.priors && lr == o.lr && jitter == o.jitter && noise_floor == o.noise_floor;
+           priors == o.priors && rule == o.rule && lr == o.lr && jitter == o.jitter && noise_floor == o.noise_floor;
   }
 };
 
@@ -75,6 +76,20 @@ __device__ __forceinline__ double sb_adam_update(double u, double g, double& mom
   mom = __dadd_rn(__dmul_rn(b1, mom), __dmul_rn(1.0 - b1, g));
   vel = __dadd_rn(__dmul_rn(b2, vel), __dmul_rn(__dmul_rn(1.0 - b2, g), g));
   return __dsub_rn(u, __ddiv_rn(__dmul_rn(alpha, mom), __dadd_rn(sqrt(vel), eps)));
+}
+
+// Keras Adadelta (rho 0.95, eps 1e-7) on one variable, operation order of gpras_b200/gpr.py:_optimize_adadelta; acc_g / acc_d
+// live in the two moment buffers.
+__device__ __forceinline__ double sb_adadelta_update(double u, double g, double& acc_g, double& acc_d, double lr) {
+  const double rho = 0.95, eps = 1e-7;
+  acc_g = __dadd_rn(__dmul_rn(rho, acc_g), __dmul_rn(__dmul_rn(1.0 - rho, g), g));
+  const double upd = __ddiv_rn(__dmul_rn(g, sqrt(__dadd_rn(acc_d, eps))), sqrt(__dadd_rn(acc_g, eps)));
+  acc_d = __dadd_rn(__dmul_rn(rho, acc_d), __dmul_rn(__dmul_rn(1.0 - rho, upd), upd));
+  return __dsub_rn(u, __dmul_rn(lr, upd));
+}
+
+__device__ __forceinline__ double sb_update(int rule, double u, double g, double& m1, double& m2, double alpha, double lr) {
+  return rule == 0 ? sb_adam_update(u, g, m1, m2, alpha) : sb_adadelta_update(u, g, m1, m2, lr);
 }
 
 // u -> theta (constrained) and Z, info = 0 (pointers of one model).
@@ -143,25 +158,27 @@ __device__ __forceinline__ void sgpr_adam_body(const double* __restrict__ result
           dlp = -(1.0 + lv) / v;
         }
         const double g = -((gl / v + dlp) * sb_dforward(uk, cfg.transform));
-        au[k] = sb_adam_update(uk, g, amom[k], avel[k], alpha);
+        au[k] = sb_update(cfg.rule, uk, g, amom[k], avel[k], alpha, cfg.lr);
       }
     }
     const double loss = -(result[0] + lp);
     losses[(long)(t - 1) * p + b] = loss;
     ast[5] = loss;
     ast[3] = (double)t;
-    if ((ast[0] - loss) / fabs(loss) > tol) {
-      ast[0] = loss, ast[1] = 0.0;
-    } else {
-      ast[1] += 1.0;
-      if (ast[1] > (double)patience) ast[2] = 0.0;
+    if (cfg.rule == 0) {  // the reference's early-stopping rule belongs to its Adam loop only
+      if ((ast[0] - loss) / fabs(loss) > tol) {
+        ast[0] = loss, ast[1] = 0.0;
+      } else {
+        ast[1] += 1.0;
+        if (ast[1] > (double)patience) ast[2] = 0.0;
+      }
     }
   }
   if (cfg.train_z) {
     for (int e = tid; e < m * D; e += blockDim.x) {
       const int k = nh + e;
       const double g = -result[3 + D + e];
-      au[k] = sb_adam_update(au[k], g, amom[k], avel[k], alpha);
+      au[k] = sb_update(cfg.rule, au[k], g, amom[k], avel[k], alpha, cfg.lr);
     }
   }
 }
@@ -685,9 +702,23 @@ int gpras_sgpr_batch_elbo_grad(gpras_sgpr_batch* h, const double* theta, const d
 //   transform  0: value = softplus(u) (+ noise_floor for the noise), GPflow; 1: value = exp(u)
 //   losses     max_iter x p out: the loss every model saw at every step (NaN where it had stopped)
 //   iters      p out: steps taken;  info p out: 0, or the failing pivot of a model whose Kuu / B lost positive definiteness
+int gpras_sgpr_batch_train(gpras_sgpr_batch* h, double* u, int n_ls, int train_hypers, int train_z, int max_iter, double lr,
+                           double jitter, int transform, int priors, double noise_floor, int rule, double* losses, int* iters,
+                           int* info);
+
 int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hypers, int train_z, int max_iter, double lr,
                           double jitter, int transform, int priors, double noise_floor, double* losses, int* iters, int* info) {
+  return gpras_sgpr_batch_train(h, u, n_ls, train_hypers, train_z, max_iter, lr, jitter, transform, priors, noise_floor, 0, losses,
+                                iters, info);
+}
+
+// The same loop with the update rule as a parameter: rule 0 = Adam (above), 1 = Keras Adadelta (_optimize_adadelta,
+// gpr.py:176-192: fixed max_iter steps, no early stopping).
+int gpras_sgpr_batch_train(gpras_sgpr_batch* h, double* u, int n_ls, int train_hypers, int train_z, int max_iter, double lr,
+                           double jitter, int transform, int priors, double noise_floor, int rule, double* losses, int* iters,
+                           int* info) {
   if (!h || !u || !iters || !info) return fail(GPRAS_E_ARG, "null argument");
+  if (rule != 0 && rule != 1) return fail(GPRAS_E_ARG, "unknown update rule");
   if (!h->has_data) return fail(GPRAS_E_STATE, "set_data has not been called");
   if ((n_ls != 1 && n_ls != h->d) || max_iter < 0 || (transform != 0 && transform != 1))
     return fail(GPRAS_E_ARG, "bad trainer configuration");
@@ -697,7 +728,7 @@ int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hy
   const int nu = 2 + n_ls + m * D;
   const size_t pitch = sizeof(double) * h->bs;
   h->conditioned = false;
-  const SgprAdamCfg cfg{n_ls, train_hypers != 0, train_z != 0, transform, priors != 0, lr, jitter, noise_floor};
+  const SgprAdamCfg cfg{n_ls, train_hypers != 0, train_z != 0, transform, priors != 0, rule, lr, jitter, noise_floor};
   int r;
   if (max_iter > h->losses_cap) {
     for (auto& g : h->graphs)  // the loss-history pointer is a captured kernel argument

@@ -319,8 +319,9 @@ class SparseBatch:
         return elbo, gt, gz, info
 
     def adam(self, u, n_ls: int, train_hypers: bool, train_z: bool, max_iter: int, learning_rate: float = 0.001,
-             jitter: float = 1e-6, transform: str = "softplus", priors: bool = True, noise_floor: float = 1e-6):
-        """One Adam stage of all models on the device (``gpras/gpr.py:147-173``).  ``u`` (p, 2 + n_ls + M D): unconstrained
+             jitter: float = 1e-6, transform: str = "softplus", priors: bool = True, noise_floor: float = 1e-6, rule: str = "adam"):
+        """One Adam stage of all models on the device (``gpras/gpr.py:147-173``), or with ``rule="adadelta"`` exactly
+        ``max_iter`` Keras-Adadelta steps (``gpr.py:176-192``).  ``u`` (p, 2 + n_ls + M D): unconstrained
         [variance, noise, lengthscale(s), Z] per model.  Returns (u, losses [max_iter, p], steps [p])."""
         u = _f64(u).copy()
         nu = 2 + int(n_ls) + self.m * self.d
@@ -329,10 +330,12 @@ class SparseBatch:
         losses = np.empty((int(max_iter), self.p))
         iters, info = np.zeros(self.p, np.int32), np.zeros(self.p, np.int32)
         self._cond = None
-        check(self.lib.gpras_sgpr_batch_adam(self._h, ptr(u), int(n_ls), int(train_hypers), int(train_z), int(max_iter),
-                                             float(learning_rate), float(jitter), 1 if transform == "log" else 0, int(priors),
-                                             float(noise_floor), ptr(losses) if max_iter > 0 else None, iters.ctypes.data,
-                                             info.ctypes.data))
+        if rule not in ("adam", "adadelta"):
+            raise ValueError(f"unknown update rule {rule!r}")
+        check(self.lib.gpras_sgpr_batch_train(self._h, ptr(u), int(n_ls), int(train_hypers), int(train_z), int(max_iter),
+                                              float(learning_rate), float(jitter), 1 if transform == "log" else 0, int(priors),
+                                              float(noise_floor), 1 if rule == "adadelta" else 0,
+                                              ptr(losses) if max_iter > 0 else None, iters.ctypes.data, info.ctypes.data))
         bad = np.flatnonzero(info)
         if bad.size:
             raise _lib.NotPositiveDefiniteError(

@@ -809,25 +809,33 @@ class GPRAS:
 
         from .parallel import dist_info
 
+        done = False
+        lockstep_methods = ("adam", "two-stage") if (exact or not device_trainer) else ("adam", "two-stage", "adadelta", "three-stage")
         if (lockstep_models and n_jobs == 1 and restarts is None and dist_info()[1] == 1
                 and (len(unique) > 1 or (not exact and device_trainer))
-                and optimization_method in ("adam", "two-stage") and set(opt_kwargs) <= {"max_iter"}
+                and optimization_method in lockstep_methods and set(opt_kwargs) <= {"max_iter"}
+                and ("max_iter" in opt_kwargs or optimization_method in ("two-stage", "three-stage"))
                 and (not exact or self.x.shape[0] <= 4096)):
-            # the reference's default path: independent per-column models trained by Adam -- all of them advance together,
-            # their evaluations overlapping on the GPU (same trajectories as the sequential loop)
+            # the reference's default path: independent per-column models trained by first-order recipes -- all of them advance
+            # together: sparse models in one device batch with the update steps on the device, otherwise their evaluations
+            # overlapping on the GPU (same trajectories as the sequential loop)
             from .sparse import fit_lockstep
 
             if initial_theta is not None:
                 for model in unique:
                     _assign_theta(model, initial_theta)
-            fit_lockstep(unique, optimization_method, device_trainer=device_trainer, **opt_kwargs)
+            done = fit_lockstep(unique, optimization_method, device_trainer=device_trainer, **opt_kwargs)
+        if done:
+            pass
         elif dist_info()[1] > 1 and len(unique) > 1 and restarts is None:
             # one process per GPU: per-column models go round-robin to ranks, parameters are all-gathered at the end
             from .parallel import run_models_sharded
 
             run_many = None
-            if (lockstep_models and n_jobs == 1 and initial_theta is None and optimization_method in ("adam", "two-stage")
-                    and set(opt_kwargs) <= {"max_iter"} and (not exact or self.x.shape[0] <= 4096)):
+            if (lockstep_models and n_jobs == 1 and initial_theta is None and optimization_method in lockstep_methods
+                    and set(opt_kwargs) <= {"max_iter"}
+                    and ("max_iter" in opt_kwargs or optimization_method in ("two-stage", "three-stage"))
+                    and (not exact or self.x.shape[0] <= 4096)):
                 from .sparse import fit_lockstep
 
                 def run_many(shard):  # this rank's models advance together (device-resident trainer where they qualify)

@@ -306,9 +306,10 @@ def _trainer_config(mdl):
     return (mdl.kernel.name, tr.pop(), pr.pop(), mdl.likelihood.variance.lower, mdl.kernel.lengthscales.size)
 
 
-def adam_device(models, batch, max_iter: int, learning_rate: float = 0.001) -> bool:
-    """``_optimize_adam`` (``gpr.py:147-173``) of all ``models`` as ONE device-resident loop (``gpras_sgpr_batch_adam``): no
-    host round trip per step.  Returns False when the models' trainable flags are not one of the recipes' stages."""
+def adam_device(models, batch, max_iter: int, learning_rate: float = 0.001, rule: str = "adam") -> bool:
+    """``_optimize_adam`` (``gpr.py:147-173``; ``rule="adadelta"``: ``_optimize_adadelta``, ``gpr.py:176-192``) of all ``models``
+    as ONE device-resident loop (``gpras_sgpr_batch_train``): no host round trip per step.  Returns False when the models'
+    trainable flags are not one of the recipes' stages."""
     m0 = models[0]
     flags = [[p.trainable for p in mdl.parameters] + [mdl.inducing_variable.trainable] for mdl in models]
     if any(f != flags[0] for f in flags) or len(set(flags[0][:3])) != 1:
@@ -320,7 +321,8 @@ def adam_device(models, batch, max_iter: int, learning_rate: float = 0.001) -> b
     u0 = np.stack([np.concatenate([mdl.kernel.variance.unconstrained, mdl.likelihood.variance.unconstrained,
                                    mdl.kernel.lengthscales.unconstrained, np.asarray(mdl.inducing_variable.Z, np.float64).ravel()])
                    for mdl in models])
-    u, losses, iters = batch.adam(u0, n_ls, train_h, train_z, int(max_iter), learning_rate, JITTER, transform, prior is not None, floor)
+    u, losses, iters = batch.adam(u0, n_ls, train_h, train_z, int(max_iter), learning_rate, JITTER, transform, prior is not None, floor,
+                                  rule=rule)
     for b, mdl in enumerate(models):
         if train_h:
             mdl.kernel.variance.unconstrained = u[b, 0:1].copy()
@@ -400,17 +402,32 @@ def multi_start_device(model, rng, n_starts: int, iter_initial: int, starts, pic
 
 
 def fit_lockstep(models, method: str, max_iter: int = 100, device_trainer: bool = True) -> bool:
-    """Train all per-column sparse models together with the Adam-based recipes (``"adam"``, ``"two-stage"``).  Returns False
-    (nothing done) for other recipes.  ``device_trainer`` (default): models that qualify (``_device_batch``) are evaluated in one
-    batched pass and their Adam steps run on the device; otherwise every round enqueues one evaluation per model and the
-    update rule runs on the host (``adam_lockstep``)."""
-    from .gpr import _set_stage
+    """Train all per-column models together with the first-order recipes.  Returns False (nothing done) when a recipe cannot
+    run this way.  ``device_trainer`` (default): sparse models that qualify (``_device_batch``) are evaluated in one batched pass
+    and their update steps run on the device -- ``"adam"``, ``"two-stage"``, ``"adadelta"``, and the Adam stage of
+    ``"three-stage"`` (its two L-BFGS stages then run model by model).  Otherwise (``"adam"`` / ``"two-stage"`` only) every round
+    enqueues one evaluation per model and the update rule runs on the host (``adam_lockstep``)."""
+    from .gpr import _optimize_bfgs, _set_stage
 
-    if method not in ("adam", "two-stage") or not models:
+    if method not in ("adam", "two-stage", "adadelta", "three-stage") or not models:
         return False
     m0 = models[0]
     n, d = m0.x.shape
     batch = _device_batch(models) if device_trainer else None
+    if method in ("adadelta", "three-stage"):
+        if batch is None:
+            return False
+        if method == "adadelta":
+            return adam_device(models, batch, max_iter, rule="adadelta")
+        for mdl in models:  # gpr.py:130-144: Adam on Z (all models together), then L-BFGS on the hyperparameters, then on everything
+            _set_stage(mdl, hypers=False, z=True)
+        adam_device(models, batch, max_iter)
+        for mdl in models:
+            _set_stage(mdl, hypers=True, z=False)
+            _optimize_bfgs(mdl, max_iter)
+            _set_stage(mdl, hypers=True, z=True)
+            _optimize_bfgs(mdl, max_iter)
+        return True
     if batch is not None:
         if method == "adam":
             if adam_device(models, batch, max_iter):

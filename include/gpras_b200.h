@@ -134,6 +134,11 @@ int gpras_sgpr_batch_elbo_grad(gpras_sgpr_batch* h, const double* theta, const d
  * losses: max_iter x p out (NaN where a model had stopped; may be NULL); iters: p out, steps taken; info: p out. */
 int gpras_sgpr_batch_adam(gpras_sgpr_batch* h, double* u, int n_ls, int train_hypers, int train_z, int max_iter, double lr,
                           double jitter, int transform, int priors, double noise_floor, double* losses, int* iters, int* info);
+/* The same device-resident loop with the update rule as a parameter: 0 = Adam (as above), 1 = Keras Adadelta
+ * (_optimize_adadelta / _optimize_tf, gpr.py:176-192: exactly max_iter steps, no early stopping). */
+int gpras_sgpr_batch_train(gpras_sgpr_batch* h, double* u, int n_ls, int train_hypers, int train_z, int max_iter, double lr,
+                           double jitter, int transform, int priors, double noise_floor, int rule, double* losses, int* iters,
+                           int* info);
 /* predict_y (gpr.py:337) of all models in one pass per tile of test inputs (m <= 64, d <= 32; GPRAS_E_ARG otherwise):
  * condition at (theta p x (2 + d), z p x m x d) -> info p; then mean, var (t x p, noise included) for xs (t x d). */
 int gpras_sgpr_batch_condition(gpras_sgpr_batch* h, const double* theta, const double* z, double jitter, int* info);

@@ -170,10 +170,12 @@ def test_batch_rejects_what_it_cannot_hold(cuda):
 
 
 @pytest.mark.parametrize("method,ard,param", [("two-stage", False, "softplus"), ("adam", False, "softplus"), ("adam", True, "softplus"),
-                                              ("two-stage", True, "log")])
+                                              ("two-stage", True, "log"), ("adadelta", False, "softplus"), ("adadelta", True, "log"),
+                                              ("three-stage", False, "softplus")])
 def test_device_trainer_matches_oracle_backed_recipe(cuda, method, ard, param):
-    """The reference's default recipe on its default model family, all columns at once on the device, against the recipe run
-    model by model on the torch-oracle-backed double: hyperparameters and inducing inputs to 1e-6."""
+    """The reference's first-order recipes on its default model family, all columns at once on the device, against the recipe
+    run model by model on the torch-oracle-backed double: hyperparameters and inducing inputs to 1e-6 (three-stage, whose last
+    two stages are L-BFGS runs on the host: the north_star's 1e-4 for optima)."""
     from gpras_b200 import GPRAS, gpr
     from gpras_b200.synth import make_gp_data
     from test_host_cpu import OracleBackedSparseModel
@@ -181,15 +183,18 @@ def test_device_trainer_matches_oracle_backed_recipe(cuda, method, ard, param):
     data = make_gp_data(220, 3, 3, 0, seed=23)
     g = GPRAS("Matern32")
     g.fit(data.x, data.y, 9, "grid", method, max_iter=25, ard=ard, parameterisation=param)
-    assert all(mdl.n_evals == (50 if method == "two-stage" else 25) for mdl in g.models)
+    rtol = 1e-4 if method == "three-stage" else 1e-6
+    if method != "three-stage":
+        assert all(mdl.n_evals == (50 if method == "two-stage" else 25) for mdl in g.models)
+    assert all(hasattr(mdl, "adam_losses") for mdl in g.models)  # the device-resident loop ran
     z0 = g._create_inducing(data.x, 9, "grid")
     ls0 = np.full(3, np.mean(np.abs(data.x))) if ard else float(np.mean(np.abs(data.x)))
     for b, dev in enumerate(g.models):
         ref = OracleBackedSparseModel("Matern32", data.x, np.ascontiguousarray(data.y[:, b : b + 1]), z0.copy(), ls0, parameterisation=param)
         gpr.OPTIMIZERS[method](ref, max_iter=25)
-        np.testing.assert_allclose(dev.theta(), ref.theta(), rtol=1e-6)
+        np.testing.assert_allclose(dev.theta(), ref.theta(), rtol=rtol)
         zr = np.asarray(ref.inducing_variable.Z)
-        np.testing.assert_allclose(np.asarray(dev.inducing_variable.Z), zr, rtol=1e-6, atol=1e-6 * np.abs(zr).max())
+        np.testing.assert_allclose(np.asarray(dev.inducing_variable.Z), zr, rtol=rtol, atol=rtol * np.abs(zr).max())
         assert dev.inducing_variable.trainable and all(p.trainable for p in dev.parameters)
     mean, var = g.predict(data.x[:10])
     assert mean.shape == (10, 3) and np.all(var > 0)
