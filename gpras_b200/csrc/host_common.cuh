@@ -155,13 +155,16 @@ constexpr int SKINNY_MAX_SLABS = 16;
 constexpr int PANEL_GROUP = 4;    // Cholesky: trailing updates for groups of this many panels ...
 constexpr int PAIR_MIN_REM = 24;  // ... while more than this many block rows remain ...
 constexpr int TAIL_GROUP = 1;     // ... and of this many afterwards
+constexpr int BULK_L_RANK = 0;
 constexpr int WIDE_COL_REM = 32;  // the side stream's block-column update uses the 128x64 shape above this many remaining rows
 
 // ---- dense building blocks -------------------------------------------------------------------
 // Tunables of the Cholesky driver, read from the environment once per process (development sweeps).
 struct PotrfTuning {
   int group = PANEL_GROUP, min_rem = PAIR_MIN_REM, tail_group = TAIL_GROUP, wide_col_rem = WIDE_COL_REM;
+  int bulk_l_rank = BULK_L_RANK;  // bulk trailing updates of at least this rank use the 128 x 128 long-k shape (0: never)
   PotrfTuning() {
+    if (const char* e = getenv("GPRAS_B200_BULK_L_RANK")) bulk_l_rank = atoi(e);
     if (const char* e = getenv("GPRAS_B200_PANEL_GROUP")) group = atoi(e) > 0 ? atoi(e) : 1;
     if (const char* e = getenv("GPRAS_B200_PAIR_MIN_REM")) min_rem = atoi(e);
     if (const char* e = getenv("GPRAS_B200_TAIL_GROUP")) tail_group = atoi(e) > 0 ? atoi(e) : 1;
@@ -324,20 +327,21 @@ int potrf_impl(cudaStream_t s, LookAhead& la, double* A, long lda, double* W, lo
         const int next_g = (j + 1 < j_single) ? G : Gt;
         const int wa = next_g < rem - 1 ? next_g : rem - 1;  // its width in block columns
         TL(j, 0, s);
+        const bool bulk_l = potrf_tuning().bulk_l_rank > 0 && kp >= potrf_tuning().bulk_l_rank;
         {
           double* ahead = A + (long)(j + 2) * 128 * (lda + 1);
-          GemmDesc u = make_desc(pn2, lda, pn2, lda, ahead, lda, rem - 1, 2 * wa, kp);
+          GemmDesc u = make_desc(pn2, lda, pn2, lda, ahead, lda, rem - 1, bulk_l ? wa : 2 * wa, kp);
           u.alpha = -1.0, u.beta = 1.0;
-          if ((r = launch_gemm(s, false, false, u, 1, launches, SHAPE_S))) return r;
+          if ((r = launch_gemm(s, false, false, u, 1, launches, bulk_l ? SHAPE_L : SHAPE_S))) return r;
         }
         CU(cudaEventRecord(evAhead[j], s));
         last_bulk = j;
         if (rem - 1 > wa) {  // the rest: lower triangle from block column j+2+wa
           double* pn3 = pn2 + (long)wa * 128 * lda;
           double* trail = A + (long)(j + 2 + wa) * 128 * (lda + 1);
-          GemmDesc u = make_desc(pn3, lda, pn3, lda, trail, lda, rem - 1 - wa, 2 * (rem - 1 - wa), kp);
+          GemmDesc u = make_desc(pn3, lda, pn3, lda, trail, lda, rem - 1 - wa, (bulk_l ? 1 : 2) * (rem - 1 - wa), kp);
           u.tri = 1, u.alpha = -1.0, u.beta = 1.0;
-          if ((r = launch_gemm(s, false, false, u, 1, launches, SHAPE_S))) return r;
+          if ((r = launch_gemm(s, false, false, u, 1, launches, bulk_l ? SHAPE_L : SHAPE_S))) return r;
         }
         TL(j, 1, s);
       }

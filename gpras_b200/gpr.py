@@ -178,6 +178,9 @@ def release_pools() -> None:
         _, ent = _POOL_CACHE.popitem(last=False)
         for g in ent["gps"]:
             g.close()
+    from .sparse import release_batches
+
+    release_batches()
 
 
 class _DeviceSlot:

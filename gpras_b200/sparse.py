@@ -248,6 +248,18 @@ def adam_lockstep(models, max_iter: int, learning_rate: float = 0.001) -> None:
 _BATCH_POOL: dict = {}
 
 
+def _lib_errors():
+    from ._lib import GprasError
+
+    return (GprasError,)
+
+
+def release_batches() -> None:
+    """Close the pooled device batches of every thread (device memory goes back to the driver)."""
+    while _BATCH_POOL:
+        _BATCH_POOL.popitem()[1].close()
+
+
 def _device_batch(models):
     """A ``SparseBatch`` holding all of ``models`` when they qualify for the device-resident trainer (one target column each over
     the same inputs, the same kernel / transform / prior configuration, at most 128 inducing points), else None."""
@@ -269,7 +281,12 @@ def _device_batch(models):
     if key not in _BATCH_POOL:
         for old in [k for k in _BATCH_POOL if k[0] == key[0]]:  # one batch per thread: a new shape replaces the old arena
             _BATCH_POOL.pop(old).close()
-        _BATCH_POOL[key] = SparseBatch(m0.kernel.name, n, d, m, len(models), device=m0.device)
+        try:
+            _BATCH_POOL[key] = SparseBatch(m0.kernel.name, n, d, m, len(models), device=m0.device)
+        except _lib_errors() as exc:  # e.g. the arena of all models does not fit: one handle per model still works
+            if "cudaMalloc" not in str(exc):
+                raise
+            return None
     batch = _BATCH_POOL[key]
     owners = tuple(id(mdl) for mdl in models)
     if getattr(batch, "_owners", None) != owners:  # (a model's data never change after construction)
