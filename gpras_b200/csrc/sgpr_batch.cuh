@@ -54,6 +54,17 @@ struct gpras_sgpr_batch {
   double *Xsh = nullptr, *yv = nullptr, *yy = nullptr;
   double *xt = nullptr, *pmean = nullptr, *pvar = nullptr;  // prediction staging: test inputs, mean / variance (t x p)
   int pred_cap = 0;
+  // trainer: the models run as staggered lanes (consecutive groups of models, one stream each), so that one lane's
+  // one-CTA-per-model kernels overlap another lane's tile passes; a graph holds a chunk of consecutive steps of all lanes
+  static constexpr int MAX_LANES = 4;
+  cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};  // [0] is `stream`
+  cudaEvent_t ev_stagger[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr}, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  struct ChunkGraph {
+    SgprAdamCfg cfg;
+    int steps, lanes;
+    cudaGraphExec_t exec;
+  };
+  std::vector<ChunkGraph> chunk_graphs;
 };
 
 namespace gpras {
@@ -440,27 +451,61 @@ int sf_prepare(int kid) {
   return fail(GPRAS_E_ARG, "unknown kernel id");
 }
 
+// The models [model0, model0 + count) of the batch on stream s (a "lane"): every per-model pointer advanced by model0 strides.
+struct SfLane {
+  cudaStream_t s;
+  int model0, count;
+  cudaEvent_t after_forward;  // recorded behind the forward pass when not null (staggers the second lane)
+};
+
+SfArgs sf_shift(const SfArgs& a0, int model0) {
+  SfArgs a = a0;
+  const long o = (long)model0 * a0.bs;
+  a.yv += (long)model0 * a0.n_pad, a.yy += model0;
+  a.theta += o, a.Z += o, a.Zs += o, a.W += o, a.Ap += o, a.Kv += o, a.Fv += o, a.slabs += o, a.aep += o, a.aats += o, a.aes += o,
+      a.RW += o, a.WBg += o, a.uvec += o, a.scal += o, a.logdetB += o, a.partA += o, a.zpA += o, a.partB += o, a.zpB += o;
+  a.info += o * 2;
+  return a;
+}
+
 // cfg == nullptr: theta / Z in device memory -> result.  cfg != nullptr: one whole Adam step, u -> u (six launches).
 template <int KID>
-int sf_launch_t(gpras_sgpr_batch* h, const SfArgs& a, const SgprAdamCfg* cfg) {
-  cudaStream_t s = h->stream;
-  const int P = h->p;
+int sf_launch_t(gpras_sgpr_batch* h, const SfArgs& a0, const SgprAdamCfg* cfg, const SfLane& lane) {
+  cudaStream_t s = lane.s;
+  const int P = lane.count;
+  const SfArgs a = sf_shift(a0, lane.model0);
+  const long o = (long)lane.model0 * a0.bs;
   const int tile_smem = sf_tile_doubles(a.D, a.mp) * (int)sizeof(double);
   if (cfg)
-    sf_prep_train_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a, h->au, cfg->n_ls, cfg->transform, cfg->noise_floor);
+    sf_prep_train_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a, h->au + o, cfg->n_ls, cfg->transform, cfg->noise_floor);
   else
     sf_prep_kernel<KID><<<dim3(1, P), SF_THREADS, sf_prep_smem(a.D), s>>>(a);
   sf_forward_kernel<KID><<<dim3(a.ntn, P), SF_THREADS, tile_smem, s>>>(a);
+  if (lane.after_forward) CU(cudaEventRecord(lane.after_forward, s));
   sf_reduce_kernel<<<dim3((a.mp * a.mp + a.mp + SF_THREADS - 1) / SF_THREADS, P), SF_THREADS, 0, s>>>(a);
   sf_mid_kernel<KID><<<dim3(1, P), SF_THREADS, sf_mid_smem(a.D), s>>>(a);
   sf_backward_kernel<KID><<<dim3(a.ntn, P), SF_THREADS, tile_smem, s>>>(a);
   if (cfg)
-    sf_finish_train_kernel<<<dim3(1, P), SF_THREADS, 0, s>>>(a, h->result, h->au, h->amom, h->avel, h->ast, h->losses, P, *cfg);
+    sf_finish_train_kernel<<<dim3(1, P), SF_THREADS, 0, s>>>(a, h->result + o, h->au + o, h->amom + o, h->avel + o, h->ast + o,
+                                                            h->losses + lane.model0, h->p, *cfg);
   else
-    sf_finalize_kernel<<<dim3(1, P), SF_THREADS, 0, s>>>(a, h->result);
+    sf_finalize_kernel<<<dim3(1, P), SF_THREADS, 0, s>>>(a, h->result + o);
   h->launches += 6;
   CU(cudaGetLastError());
   return 0;
+}
+
+int sf_record_lane(gpras_sgpr_batch* h, double jitter, const SgprAdamCfg* cfg, const SfLane& lane) {
+  SfArgs a = h->fa;
+  a.jitter = jitter;
+  switch (h->kid) {
+    case K_RBF: return sf_launch_t<K_RBF>(h, a, cfg, lane);
+    case K_MATERN12: return sf_launch_t<K_MATERN12>(h, a, cfg, lane);
+    case K_MATERN32: return sf_launch_t<K_MATERN32>(h, a, cfg, lane);
+    case K_MATERN52: return sf_launch_t<K_MATERN52>(h, a, cfg, lane);
+    case K_EXPONENTIAL: return sf_launch_t<K_EXPONENTIAL>(h, a, cfg, lane);
+  }
+  return fail(GPRAS_E_ARG, "unknown kernel id");
 }
 
 // conditioning for prediction: the first four kernels of the evaluation (W, WB, u per model)
@@ -508,16 +553,7 @@ int sf_predict(gpras_sgpr_batch* h, int t) {
 }
 
 int sf_record_eval(gpras_sgpr_batch* h, double jitter, const SgprAdamCfg* cfg = nullptr) {
-  SfArgs a = h->fa;
-  a.jitter = jitter;
-  switch (h->kid) {
-    case K_RBF: return sf_launch_t<K_RBF>(h, a, cfg);
-    case K_MATERN12: return sf_launch_t<K_MATERN12>(h, a, cfg);
-    case K_MATERN32: return sf_launch_t<K_MATERN32>(h, a, cfg);
-    case K_MATERN52: return sf_launch_t<K_MATERN52>(h, a, cfg);
-    case K_EXPONENTIAL: return sf_launch_t<K_EXPONENTIAL>(h, a, cfg);
-  }
-  return fail(GPRAS_E_ARG, "unknown kernel id");
+  return sf_record_lane(h, jitter, cfg, SfLane{h->stream, 0, h->p, nullptr});
 }
 
 int sb_eval(gpras_sgpr_batch* h, double jitter) { return h->fused ? sf_record_eval(h, jitter) : sb_record_eval(h, jitter); }
@@ -621,6 +657,12 @@ int gpras_sgpr_batch_destroy(gpras_sgpr_batch* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& g : h->graphs)
     if (g.second) cudaGraphExecDestroy(g.second);
+  for (auto& g : h->chunk_graphs) cudaGraphExecDestroy(g.exec);
+  for (int l = 1; l < gpras_sgpr_batch::MAX_LANES; l++) {
+    if (h->ev_stagger[l]) cudaEventDestroy(h->ev_stagger[l]);
+    if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);
+    if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
+  }
   if (h->arena) cudaFree(h->arena);
   if (h->Xsh) cudaFree(h->Xsh);
   if (h->yv) cudaFree(h->yv);
@@ -734,6 +776,8 @@ int gpras_sgpr_batch_train(gpras_sgpr_batch* h, double* u, int n_ls, int train_h
     for (auto& g : h->graphs)  // the loss-history pointer is a captured kernel argument
       if (g.second) cudaGraphExecDestroy(g.second);
     h->graphs.clear();
+    for (auto& g : h->chunk_graphs) cudaGraphExecDestroy(g.exec);
+    h->chunk_graphs.clear();
     CU(cudaStreamSynchronize(s));
     if (h->losses) cudaFree(h->losses);
     h->losses = nullptr;
@@ -764,42 +808,119 @@ int gpras_sgpr_batch_train(gpras_sgpr_batch* h, double* u, int n_ls, int train_h
     if ((r = sb_eval(h, jitter))) return r;
     h->warmed = true;
   }
-  cudaGraphExec_t exec = nullptr;
-  for (auto& g : h->graphs)
-    if (g.first == cfg) exec = g.second;
-  if (!exec && max_iter > 0 && !getenv("GPRAS_B200_NO_GRAPHS")) {
-    cudaGraph_t graph = nullptr;
-    h->launches = 0;
-    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    r = record_step();
-    cudaError_t e = cudaStreamEndCapture(s, &graph);
-    if (r == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
-    if (graph) cudaGraphDestroy(graph);
-    if (r != 0 || e != cudaSuccess || !exec) {
-      cudaGetLastError();
-      exec = nullptr;  // eager launches below (still the CUDA path)
-    } else {
-      if (h->graphs.size() >= 8) {
-        cudaGraphExecDestroy(h->graphs.front().second);
-        h->graphs.erase(h->graphs.begin());
-      }
-      h->graphs.emplace_back(cfg, exec);
-    }
-  }
   double* h_st = h->h_pinned + (size_t)P * h->nu;
-  for (int it = 0; it < max_iter; it++) {
-    if (exec)
-      CU(cudaGraphLaunch(exec, s));
-    else {
+  auto all_stopped = [&](bool* stopped) -> int {  // has every model stopped early?
+    CU(cudaMemcpy2DAsync(h_st, sizeof(double) * gpras::AST, h->ast, pitch, sizeof(double) * gpras::AST, P, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    bool any = false;
+    for (int b = 0; b < P; b++) any = any || h_st[(size_t)b * gpras::AST + 2] != 0.0;
+    *stopped = !any;
+    return 0;
+  };
+  const bool use_graphs = !getenv("GPRAS_B200_NO_GRAPHS");
+  if (h->fused && use_graphs && max_iter > 0) {
+    // Fused path: graphs of up to CHUNK consecutive steps.  With four or more models the batch runs as two lanes (halves of the
+    // models on two streams, the second lane starting behind the first lane's first forward pass): one lane's one-CTA-per-model
+    // kernels (Cholesky chains of prep / mid) then overlap the other lane's tile passes, and each tile pass is a single wave.
+    constexpr int CHUNK = 25;
+    int lanes = P >= 4 ? 2 : 1;
+    if (const char* e = getenv("GPRAS_B200_SGPR_LANES")) lanes = atoi(e);
+    if (lanes > gpras_sgpr_batch::MAX_LANES) lanes = gpras_sgpr_batch::MAX_LANES;
+    if (lanes > P) lanes = P;
+    if (lanes < 1) lanes = 1;
+    h->lane_stream[0] = s;
+    for (int l = 1; l < lanes; l++)
+      if (!h->lane_stream[l]) {
+        CU(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_stagger[l], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_join[l], cudaEventDisableTiming));
+      }
+    auto chunk_graph = [&](int steps, cudaGraphExec_t* out) -> int {
+      for (auto& g : h->chunk_graphs)
+        if (g.cfg == cfg && g.steps == steps && g.lanes == lanes) {
+          *out = g.exec;
+          return 0;
+        }
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
       h->launches = 0;
-      if ((r = record_step())) return r;
+      CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rr = 0;
+      for (int it = 0; it < steps && rr == 0; it++) {
+        for (int l = 0; l < lanes && rr == 0; l++) {  // lane l: models [l P / lanes, (l + 1) P / lanes)
+          const int m0 = (int)((long)l * P / lanes), m1 = (int)((long)(l + 1) * P / lanes);
+          // lane l + 1 starts behind lane l's first forward pass
+          cudaEvent_t after = (it == 0 && l + 1 < lanes) ? h->ev_stagger[l + 1] : nullptr;
+          if (it == 0 && l > 0 && cudaStreamWaitEvent(h->lane_stream[l], h->ev_stagger[l], 0) != cudaSuccess) rr = GPRAS_E_CUDA;
+          if (rr == 0) rr = sf_record_lane(h, jitter, &cfg, SfLane{h->lane_stream[l], m0, m1 - m0, after});
+        }
+      }
+      for (int l = 1; l < lanes && rr == 0; l++)
+        if (cudaEventRecord(h->ev_join[l], h->lane_stream[l]) != cudaSuccess || cudaStreamWaitEvent(s, h->ev_join[l], 0) != cudaSuccess)
+          rr = GPRAS_E_CUDA;
+      cudaError_t e = cudaStreamEndCapture(s, &graph);
+      if (rr == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (rr != 0 || e != cudaSuccess || !exec) {
+        cudaGetLastError();
+        return fail(GPRAS_E_CUDA, "capturing the trainer's graph failed", e);
+      }
+      h->launches /= steps;  // launches of one step (all lanes)
+      if (h->chunk_graphs.size() >= 8) {
+        cudaGraphExecDestroy(h->chunk_graphs.front().exec);
+        h->chunk_graphs.erase(h->chunk_graphs.begin());
+      }
+      h->chunk_graphs.push_back({cfg, steps, lanes, exec});
+      *out = exec;
+      return 0;
+    };
+    for (int done = 0; done < max_iter;) {
+      const int steps = max_iter - done < CHUNK ? max_iter - done : CHUNK;
+      cudaGraphExec_t exec = nullptr;
+      if ((r = chunk_graph(steps, &exec))) return r;
+      CU(cudaGraphLaunch(exec, s));
+      done += steps;
+      if (done < max_iter && rule == 0) {
+        bool stopped = false;
+        if ((r = all_stopped(&stopped))) return r;
+        if (stopped) break;
+      }
     }
-    if ((it + 1) % 32 == 0 && it + 1 < max_iter) {  // has every model stopped early?
-      CU(cudaMemcpy2DAsync(h_st, sizeof(double) * gpras::AST, h->ast, pitch, sizeof(double) * gpras::AST, P, cudaMemcpyDeviceToHost, s));
-      CU(cudaStreamSynchronize(s));
-      bool any = false;
-      for (int b = 0; b < P; b++) any = any || h_st[(size_t)b * gpras::AST + 2] != 0.0;
-      if (!any) break;
+  } else {
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : h->graphs)
+      if (g.first == cfg) exec = g.second;
+    if (!exec && max_iter > 0 && use_graphs) {
+      cudaGraph_t graph = nullptr;
+      h->launches = 0;
+      CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      r = record_step();
+      cudaError_t e = cudaStreamEndCapture(s, &graph);
+      if (r == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (r != 0 || e != cudaSuccess || !exec) {
+        cudaGetLastError();
+        exec = nullptr;  // eager launches below (still the CUDA path)
+      } else {
+        if (h->graphs.size() >= 8) {
+          cudaGraphExecDestroy(h->graphs.front().second);
+          h->graphs.erase(h->graphs.begin());
+        }
+        h->graphs.emplace_back(cfg, exec);
+      }
+    }
+    for (int it = 0; it < max_iter; it++) {
+      if (exec)
+        CU(cudaGraphLaunch(exec, s));
+      else {
+        h->launches = 0;
+        if ((r = record_step())) return r;
+      }
+      if ((it + 1) % 32 == 0 && it + 1 < max_iter) {
+        bool stopped = false;
+        if ((r = all_stopped(&stopped))) return r;
+        if (stopped) break;
+      }
     }
   }
   CU(cudaMemcpy2DAsync(h->h_pinned, sizeof(double) * nu, h->au, pitch, sizeof(double) * nu, P, cudaMemcpyDeviceToHost, s));

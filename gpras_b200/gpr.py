@@ -955,11 +955,15 @@ class GPRAS:
         return len(self.models) * per <= self.PREDICT_HANDLE_BUDGET_BYTES
 
     def release(self) -> None:
-        """Give the per-model prediction handles back (device memory)."""
+        """Give the per-model prediction handles and the device batch of these models back (device memory)."""
         for m in self.models:
             rel = getattr(m, "release", None)
             if rel is not None:
                 rel()
+        if self.models and not (self._opts or {}).get("exact", False):
+            from .sparse import release_batches
+
+            release_batches(self.models)
 
     def predict_std(self, x: NDArray[Any]) -> tuple[NDArray[Any], NDArray[Any]]:
         """Explicit extra: (mean, std); callers of the reference take ``np.sqrt`` themselves (pipeline.py:262-263)."""

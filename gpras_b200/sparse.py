@@ -254,10 +254,14 @@ def _lib_errors():
     return (GprasError,)
 
 
-def release_batches() -> None:
-    """Close the pooled device batches of every thread (device memory goes back to the driver)."""
-    while _BATCH_POOL:
-        _BATCH_POOL.popitem()[1].close()
+def release_batches(models=None) -> None:
+    """Close the pooled device batches of every thread (device memory goes back to the driver); with ``models`` only the
+    batches that currently hold those models."""
+    ids = None if models is None else {id(m) for m in models}
+    for key in list(_BATCH_POOL):
+        batch = _BATCH_POOL[key]
+        if ids is None or ids & set(getattr(batch, "_owners", None) or ()):
+            _BATCH_POOL.pop(key).close()
 
 
 def _device_batch(models):
