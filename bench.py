@@ -614,7 +614,7 @@ def run_ours(args) -> None:
                                   "grid inducing inputs",
                       "seconds": secs, "model_steps": steps_, "device_trainer_us_per_lockstep_iteration": secs["device_trainer"] / 200 * 1e6,
                       "speedup_vs_sequential": secs["sequential"] / secs["device_trainer"],
-                      "max_rel_diff_of_fitted_parameters_vs_sequential": err, "launches_per_iteration": 6}
+                      "max_rel_diff_of_fitted_parameters_vs_sequential": err, "launches_per_iteration": "6 per lane of models (two staggered lanes when there are four or more models)"}
         if world == 1 and not args.no_cpu_baseline:
             import torch as _t
 
