@@ -60,15 +60,25 @@ struct SfArgs {
 
 // ---- in-CTA dense helpers on mp x mp shared-memory matrices (pitch SF_LD), 256 threads --------------------------------
 
-// L = chol(A) (lower; A's lower triangle is consumed), rs[j] = 1 / L_jj.  Right-looking with 8-column panels: every thread
-// factors the 8 x 8 diagonal block redundantly in registers (no broadcast, no barrier), one thread per row solves the panel
-// below it, then the trailing triangle takes the rank-8 update on a 16 x 16 thread grid: two barriers per panel.  A
-// non-positive pivot records info = column + 1 (LAPACK convention) and continues with a unit pivot.  Ends with a barrier.
-__device__ __forceinline__ void sf_chol(double* __restrict__ A, double* __restrict__ L, double* __restrict__ rs, int mp,
-                                        int* __restrict__ info) {
+// Cholesky factor AND its inverse in one sweep: A = L L^T (lower triangle of A consumed), Wm = L^-1 (lower triangular, zeros
+// above the diagonal), rs[j] = 1 / L_jj.  Right-looking with 8-column panels; Wm starts as the identity and is carried along as
+// a right-hand side (block forward substitution L X = I), so the inverse costs no extra pass and no extra barrier:
+//   per panel J   every thread factors the 8 x 8 diagonal block redundantly in registers (no broadcast, no barrier);
+//                 one thread per row below solves the panel  L_iJ = A_iJ L_JJ^-T  (kept in the panel buffer Lp only: later
+//                 panels never read earlier columns of L), one thread per column solves  X_J = L_JJ^-1 R_J;      -- barrier --
+//                 rank-8 updates of the trailing triangle of A and of the remaining right-hand-side rows
+//                 R_i -= L_iJ X_J  on a 16 x 16 thread grid.                                                        -- barrier --
+// A non-positive pivot records info = column + 1 (LAPACK convention) and continues with a unit pivot.  Ends with a barrier.
+constexpr int SF_LP = 9;  // pitch of the panel buffer [SF_MP][8]
+__device__ __forceinline__ void sf_chol_inv(double* __restrict__ A, double* __restrict__ Lp, double* __restrict__ Wm,
+                                            double* __restrict__ rs, int mp, int* __restrict__ info) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int e = tid; e < mp * mp; e += SF_THREADS) {
+    const int i = e / mp, j = e - i * mp;
+    Wm[i * SF_LD + j] = i == j ? 1.0 : 0.0;
+  }
   for (int j0 = 0; j0 < mp; j0 += 8) {
-    __syncthreads();  // the trailing update of the previous panel is complete
+    __syncthreads();  // the updates of the previous panel are complete (first pass: A and the identity are in place)
     double Dg[8][8], rsv[8];
 #pragma unroll
     for (int r = 0; r < 8; r++)
@@ -91,16 +101,12 @@ __device__ __forceinline__ void sf_chol(double* __restrict__ A, double* __restri
 #pragma unroll
         for (int r = c2; r < 8; r++) Dg[r][c2] -= Dg[r][c] * Dg[c2][c];
     }
-    const int i = j0 + tid;
+    const int i = j0 + tid, cx = tid - 128;
     if (tid < 8) {
 #pragma unroll
       for (int r = 0; r < 8; r++)
-        if (tid == r) {
-#pragma unroll
-          for (int c = 0; c <= r; c++) L[i * SF_LD + j0 + c] = Dg[r][c];
-          rs[i] = rsv[r];
-        }
-    } else if (i < mp) {  // x = a L_JJ^-T
+        if (tid == r) rs[i] = rsv[r];
+    } else if (i < mp) {  // L_iJ = a L_JJ^-T
       double v[8];
 #pragma unroll
       for (int c = 0; c < 8; c++) v[c] = A[i * SF_LD + j0 + c];
@@ -112,83 +118,39 @@ __device__ __forceinline__ void sf_chol(double* __restrict__ A, double* __restri
         v[c] = sacc * rsv[c];
       }
 #pragma unroll
-      for (int c = 0; c < 8; c++) L[i * SF_LD + j0 + c] = v[c];
+      for (int c = 0; c < 8; c++) Lp[i * SF_LP + c] = v[c];
+    } else if (cx >= 0 && cx < j0 + 8) {  // column cx of X_J = L_JJ^-1 R_J
+      double x[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) x[r] = Wm[(j0 + r) * SF_LD + cx];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        double sacc = x[r];
+#pragma unroll
+        for (int r1 = 0; r1 < r; r1++) sacc = fma(-Dg[r][r1], x[r1], sacc);
+        x[r] = sacc * rsv[r];
+      }
+#pragma unroll
+      for (int r = 0; r < 8; r++) Wm[(j0 + r) * SF_LD + cx] = x[r];
     }
     __syncthreads();
     for (int ii = j0 + 8 + ty; ii < mp; ii += 16) {
       double li[8];
 #pragma unroll
-      for (int c = 0; c < 8; c++) li[c] = L[ii * SF_LD + j0 + c];
+      for (int c = 0; c < 8; c++) li[c] = Lp[ii * SF_LP + c];
       for (int k = j0 + 8 + tx; k <= ii; k += 16) {
         double sacc = A[ii * SF_LD + k];
 #pragma unroll
-        for (int c = 0; c < 8; c++) sacc = fma(-li[c], L[k * SF_LD + j0 + c], sacc);
+        for (int c = 0; c < 8; c++) sacc = fma(-li[c], Lp[k * SF_LP + c], sacc);
         A[ii * SF_LD + k] = sacc;
       }
-    }
-  }
-  __syncthreads();
-}
-
-// Wm = L^-1 (lower triangular, zeros above the diagonal; rs[j] = 1 / L_jj from sf_chol): the 8 x 8 diagonal blocks are
-// inverted by one thread each in registers, then recursive doubling -- for adjacent diagonal blocks of size b,
-// W21 = -W22 (L21 W11) -- with every entry of a level computed in parallel (T = L21 W11 is parked transposed in the unused
-// upper triangle of Wm).  Ends with a barrier.
-__device__ __forceinline__ void sf_trinv(const double* __restrict__ L, const double* __restrict__ rs, double* __restrict__ Wm,
-                                         int mp) {
-  const int tid = threadIdx.x;
-  if (tid < (mp >> 3)) {
-    const int j0 = 8 * tid;
-    double Lb[8][8], X[8][8], rsv[8];
+      for (int cc = tx; cc < j0 + 8; cc += 16) {
+        double sacc = Wm[ii * SF_LD + cc];
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      rsv[r] = rs[j0 + r];
-#pragma unroll
-      for (int c = 0; c < r; c++) Lb[r][c] = L[(j0 + r) * SF_LD + j0 + c];
-    }
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-      X[c][c] = rsv[c];
-#pragma unroll
-      for (int r = c + 1; r < 8; r++) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int k = c; k < r; k++) sacc = fma(Lb[r][k], X[k][c], sacc);
-        X[r][c] = -sacc * rsv[r];
+        for (int r = 0; r < 8; r++) sacc = fma(-li[r], Wm[(j0 + r) * SF_LD + cc], sacc);
+        Wm[ii * SF_LD + cc] = sacc;
       }
     }
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-#pragma unroll
-      for (int c = 0; c <= r; c++) Wm[(j0 + r) * SF_LD + j0 + c] = X[r][c];
-  }
-  __syncthreads();
-  for (int b = 8; b < mp; b <<= 1) {
-    const int npairs = (mp + 2 * b - 1) / (2 * b), bb = b * b, total = npairs * bb;
-    for (int e = tid; e < total; e += SF_THREADS) {  // T[i][j] = sum_k L[i][k] W[k][j], k in the first block, k >= j
-      const int pr = e / bb, rem = e - pr * bb, ii = rem / b, jj = rem - ii * b;
-      const int r0 = pr * 2 * b, i = r0 + b + ii, j = r0 + jj;
-      if (i < mp) {
-        double sacc = 0.0;
-        for (int k = j; k < r0 + b; k++) sacc = fma(L[i * SF_LD + k], Wm[k * SF_LD + j], sacc);
-        Wm[j * SF_LD + i] = sacc;
-      }
-    }
-    __syncthreads();
-    for (int e = tid; e < total; e += SF_THREADS) {  // W[i][j] = -sum_k W[i][k] T[k][j], k in the second block, k <= i
-      const int pr = e / bb, rem = e - pr * bb, ii = rem / b, jj = rem - ii * b;
-      const int r0 = pr * 2 * b, i = r0 + b + ii, j = r0 + jj;
-      if (i < mp) {
-        double sacc = 0.0;
-        for (int k = r0 + b; k <= i; k++) sacc = fma(Wm[i * SF_LD + k], Wm[j * SF_LD + k], sacc);
-        Wm[i * SF_LD + j] = -sacc;
-      }
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < mp * mp; e += SF_THREADS) {
-    const int i = e / mp, j = e - i * mp;
-    if (j > i) Wm[i * SF_LD + j] = 0.0;
   }
   __syncthreads();
 }
@@ -250,7 +212,7 @@ template <int KID>
 __device__ __forceinline__ void sf_prep_body(const SfArgs& a) {
   extern __shared__ __align__(16) double smem[];
   double* SA = smem;             // Kuu
-  double* SL = SA + SF_MAT;      // L
+  double* SL = SA + SF_MAT;      // panel buffer of the factorisation
   double* SWm = SL + SF_MAT;     // W
   double* zs = SWm + SF_MAT;     // [mp][D]
   double* rs = zs + SF_MP * a.D;
@@ -284,8 +246,7 @@ __device__ __forceinline__ void sf_prep_body(const SfArgs& a) {
       if (i >= m || j >= m) k = i == j ? 1.0 : 0.0;
       SA[i * SF_LD + j] = k;
     }
-  sf_chol(SA, SL, rs, mp, info);
-  sf_trinv(SL, rs, SWm, mp);
+  sf_chol_inv(SA, SL, SWm, rs, mp, info);  // (SL serves as the panel buffer)
   double* Wg = a.W + off;
   for (int e = tid; e < mp * mp; e += SF_THREADS) {
     const int i = e / mp, j = e - i * mp;
@@ -471,7 +432,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
   double* SW = smem;            // W = L^-1
   double* SA = SW + SF_MAT;     // AATs -> RA -> Guu
   double* SB = SA + SF_MAT;     // B -> WB -> Rm -> T1
-  double* SL = SB + SF_MAT;     // LB -> Binv -> RW
+  double* SL = SB + SF_MAT;     // WB (swapped into SB after the factorisation) -> Binv -> RW
   double* zs = SL + SF_MAT;     // [mp][D]
   double* ae = zs + SF_MP * a.D;
   double* cv = ae + SF_MP;
@@ -497,9 +458,14 @@ __global__ void __launch_bounds__(SF_THREADS, 1) sf_mid_kernel(const SfArgs a) {
     SB[i * SF_LD + j] = sv + (i == j ? 1.0 : 0.0);
   }
   if (tid < mp) ae[tid] = (a.aes + off)[tid] / s2;
-  // LB = chol(B), WB = LB^-1 (into SB), log det
-  sf_chol(SB, SL, rs, mp, info);
-  sf_trinv(SL, rs, SB, mp);
+  // LB = chol(B) and WB = LB^-1 in one sweep (B in SB is consumed, WB lands in SL; `red` is the panel buffer), log det.
+  // The two buffers then swap names: below, SB holds WB and SL is free, as the comments at their declarations say.
+  sf_chol_inv(SB, red, SL, rs, mp, info);
+  {
+    double* t_ = SB;
+    SB = SL;
+    SL = t_;
+  }
   if (tid < 64) {
     double lg = tid < mp ? -log(rs[tid]) : 0.0;
     lg = warp_sum(lg);
