@@ -818,6 +818,7 @@ int gpras_sgpr_batch_train(gpras_sgpr_batch* h, double* u, int n_ls, int train_h
     return 0;
   };
   const bool use_graphs = !getenv("GPRAS_B200_NO_GRAPHS");
+  bool chunked_done = false;
   if (h->fused && use_graphs && max_iter > 0) {
     // Fused path: graphs of up to CHUNK consecutive steps.  With four or more models the batch runs as two lanes (halves of the
     // models on two streams, the second lane starting behind the first lane's first forward pass): one lane's one-CTA-per-model
@@ -874,10 +875,15 @@ int gpras_sgpr_batch_train(gpras_sgpr_batch* h, double* u, int n_ls, int train_h
       *out = exec;
       return 0;
     };
+    chunked_done = true;
     for (int done = 0; done < max_iter;) {
       const int steps = max_iter - done < CHUNK ? max_iter - done : CHUNK;
       cudaGraphExec_t exec = nullptr;
-      if ((r = chunk_graph(steps, &exec))) return r;
+      if ((r = chunk_graph(steps, &exec))) {
+        if (done > 0) return r;
+        chunked_done = false;  // nothing has run yet: eager launches below (still the CUDA path, never a CPU one)
+        break;
+      }
       CU(cudaGraphLaunch(exec, s));
       done += steps;
       if (done < max_iter && rule == 0) {
@@ -886,11 +892,12 @@ int gpras_sgpr_batch_train(gpras_sgpr_batch* h, double* u, int n_ls, int train_h
         if (stopped) break;
       }
     }
-  } else {
+  }
+  if (!chunked_done) {
     cudaGraphExec_t exec = nullptr;
     for (auto& g : h->graphs)
       if (g.first == cfg) exec = g.second;
-    if (!exec && max_iter > 0 && use_graphs) {
+    if (!exec && max_iter > 0 && use_graphs && !h->fused) {
       cudaGraph_t graph = nullptr;
       h->launches = 0;
       CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
