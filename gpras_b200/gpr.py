@@ -758,7 +758,7 @@ class GPRAS:
         initial_theta: NDArray[Any] | None = None,
         restarts: NDArray[Any] | None = None,
         restart_lanes: int | None = None,
-        kmeans_on_device: bool = False,
+        kmeans_on_device: bool = True,
         n_jobs: int = 1,
         lockstep_models: bool = True,
         device_trainer: bool = True,
@@ -776,7 +776,9 @@ class GPRAS:
         start points, column order [variance, noise, lengthscale(s)]) runs the recipe from every start and keeps
         the lowest final loss (handed out to ranks by a ticket counter when ``torch.distributed`` is initialised;
         ``restart_lanes`` restarts in flight per GPU, default 2 for exact models above 4096 rows, else 1);
-        ``kmeans_on_device`` runs the Lloyd iterations of the "kmeans" initialiser on the GPU; ``n_jobs > 1``
+        ``kmeans_on_device`` (default on) runs the Lloyd iterations of the "kmeans" initialiser on the GPU from scikit-learn's own
+        k-means++ seeds (same iteration count, labels and inertia as ``KMeans(random_state=0, n_init="auto")``, centres to 1e-15;
+        ``False`` calls scikit-learn's ``KMeans`` itself, as the reference does); ``n_jobs > 1``
         optimises that many per-column models concurrently on the GPU (host threads, one device handle each; the
         reference loops sequentially, ``gpr.py:273-274``, and so does the default).  Under ``torch.distributed`` (one
         process per GPU) per-column models are sharded round-robin over ranks and their parameters all-gathered.
