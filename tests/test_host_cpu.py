@@ -339,3 +339,66 @@ def test_run_restarts_lanes_match_single_lane():
         assert m.n_evals > 0
     np.testing.assert_array_equal(tabs[0], tabs[1])
     np.testing.assert_array_equal(tabs[0], tabs[2])
+
+
+def test_fit_routes_first_order_recipes_of_sparse_models_to_the_batched_trainer(monkeypatch):
+    """Host logic of ``GPRAS.fit`` (no device needed): which calls go to ``sparse.fit_lockstep`` (all per-column models together),
+    with which options, and what happens when it declines."""
+    from gpras_b200 import sparse as sp
+
+    data = make_gp_data(60, 3, 4, seed=1)
+    calls, sequential = [], []
+
+    def fake_lockstep(models, method, max_iter=100, device_trainer=True):
+        calls.append((len(models), method, max_iter, device_trainer))
+        return method != "adadelta"  # decline one recipe: fit must then run it model by model
+
+    monkeypatch.setattr(sp, "fit_lockstep", fake_lockstep)
+    for name in list(gpr.OPTIMIZERS):
+        monkeypatch.setitem(gpr.OPTIMIZERS, name, lambda model, _n=name, **kw: sequential.append((_n, kw)))
+
+    def run(method, **kw):
+        calls.clear()
+        sequential.clear()
+        g = gpr.GPRAS("Matern32")
+        g.fit(data.x, data.y, 7, "grid", method, **kw)
+        return list(calls), list(sequential)
+
+    c, s_ = run("two-stage")
+    assert c == [(4, "two-stage", 100, True)] and not s_
+    c, s_ = run("adam", max_iter=12)
+    assert c == [(4, "adam", 12, True)] and not s_
+    c, s_ = run("three-stage", max_iter=9)
+    assert c == [(4, "three-stage", 9, True)] and not s_
+    c, s_ = run("adadelta", max_iter=5)  # declined -> sequential loop over the four models
+    assert c == [(4, "adadelta", 5, True)] and s_ == [("adadelta", {"max_iter": 5})] * 4
+    c, s_ = run("adam")  # no max_iter: the reference's _optimize_adam has no default either -> the recipe itself is called
+    assert not c and len(s_) == 4
+    c, s_ = run("L-BFGS-B", max_iter=10)
+    assert not c and s_ == [("L-BFGS-B", {"max_iter": 10})] * 4
+    c, s_ = run("two-stage", lockstep_models=False)
+    assert not c and len(s_) == 4
+    c, s_ = run("adadelta", max_iter=5, device_trainer=False)  # host lock-step knows Adam only
+    assert not c and len(s_) == 4
+    c, s_ = run("two-stage", device_trainer=False)
+    assert c == [(4, "two-stage", 100, False)] and not s_
+    c, s_ = run("two-stage", n_jobs=2)
+    assert not c and len(s_) == 4
+
+
+def test_sparse_models_qualify_for_a_device_batch_only_when_configured_alike():
+    from gpras_b200 import sparse as sp
+
+    data = make_gp_data(40, 2, 3, seed=2)
+    z = data.x[:6].copy()
+    mk = lambda j, **kw: sp.SparseModel("RBF", data.x, np.ascontiguousarray(data.y[:, j : j + 1]), z.copy(), 1.0, **kw)  # noqa: E731
+    a, b = mk(0), mk(1)
+    assert sp._trainer_config(a) == ("RBF", "softplus", "LogNormal(0,1)", gpr.NOISE_FLOOR, 1) == sp._trainer_config(b)
+    assert sp._trainer_config(mk(0, priors=False))[2] is None
+    assert sp._trainer_config(mk(0, parameterisation="log"))[1:4] == ("log", "LogNormal(0,1)", 0.0)
+    a.kernel.variance.prior = None  # mixed prior settings: the device trainer applies one setting to all three hyperparameters
+    assert sp._trainer_config(a) is None
+    # test doubles never join a device batch; neither do models that differ in configuration (checked before any device call)
+    assert sp._device_batch([OracleBackedSparseModel("RBF", data.x, data.y[:, :1], z.copy(), 1.0)]) is None
+    assert sp._device_batch([mk(0), mk(1, parameterisation="log")]) is None
+    assert sp._device_batch([mk(0), sp.SparseModel("RBF", data.x, np.ascontiguousarray(data.y[:, 1:2]), z[:5].copy(), 1.0)]) is None
