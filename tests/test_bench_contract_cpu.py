@@ -13,7 +13,7 @@ REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
 
 
 @pytest.mark.parametrize("name", ["r01/bench_1gpu_final.json", "r01/bench_2gpu_final.json", "r01/bench_8gpu_final.json",
-                                  "r02/bench_1gpu_final.json", "r02/bench_2gpu_dev.json"])
+                                  "r02/bench_1gpu_final.json", "r02/bench_2gpu_dev.json", "r02/bench_2gpu_final.json"])
 def test_committed_bench_lines_follow_the_contract(name):
     d = json.loads((ROOT / "profiles" / name).read_text().strip().splitlines()[-1])
     for k in REQUIRED:
@@ -56,6 +56,21 @@ def test_round2_bench_line_is_job_level_and_both_arms_share_the_config():
         assert ours[k] is not None, k
     assert ours["strong"]["scaling"] == "strong" and ours["cfg5_sweep"]["scaling"] == "strong"
     assert ref["steps"] <= 3 and ref["steps_requested"] >= ref["steps"]
+
+
+def test_round2_bench_line_carries_the_sparse_family_and_the_large_transform():
+    """The reference's default model family (per-column sparse models) is timed through ``GPRAS.fit`` itself, against the
+    host-driven loops of the same device evaluation and with the fitted parameters compared; one-rank runs only (under
+    torch.distributed ``fit`` shards the models over ranks)."""
+    ours = json.loads((ROOT / "profiles" / "r02" / "bench_1gpu_final.json").read_text().strip().splitlines()[-1])
+    sf = ours["sparse_fit"]
+    assert set(sf["seconds"]) == {"device_trainer", "host_lockstep", "sequential"}
+    assert sf["seconds"]["device_trainer"] < sf["seconds"]["host_lockstep"] < sf["seconds"]["sequential"]
+    assert sf["max_rel_diff_of_fitted_parameters_vs_sequential"] < 1e-8
+    big = ours["preprocess"]["cfg3_cells"]["modes_16"]
+    assert 0.0 < big["transform_hbm_frac"] < 1.0 and abs(big["transform_GBps"] / 6543.7 - big["transform_hbm_frac"]) < 1e-9
+    two = json.loads((ROOT / "profiles" / "r02" / "bench_2gpu_final.json").read_text().strip().splitlines()[-1])
+    assert two["n_gpus"] == 2 and two["sparse_fit"] is None and two["strong"]["scaling"] == "strong"
 
 
 def test_bench_ncu_figures_come_from_profiles():
